@@ -1,0 +1,217 @@
+/*
+ * plonk_b200.h -- C ABI of the B200-native batched prove/verify path of plonk.c.
+ *
+ * The reference (kazuakiishiguro/plonk.c) has no FFI: its API is ten headers that define their
+ * functions in place (src/hf.h ... src/plonk.h) and are #included into one translation unit.
+ * This library is the batched equivalent of those functions.  Every entry point below names the
+ * reference function whose per-item result it reproduces byte for byte; the drop-in scalar headers
+ * in this directory (hf.h gf.h poly.h matrix.h g1.h g2.h gt.h pairing.h srs.h constraints.h plonk.h)
+ * route the reference's heavyweight functions through these entry points at batch size 1.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all data are bytes (one field element per byte, canonical
+ *    residues: F17 values in [0,17), F101 values in [0,101)) unless stated otherwise.
+ *  - G1 is the reference's struct {GF x; GF y; bool infinite} = 3 bytes (g1.h:8-11), G2 is
+ *    {GF x; GF y} = 2 bytes (g2.h:7-9), GTP is {GF a; GF b} = 2 bytes (gt.h:7-9), PROOF is 34 bytes
+ *    (plonk.h:24-41), CHALLENGE is 5 bytes (plonk.h:16-22).  Batches are arrays of these structs.
+ *  - `*_dev` entry points take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
+ *    void*, NULL = default stream) without synchronising.  The entry points without the suffix take
+ *    HOST pointers, copy in, run, copy out and synchronise.
+ *  - return value: 0 on success, negative pb_status on failure (pb_last_error() has the text).
+ *    There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    PB_ERR_NO_DEVICE.
+ *  - where the reference would exit() or abort() on an item, the batch entry point writes a per-item
+ *    status byte instead (SURVEY.md Appendix B numbering for plonk_prove) and zero-fills the item.
+ */
+#ifndef PLONK_B200_H
+#define PLONK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PB_OK = 0,
+  PB_ERR_NO_DEVICE = -1, /* no CUDA device / driver: the product path refuses to run */
+  PB_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  PB_ERR_ARG = -3        /* invalid argument (null pointer, unsupported size, malformed circuit) */
+} pb_status;
+
+/* per-item status of pb_plonk_prove*: the SURVEY.md Appendix-B row of the first reference exit that
+ * fires, in the reference's execution order.  0 = the reference returns a PROOF. */
+enum {
+  PB_PROVE_OK = 0,
+  PB_PROVE_UNSATISFIED = 1,     /* assert(constraints_satisfy) plonk.h:231                        */
+  PB_PROVE_BAD_COPY_TYPE = 3,   /* "Invalid copy_of type" plonk.h:155-157                         */
+  PB_PROVE_SRS_ABC = 5,         /* a/b/c longer than the SRS: srs.h:54-57 via plonk.h:299-301     */
+  PB_PROVE_ACC_ASSERT = 6,      /* assert(acc_x(omega^n) == 1) plonk.h:368                        */
+  PB_PROVE_SRS_Z = 7,           /* z longer than the SRS: plonk.h:379                             */
+  PB_PROVE_REMAINDER = 8,       /* "Non-zero remainder in t(x) division" plonk.h:507-510          */
+  PB_PROVE_SLICE = 9,           /* "Invalid slice indices" poly.h:219-222 via plonk.h:517-519     */
+  PB_PROVE_SRS_T = 10,          /* t_lo/t_mid/t_hi longer than the SRS: plonk.h:522-524           */
+  PB_PROVE_OPENING_ASSERT = 11, /* assert(poly_is_zero(rem)) plonk.h:610,617                      */
+  PB_PROVE_SRS_W = 12,          /* W_z / W_zw longer than the SRS: plonk.h:620-621                */
+  PB_PROVE_BAD_INPUT = 254      /* an input byte is not a canonical F17 residue (not a reference path) */
+};
+
+/* verdicts of pb_plonk_verify* (the verifier is new: the reference has none, plonk.h:656-659) */
+enum { PB_VERIFY_REJECT = 0, PB_VERIFY_ACCEPT = 1, PB_VERIFY_BAD_POINT = 2, PB_VERIFY_BAD_SCALAR = 3 };
+
+/* field / group operation selectors */
+enum { PB_OP_ADD = 0, PB_OP_SUB = 1, PB_OP_MUL = 2, PB_OP_DIV = 3, PB_OP_NEG = 4, PB_OP_INV = 5, PB_OP_POW = 6 };
+enum { PB_POLY_ADD = 0, PB_POLY_SUB = 1, PB_POLY_MUL = 2 };
+enum { PB_POLY_SCALE = 0, PB_POLY_NEGATE = 1, PB_POLY_SHIFT = 2, PB_POLY_ADD_HF = 3 };
+enum { PB_G_ADD = 0, PB_G_DOUBLE = 1, PB_G_NEG = 2 };
+
+#define PB_CIRCUIT_BYTES 44 /* q_l[4] q_r[4] q_o[4] q_m[4] q_c[4] | c_a.type[4] c_a.index[4] | c_b.. | c_c.. */
+#define PB_WITNESS_BYTES 12 /* ASSIGNMENTS a[4] b[4] c[4] (constraints.h:57-62) */
+#define PB_RAND_BYTES 9     /* HF rand[9] (plonk.h:228) */
+#define PB_CHALLENGE_BYTES 5
+#define PB_PROOF_BYTES 34
+#define PB_POLY_MAX 64      /* longest polynomial the generic poly entry points accept */
+#define PB_SRS_MAX 64       /* longest SRS a context accepts */
+
+const char *pb_last_error(void);
+int pb_abi_version(void);
+int pb_device_count(void); /* >= 0, or PB_ERR_NO_DEVICE */
+
+/* pinned host memory for the host-pointer entry points (optional; any host memory works) */
+int pb_host_alloc(void **out, size_t bytes);
+int pb_host_free(void *p);
+
+/* ---- context: one circuit + one SRS on one device.  Replaces plonk_new (plonk.h:53-119) plus the
+ * circuit-constant part of plonk_prove (plonk.h:254-275: sigma mapping and the eleven interpolations
+ * that do not depend on the witness).  h_len is fixed at 4 (omega = 4 has order 4 in F17, plonk.h:12). */
+typedef struct pb_ctx pb_ctx;
+int pb_ctx_create(pb_ctx **out, int device, const uint8_t circuit[PB_CIRCUIT_BYTES],
+                  const uint8_t *srs_g1s /* [srs_len][3] */, uint32_t srs_len, const uint8_t srs_g2[4]);
+int pb_ctx_destroy(pb_ctx *ctx);
+/* what plonk_new computes: h[4] k1_h[4] k2_h[4] h_pows_inv[16] z_h_x[8] z_h_x.len -> out[37] (plonk.h:43-51) */
+int pb_ctx_setup_dump(const pb_ctx *ctx, uint8_t out[37]);
+/* sigma_1..3[4] then S_sigma1..3 / QL QR QO QM QC / L1 coefficient rows [4] -> out[12 + 9*4] */
+int pb_ctx_circuit_dump(const pb_ctx *ctx, uint8_t out[48]);
+/* the eight preprocessed commitments [q_M][q_L][q_R][q_O][q_C][S1][S2][S3] and srs.g1s[0]: out[9][3] */
+int pb_ctx_verifier_key(const pb_ctx *ctx, uint8_t out[27]);
+/* the fixed-base table T[i][c] = g1_mul(srs.g1s[i], c), c in [0,17): out[srs_len][17][3] */
+int pb_ctx_srs_table(const pb_ctx *ctx, uint8_t *out);
+
+/* ---- kernel family (1): hf.h / gf.h element-wise.  field = 17 or 101.  out[i] = a[i] op b[i];
+ * NEG and INV ignore b (may be NULL); POW uses b[i] as the exponent.  hf.h:79-203, gf.h:87-172. */
+int pb_field_op_dev(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream);
+int pb_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+
+/* ---- kernel family (2): poly.h, matrix.h interpolation.  A polynomial batch is rows of `stride`
+ * coefficient bytes (low degree first) plus one length byte per row; rows are passed through
+ * poly_new first (trailing zeros trimmed, poly.h:20-38); 1 <= len <= stride <= PB_POLY_MAX. */
+/* poly_add / poly_sub / poly_mul (poly.h:72-122); so >= the untrimmed result length */
+int pb_poly_binop_dev(int op, const uint8_t *a, const uint8_t *alen, size_t sa, const uint8_t *b, const uint8_t *blen,
+                      size_t sb, uint8_t *out, uint8_t *olen, size_t so, size_t n, void *stream);
+int pb_poly_binop(int op, const uint8_t *a, const uint8_t *alen, size_t sa, const uint8_t *b, const uint8_t *blen,
+                  size_t sb, uint8_t *out, uint8_t *olen, size_t so, size_t n);
+/* poly_divide (poly.h:124-177); status[i] = 1 where the reference exits on a zero divisor */
+int pb_poly_divide_dev(const uint8_t *num, const uint8_t *nlen, size_t sn, const uint8_t *den, const uint8_t *dlen, size_t sd,
+                       uint8_t *quot, uint8_t *qlen, size_t sq, uint8_t *rem, uint8_t *rlen, size_t sr,
+                       uint8_t *status, size_t n, void *stream);
+int pb_poly_divide(const uint8_t *num, const uint8_t *nlen, size_t sn, const uint8_t *den, const uint8_t *dlen, size_t sd,
+                   uint8_t *quot, uint8_t *qlen, size_t sq, uint8_t *rem, uint8_t *rlen, size_t sr,
+                   uint8_t *status, size_t n);
+/* poly_eval (poly.h:265-272) */
+int pb_poly_eval_dev(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *x, uint8_t *out, size_t n, void *stream);
+int pb_poly_eval(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *x, uint8_t *out, size_t n);
+/* poly_scale / poly_negate / poly_shift / poly_add_hf (poly.h:179-216, 240-254, 67-70); k[i] is the scalar or shift */
+int pb_poly_unop_dev(int op, const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *k, uint8_t *out,
+                     uint8_t *olen, size_t so, size_t n, void *stream);
+int pb_poly_unop(int op, const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *k, uint8_t *out,
+                 uint8_t *olen, size_t so, size_t n);
+/* poly_slice (poly.h:218-238); status[i] = 1 where the reference exits on bad indices */
+int pb_poly_slice_dev(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *start, const uint8_t *end,
+                      uint8_t *out, uint8_t *olen, size_t so, uint8_t *status, size_t n, void *stream);
+int pb_poly_slice(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *start, const uint8_t *end,
+                  uint8_t *out, uint8_t *olen, size_t so, uint8_t *status, size_t n);
+/* poly_lagrange (poly.h:288-321) over `len` points per item; status[i] = 1 on duplicate x */
+int pb_poly_lagrange_dev(const uint8_t *xs, const uint8_t *ys, size_t len, uint8_t *out, uint8_t *olen, size_t so,
+                         uint8_t *status, size_t n, void *stream);
+int pb_poly_lagrange(const uint8_t *xs, const uint8_t *ys, size_t len, uint8_t *out, uint8_t *olen, size_t so,
+                     uint8_t *status, size_t n);
+/* interpolate_at_h (plonk.h:162-195): h_pows_inv (4x4) times vals[i][4]; out[i][4] + trimmed length */
+int pb_interpolate_at_h_dev(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out, uint8_t *olen, size_t n, void *stream);
+int pb_interpolate_at_h(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out, uint8_t *olen, size_t n);
+/* matrix_mul (matrix.h:81-98): out[i] = a[i] (m x k) times b[i] (k x c), row-major, m,k,c <= 8 */
+int pb_matrix_mul_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n, void *stream);
+int pb_matrix_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n);
+/* matrix_inv (matrix.h:151-176, Gauss-Jordan on (M | I), no singularity detection), dim <= 8 */
+int pb_matrix_inv_dev(const uint8_t *a, uint8_t *out, uint32_t dim, size_t n, void *stream);
+int pb_matrix_inv(const uint8_t *a, uint8_t *out, uint32_t dim, size_t n);
+
+/* ---- kernel family (3): g1.h, g2.h, srs.h */
+/* g1_add / g1_double / g1_neg (g1.h:37-89); b is ignored for DOUBLE and NEG */
+int pb_g1_op_dev(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream);
+int pb_g1_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+/* g1_mul (g1.h:91-103): raw 64-bit scalars, LSB-first double-and-add */
+int pb_g1_mul_dev(const uint8_t *points, const uint64_t *scalars, uint8_t *out, size_t n, void *stream);
+int pb_g1_mul(const uint8_t *points, const uint64_t *scalars, uint8_t *out, size_t n);
+/* same with one-byte scalars (the KZG case: scalars are F17 coefficients) */
+int pb_g1_mul_u8_dev(const uint8_t *points, const uint8_t *scalars, uint8_t *out, size_t n, void *stream);
+int pb_g1_mul_u8(const uint8_t *points, const uint8_t *scalars, uint8_t *out, size_t n);
+/* g1_is_on_curve (g1.h:26-31): out[i] in {0,1} */
+int pb_g1_is_on_curve_dev(const uint8_t *points, uint8_t *out, size_t n, void *stream);
+int pb_g1_is_on_curve(const uint8_t *points, uint8_t *out, size_t n);
+/* g2_add / g2_neg (g2.h:27-66) */
+int pb_g2_op_dev(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream);
+int pb_g2_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+/* g2_mul (g2.h:68-84); scalar 0 is undefined in the reference and yields (0xFF,0xFF) here */
+int pb_g2_mul_dev(const uint8_t *points, const uint64_t *scalars, uint8_t *out, size_t n, void *stream);
+int pb_g2_mul(const uint8_t *points, const uint64_t *scalars, uint8_t *out, size_t n);
+/* srs_eval_at_s (srs.h:53-68), the KZG commitment, against the context's SRS;
+ * status[i] = 1 where the reference exits because the polynomial is longer than the SRS */
+int pb_srs_eval_at_s_dev(const pb_ctx *ctx, const uint8_t *polys, const uint8_t *plen, size_t sp, uint8_t *out,
+                         uint8_t *status, size_t n, void *stream);
+int pb_srs_eval_at_s(const pb_ctx *ctx, const uint8_t *polys, const uint8_t *plen, size_t sp, uint8_t *out,
+                     uint8_t *status, size_t n);
+
+/* ---- kernel family (4): gt.h, pairing.h */
+int pb_gtp_mul_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream); /* gt.h:23-28 */
+int pb_gtp_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+int pb_gtp_pow_dev(const uint8_t *a, const uint64_t *e, uint8_t *out, size_t n, void *stream); /* gt.h:30-51 */
+int pb_gtp_pow(const uint8_t *a, const uint64_t *e, uint8_t *out, size_t n);
+int pb_line_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream); /* pairing.h:19-29, out[i][3] */
+int pb_line(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+/* pairing (pairing.h:66-83): out[i] = e(p[i], q[i]) in GT */
+int pb_pairing_dev(const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, void *stream);
+int pb_pairing(const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n);
+/* pairing_f (pairing.h:31-64), the Miller function for r >= 1 */
+int pb_pairing_f_dev(uint64_t r, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, void *stream);
+int pb_pairing_f(uint64_t r, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n);
+
+/* ---- protocol: plonk.h */
+/* constraints_satisfy (constraints.h:145-171): out[i] in {0,1} */
+int pb_constraints_satisfy_dev(const pb_ctx *ctx, const uint8_t *witness, uint8_t *out, size_t n, void *stream);
+int pb_constraints_satisfy(const pb_ctx *ctx, const uint8_t *witness, uint8_t *out, size_t n);
+/* plonk_prove (plonk.h:223-656) over a batch: witness[n][12], rnd[n][9], chal[n][5] -> proofs[n][34], status[n] */
+int pb_plonk_prove_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                       uint8_t *proofs, uint8_t *status, size_t n, void *stream);
+int pb_plonk_prove(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                   uint8_t *proofs, uint8_t *status, size_t n);
+/* plonk_verify (new; specification: oracle/verify_spec.inc): proofs[n][34], chal[n][5], u[n] ->
+ * verdict[n]; gt (optional, may be NULL): [n][4] = lhs.a lhs.b rhs.a rhs.b of the final pairing check */
+int pb_plonk_verify_dev(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
+                        uint8_t *verdict, uint8_t *gt, size_t n, void *stream);
+int pb_plonk_verify(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
+                    uint8_t *verdict, uint8_t *gt, size_t n);
+/* prove then verify every completed proof (status 0); verdict[i] = 0xFF where status[i] != 0.
+ * Host-pointer version: chunked, copies overlapped with compute on internal streams. */
+int pb_plonk_prove_verify_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                              const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n, void *stream);
+int pb_plonk_prove_verify(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                          const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n);
+/* on-device tally: counts[0..15] += number of items per status byte (0..14, 15 = anything else),
+ * counts[16] += verdict==1, counts[17] += a 64-bit sum of all proof bytes (checksum). counts: int64[18] device ptr */
+int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *verdict, size_t n, int64_t *counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONK_B200_H */

@@ -1,0 +1,880 @@
+// cabi.cu -- the C ABI declared in include/plonk_b200.h: context creation, kernel launches, and the
+// host-pointer wrappers (copy in, launch, copy out).  No arithmetic of the path happens on the host:
+// even the per-circuit constants (inverse Vandermonde matrix, interpolations, SRS table, verifier
+// key) are produced by the batch kernels at context creation.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/plonk_b200.h"
+#include "kernels.cuh"
+
+using namespace pb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+    return fail(PB_ERR_NO_DEVICE, std::string("plonk_b200: no usable CUDA device (") + cudaGetErrorString(e) +
+                                      "); this library has no CPU fallback [" + what + "]");
+  return fail(PB_ERR_CUDA, std::string("plonk_b200: CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+#define ARG(cond)                                                         \
+  do {                                                                    \
+    if (!(cond)) return fail(PB_ERR_ARG, "plonk_b200: bad argument: " #cond); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline unsigned blocks_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (n <= 0) return fail(PB_ERR_NO_DEVICE, "plonk_b200: no CUDA device; this library has no CPU fallback");
+  return PB_OK;
+}
+
+// RAII device scratch for the host-pointer wrappers
+struct Dev {
+  void* p = nullptr;
+  cudaError_t err = cudaSuccess;
+  explicit Dev(size_t bytes) { err = cudaMalloc(&p, bytes ? bytes : 16); }
+  ~Dev() { if (p) cudaFree(p); }
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+#define DEV(name, bytes) Dev name(bytes); if (name.err != cudaSuccess) return cuda_fail(name.err, "cudaMalloc")
+#define H2D(dev, host, bytes) CU(cudaMemcpy((dev).p, host, bytes, cudaMemcpyHostToDevice))
+#define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
+#define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
+
+constexpr size_t PIPE_CHUNK = 1u << 18;   // items per pipeline chunk of the host-pointer prove/verify
+constexpr int PIPE_SLOTS = 3;
+
+struct PipeSlot {
+  cudaStream_t stream = nullptr;
+  uint8_t *wit = nullptr, *rnd = nullptr, *chal = nullptr, *u = nullptr, *proofs = nullptr, *status = nullptr, *verdict = nullptr;
+};
+
+}  // namespace
+
+struct pb_ctx {
+  int device = 0;
+  CircuitConst cc{};
+  VerifyKey vk{};
+  bool vk_valid = true;               // false when a selector polynomial is longer than the SRS
+  ProverTables* d_tables = nullptr;   // device
+  uint32_t* d_srs_table = nullptr;    // device, [srs_len][17]
+  uint32_t srs_len = 0;
+  std::vector<uint8_t> srs_g1s;       // host copy, [srs_len][3]
+  uint8_t srs_g2[4] = {0, 0, 0, 0};
+  uint8_t setup[37] = {0};            // h k1_h k2_h h_pows_inv z_h len
+  uint8_t circuit_dump[48] = {0};
+  uint8_t vkey_bytes[27] = {0};
+  std::vector<uint8_t> table_bytes;   // [srs_len][17][3]
+  std::mutex pipe_mu;
+  bool pipe_ready = false;
+  PipeSlot slots[PIPE_SLOTS];
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
+};
+
+int pipe_init(pb_ctx* c) {
+  if (c->pipe_ready) return PB_OK;
+  for (auto& s : c->slots) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&s.wit, PIPE_CHUNK * 12));
+    CU(cudaMalloc(&s.rnd, PIPE_CHUNK * 9));
+    CU(cudaMalloc(&s.chal, PIPE_CHUNK * 5));
+    CU(cudaMalloc(&s.u, PIPE_CHUNK));
+    CU(cudaMalloc(&s.proofs, PIPE_CHUNK * 34));
+    CU(cudaMalloc(&s.status, PIPE_CHUNK));
+    CU(cudaMalloc(&s.verdict, PIPE_CHUNK));
+  }
+  c->pipe_ready = true;
+  return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pb_last_error(void) { return g_err.c_str(); }
+int pb_abi_version(void) { return 1; }
+int pb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  return n;
+}
+int pb_host_alloc(void** out, size_t bytes) {
+  ARG(out != nullptr);
+  int rc = require_device();
+  if (rc) return rc;
+  CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+  return PB_OK;
+}
+int pb_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------ family (1)
+int pb_field_op_dev(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  ARG(field == 17 || field == 101);
+  ARG(op >= 0 && op <= 6);
+  ARG(a && out);
+  ARG(b || op == PB_OP_NEG || op == PB_OP_INV);
+  ARG(aligned16(a) && aligned16(out) && (!b || aligned16(b)));
+  if (n == 0) return PB_OK;
+  unsigned grid = blocks_for((n + 15) / 16, BLOCK_LIGHT);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (field == 17) field_op_kernel<17><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
+  else field_op_kernel<101><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
+  LAUNCH_CHECK("field_op_kernel");
+  return PB_OK;
+}
+int pb_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && out);
+  DEV(da, n); DEV(db, n); DEV(dout, n);
+  H2D(da, a, n);
+  if (b) H2D(db, b, n);
+  rc = pb_field_op_dev(field, op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n);
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------ family (2)
+int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
+                      uint8_t* out, uint8_t* olen, size_t so, size_t n, void* stream) {
+  ARG(op >= 0 && op <= 2);
+  ARG(a && alen && b && blen && out && olen);
+  ARG(sa >= 1 && sb >= 1 && sa <= PB_POLY_MAX && sb <= PB_POLY_MAX);
+  ARG(so >= (op == 2 ? sa + sb - 1 : (sa > sb ? sa : sb)) && so <= 2 * PB_POLY_MAX);
+  if (n == 0) return PB_OK;
+  poly_binop_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, alen, (int)sa, b, blen, (int)sb, out, olen, (int)so, n);
+  LAUNCH_CHECK("poly_binop_kernel");
+  return PB_OK;
+}
+int pb_poly_binop(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
+                  uint8_t* out, uint8_t* olen, size_t so, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && alen && b && blen && out && olen);
+  DEV(da, n * sa); DEV(dal, n); DEV(db, n * sb); DEV(dbl, n); DEV(dout, n * so); DEV(dol, n);
+  H2D(da, a, n * sa); H2D(dal, alen, n); H2D(db, b, n * sb); H2D(dbl, blen, n);
+  rc = pb_poly_binop_dev(op, da.as<uint8_t>(), dal.as<uint8_t>(), sa, db.as<uint8_t>(), dbl.as<uint8_t>(), sb,
+                         dout.as<uint8_t>(), dol.as<uint8_t>(), so, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * so); D2H(olen, dol, n);
+  return PB_OK;
+}
+
+int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
+                       uint8_t* quot, uint8_t* qlen, size_t sq, uint8_t* rem, uint8_t* rlen, size_t sr,
+                       uint8_t* status, size_t n, void* stream) {
+  ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
+  ARG(sn >= 1 && sd >= 1 && sn <= PB_POLY_MAX && sd <= PB_POLY_MAX && sq >= 1 && sr >= 1);
+  if (n == 0) return PB_OK;
+  poly_divide_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(num, nlen, (int)sn, den, dlen, (int)sd, quot, qlen, (int)sq,
+                                                                              rem, rlen, (int)sr, status, n);
+  LAUNCH_CHECK("poly_divide_kernel");
+  return PB_OK;
+}
+int pb_poly_divide(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
+                   uint8_t* quot, uint8_t* qlen, size_t sq, uint8_t* rem, uint8_t* rlen, size_t sr, uint8_t* status, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
+  DEV(dn, n * sn); DEV(dnl, n); DEV(dd, n * sd); DEV(ddl, n); DEV(dq, n * sq); DEV(dql, n); DEV(dr, n * sr); DEV(drl, n); DEV(dst, n);
+  H2D(dn, num, n * sn); H2D(dnl, nlen, n); H2D(dd, den, n * sd); H2D(ddl, dlen, n);
+  rc = pb_poly_divide_dev(dn.as<uint8_t>(), dnl.as<uint8_t>(), sn, dd.as<uint8_t>(), ddl.as<uint8_t>(), sd, dq.as<uint8_t>(),
+                          dql.as<uint8_t>(), sq, dr.as<uint8_t>(), drl.as<uint8_t>(), sr, dst.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(quot, dq, n * sq); D2H(qlen, dql, n); D2H(rem, dr, n * sr); D2H(rlen, drl, n); D2H(status, dst, n);
+  return PB_OK;
+}
+
+int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n, void* stream) {
+  ARG(p && plen && x && out && sp >= 1);
+  if (n == 0) return PB_OK;
+  poly_eval_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(p, plen, (int)sp, x, out, n);
+  LAUNCH_CHECK("poly_eval_kernel");
+  return PB_OK;
+}
+int pb_poly_eval(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(p && plen && x && out);
+  DEV(dp, n * sp); DEV(dl, n); DEV(dx, n); DEV(dout, n);
+  H2D(dp, p, n * sp); H2D(dl, plen, n); H2D(dx, x, n);
+  rc = pb_poly_eval_dev(dp.as<uint8_t>(), dl.as<uint8_t>(), sp, dx.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n);
+  return PB_OK;
+}
+
+int pb_poly_unop_dev(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen,
+                     size_t so, size_t n, void* stream) {
+  ARG(op >= 0 && op <= 3);
+  ARG(p && plen && out && olen && sp >= 1 && sp <= PB_POLY_MAX && so >= sp && so <= 2 * PB_POLY_MAX);
+  ARG(k || op == PB_POLY_NEGATE);
+  if (n == 0) return PB_OK;
+  poly_unop_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, p, plen, (int)sp, k, out, olen, (int)so, n);
+  LAUNCH_CHECK("poly_unop_kernel");
+  return PB_OK;
+}
+int pb_poly_unop(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen, size_t so, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(p && plen && out && olen);
+  DEV(dp, n * sp); DEV(dl, n); DEV(dk, n); DEV(dout, n * so); DEV(dol, n);
+  H2D(dp, p, n * sp); H2D(dl, plen, n);
+  if (k) H2D(dk, k, n);
+  rc = pb_poly_unop_dev(op, dp.as<uint8_t>(), dl.as<uint8_t>(), sp, k ? dk.as<uint8_t>() : nullptr, dout.as<uint8_t>(), dol.as<uint8_t>(), so, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * so); D2H(olen, dol, n);
+  return PB_OK;
+}
+
+int pb_poly_slice_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
+                      uint8_t* olen, size_t so, uint8_t* status, size_t n, void* stream) {
+  ARG(p && plen && start && end && out && olen && status && sp >= 1 && sp <= PB_POLY_MAX && so >= sp);
+  if (n == 0) return PB_OK;
+  poly_slice_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(p, plen, (int)sp, start, end, out, olen, (int)so, status, n);
+  LAUNCH_CHECK("poly_slice_kernel");
+  return PB_OK;
+}
+int pb_poly_slice(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
+                  uint8_t* olen, size_t so, uint8_t* status, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(p && plen && start && end && out && olen && status);
+  DEV(dp, n * sp); DEV(dl, n); DEV(ds, n); DEV(de, n); DEV(dout, n * so); DEV(dol, n); DEV(dst, n);
+  H2D(dp, p, n * sp); H2D(dl, plen, n); H2D(ds, start, n); H2D(de, end, n);
+  rc = pb_poly_slice_dev(dp.as<uint8_t>(), dl.as<uint8_t>(), sp, ds.as<uint8_t>(), de.as<uint8_t>(), dout.as<uint8_t>(), dol.as<uint8_t>(), so,
+                         dst.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * so); D2H(olen, dol, n); D2H(status, dst, n);
+  return PB_OK;
+}
+
+int pb_poly_lagrange_dev(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status,
+                         size_t n, void* stream) {
+  ARG(xs && ys && out && olen && status && len >= 1 && len <= 16 && so >= len);
+  if (n == 0) return PB_OK;
+  poly_lagrange_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(xs, ys, (int)len, out, olen, (int)so, status, n);
+  LAUNCH_CHECK("poly_lagrange_kernel");
+  return PB_OK;
+}
+int pb_poly_lagrange(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(xs && ys && out && olen && status);
+  DEV(dx, n * len); DEV(dy, n * len); DEV(dout, n * so); DEV(dol, n); DEV(dst, n);
+  H2D(dx, xs, n * len); H2D(dy, ys, n * len);
+  rc = pb_poly_lagrange_dev(dx.as<uint8_t>(), dy.as<uint8_t>(), len, dout.as<uint8_t>(), dol.as<uint8_t>(), so, dst.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * so); D2H(olen, dol, n); D2H(status, dst, n);
+  return PB_OK;
+}
+
+int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n, void* stream) {
+  ARG(ctx && vals && out && olen);
+  ARG(aligned16(vals) && aligned16(out));
+  if (n == 0) return PB_OK;
+  interpolate_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, vals, out, olen, n);
+  LAUNCH_CHECK("interpolate_kernel");
+  return PB_OK;
+}
+int pb_interpolate_at_h(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n) {
+  ARG(ctx && vals && out && olen);
+  DeviceGuard g(ctx->device);
+  DEV(dv, n * 4); DEV(dout, n * 4); DEV(dol, n);
+  H2D(dv, vals, n * 4);
+  int rc = pb_interpolate_at_h_dev(ctx, dv.as<uint8_t>(), dout.as<uint8_t>(), dol.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 4); D2H(olen, dol, n);
+  return PB_OK;
+}
+
+int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n, void* stream) {
+  ARG(a && b && out && m >= 1 && k >= 1 && c >= 1 && m <= 8 && k <= 8 && c <= 8);
+  if (n == 0) return PB_OK;
+  matrix_mul_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, (int)m, (int)k, (int)c, n);
+  LAUNCH_CHECK("matrix_mul_kernel");
+  return PB_OK;
+}
+int pb_matrix_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && b && out);
+  DEV(da, n * m * k); DEV(db, n * k * c); DEV(dout, n * m * c);
+  H2D(da, a, n * m * k); H2D(db, b, n * k * c);
+  rc = pb_matrix_mul_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), m, k, c, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * m * c);
+  return PB_OK;
+}
+int pb_matrix_inv_dev(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n, void* stream) {
+  ARG(a && out && dim >= 1 && dim <= 8);
+  if (n == 0) return PB_OK;
+  matrix_inv_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, out, (int)dim, n);
+  LAUNCH_CHECK("matrix_inv_kernel");
+  return PB_OK;
+}
+int pb_matrix_inv(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && out);
+  DEV(da, n * dim * dim); DEV(dout, n * dim * dim);
+  H2D(da, a, n * dim * dim);
+  rc = pb_matrix_inv_dev(da.as<uint8_t>(), dout.as<uint8_t>(), dim, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * dim * dim);
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------ family (3)
+int pb_g1_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  ARG(op >= 0 && op <= 2 && a && out && (b || op != PB_G_ADD));
+  if (n == 0) return PB_OK;
+  g1_op_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
+  LAUNCH_CHECK("g1_op_kernel");
+  return PB_OK;
+}
+int pb_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && out);
+  DEV(da, n * 3); DEV(db, n * 3); DEV(dout, n * 3);
+  H2D(da, a, n * 3);
+  if (b) H2D(db, b, n * 3);
+  rc = pb_g1_op_dev(op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 3);
+  return PB_OK;
+}
+int pb_g1_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
+  ARG(points && scalars && out);
+  if (n == 0) return PB_OK;
+  g1_mul_kernel<uint64_t><<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
+  LAUNCH_CHECK("g1_mul_kernel");
+  return PB_OK;
+}
+int pb_g1_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(points && scalars && out);
+  DEV(dp, n * 3); DEV(ds, n * 8); DEV(dout, n * 3);
+  H2D(dp, points, n * 3); H2D(ds, scalars, n * 8);
+  rc = pb_g1_mul_dev(dp.as<uint8_t>(), ds.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 3);
+  return PB_OK;
+}
+int pb_g1_mul_u8_dev(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n, void* stream) {
+  ARG(points && scalars && out);
+  if (n == 0) return PB_OK;
+  g1_mul_kernel<uint8_t><<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
+  LAUNCH_CHECK("g1_mul_kernel");
+  return PB_OK;
+}
+int pb_g1_mul_u8(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(points && scalars && out);
+  DEV(dp, n * 3); DEV(ds, n); DEV(dout, n * 3);
+  H2D(dp, points, n * 3); H2D(ds, scalars, n);
+  rc = pb_g1_mul_u8_dev(dp.as<uint8_t>(), ds.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 3);
+  return PB_OK;
+}
+int pb_g1_is_on_curve_dev(const uint8_t* points, uint8_t* out, size_t n, void* stream) {
+  ARG(points && out);
+  if (n == 0) return PB_OK;
+  g1_on_curve_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(points, out, n);
+  LAUNCH_CHECK("g1_on_curve_kernel");
+  return PB_OK;
+}
+int pb_g1_is_on_curve(const uint8_t* points, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(points && out);
+  DEV(dp, n * 3); DEV(dout, n);
+  H2D(dp, points, n * 3);
+  rc = pb_g1_is_on_curve_dev(dp.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n);
+  return PB_OK;
+}
+int pb_g2_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  ARG((op == PB_G_ADD || op == PB_G_NEG) && a && out && (b || op != PB_G_ADD));
+  if (n == 0) return PB_OK;
+  g2_op_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
+  LAUNCH_CHECK("g2_op_kernel");
+  return PB_OK;
+}
+int pb_g2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && out);
+  DEV(da, n * 2); DEV(db, n * 2); DEV(dout, n * 2);
+  H2D(da, a, n * 2);
+  if (b) H2D(db, b, n * 2);
+  rc = pb_g2_op_dev(op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+int pb_g2_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
+  ARG(points && scalars && out);
+  if (n == 0) return PB_OK;
+  g2_mul_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
+  LAUNCH_CHECK("g2_mul_kernel");
+  return PB_OK;
+}
+int pb_g2_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(points && scalars && out);
+  DEV(dp, n * 2); DEV(ds, n * 8); DEV(dout, n * 2);
+  H2D(dp, points, n * 2); H2D(ds, scalars, n * 8);
+  rc = pb_g2_mul_dev(dp.as<uint8_t>(), ds.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+
+int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status,
+                         size_t n, void* stream) {
+  ARG(ctx && polys && plen && out && status && sp >= 1 && sp <= PB_POLY_MAX);
+  if (n == 0) return PB_OK;
+  commit_kernel<<<blocks_for(n, BLOCK), BLOCK, ctx->srs_len * 17 * sizeof(uint32_t), S(stream)>>>(ctx->d_srs_table, ctx->srs_len, polys, plen,
+                                                                                                 (int)sp, out, status, n);
+  LAUNCH_CHECK("commit_kernel");
+  return PB_OK;
+}
+int pb_srs_eval_at_s(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status, size_t n) {
+  ARG(ctx && polys && plen && out && status);
+  DeviceGuard g(ctx->device);
+  DEV(dp, n * sp); DEV(dl, n); DEV(dout, n * 3); DEV(dst, n);
+  H2D(dp, polys, n * sp); H2D(dl, plen, n);
+  int rc = pb_srs_eval_at_s_dev(ctx, dp.as<uint8_t>(), dl.as<uint8_t>(), sp, dout.as<uint8_t>(), dst.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 3); D2H(status, dst, n);
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------ family (4)
+int pb_gtp_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  ARG(a && b && out);
+  if (n == 0) return PB_OK;
+  gtp_mul_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
+  LAUNCH_CHECK("gtp_mul_kernel");
+  return PB_OK;
+}
+int pb_gtp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && b && out);
+  DEV(da, n * 2); DEV(db, n * 2); DEV(dout, n * 2);
+  H2D(da, a, n * 2); H2D(db, b, n * 2);
+  rc = pb_gtp_mul_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+int pb_gtp_pow_dev(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n, void* stream) {
+  ARG(a && e && out);
+  if (n == 0) return PB_OK;
+  gtp_pow_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, e, out, n);
+  LAUNCH_CHECK("gtp_pow_kernel");
+  return PB_OK;
+}
+int pb_gtp_pow(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && e && out);
+  DEV(da, n * 2); DEV(de, n * 8); DEV(dout, n * 2);
+  H2D(da, a, n * 2); H2D(de, e, n * 8);
+  rc = pb_gtp_pow_dev(da.as<uint8_t>(), de.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+int pb_line_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  ARG(a && b && out);
+  if (n == 0) return PB_OK;
+  line_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
+  LAUNCH_CHECK("line_kernel");
+  return PB_OK;
+}
+int pb_line(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a && b && out);
+  DEV(da, n * 3); DEV(db, n * 3); DEV(dout, n * 3);
+  H2D(da, a, n * 3); H2D(db, b, n * 3);
+  rc = pb_line_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 3);
+  return PB_OK;
+}
+int pb_pairing_dev(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
+  ARG(p && q && out);
+  if (n == 0) return PB_OK;
+  pairing_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(p, q, out, n);
+  LAUNCH_CHECK("pairing_kernel");
+  return PB_OK;
+}
+int pb_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(p && q && out);
+  DEV(dp, n * 3); DEV(dq, n * 2); DEV(dout, n * 2);
+  H2D(dp, p, n * 3); H2D(dq, q, n * 2);
+  rc = pb_pairing_dev(dp.as<uint8_t>(), dq.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+int pb_pairing_f_dev(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
+  ARG(p && q && out && r >= 1);
+  if (n == 0) return PB_OK;
+  pairing_f_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(r, p, q, out, n);
+  LAUNCH_CHECK("pairing_f_kernel");
+  return PB_OK;
+}
+int pb_pairing_f(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(p && q && out);
+  DEV(dp, n * 3); DEV(dq, n * 2); DEV(dout, n * 2);
+  H2D(dp, p, n * 3); H2D(dq, q, n * 2);
+  rc = pb_pairing_f_dev(r, dp.as<uint8_t>(), dq.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n * 2);
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------ context
+int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYTES], const uint8_t* srs_g1s, uint32_t srs_len,
+                  const uint8_t srs_g2[4]) {
+  ARG(out && circuit && srs_g1s && srs_g2);
+  ARG(srs_len >= 1 && srs_len <= PB_SRS_MAX);
+  int rc = require_device();
+  if (rc) return rc;
+  for (int i = 0; i < 20; i++) ARG(circuit[i] < 17);
+  for (int s = 0; s < 3; s++)
+    for (int i = 0; i < 4; i++) ARG(circuit[24 + 8 * s + i] >= 1 && circuit[24 + 8 * s + i] <= 4);   // 1-based index into H (plonk.h:144)
+  for (uint32_t i = 0; i < srs_len; i++) ARG(srs_g1s[3 * i] < 101 && srs_g1s[3 * i + 1] < 101);
+  for (int i = 0; i < 4; i++) ARG(srs_g2[i] < 101);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(PB_ERR_CUDA, "plonk_b200: cudaSetDevice failed");
+
+  pb_ctx* c = new pb_ctx();
+  c->device = device;
+  c->srs_len = srs_len;
+  c->srs_g1s.assign(srs_g1s, srs_g1s + 3 * srs_len);
+  memcpy(c->srs_g2, srs_g2, 4);
+  auto bail = [&](int code) { pb_ctx_destroy(c); return code; };
+
+  // plonk_new (plonk.h:53-119): H, k1 H, k2 H, inverse Vandermonde matrix, Z_H
+  uint8_t h[4], k1h[4], k2h[4], V[16], Vinv[16];
+  for (int i = 0; i < 4; i++) h[i] = (uint8_t)pow17(4u, (uint64_t)i);
+  for (int i = 0; i < 4; i++) { k1h[i] = (uint8_t)mul17(h[i], 2u); k2h[i] = (uint8_t)mul17(h[i], 3u); }
+  for (int r = 0; r < 4; r++) for (int col = 0; col < 4; col++) V[r * 4 + col] = (uint8_t)pow17(h[r], (uint64_t)col);
+  if ((rc = pb_matrix_inv(V, Vinv, 4, 1))) return bail(rc);
+  for (int r = 0; r < 4; r++)
+    for (int col = 0; col < 4; col++) {
+      uint32_t s = 0;
+      for (int k = 0; k < 4; k++) s += (uint32_t)V[r * 4 + k] * Vinv[k * 4 + col];
+      if (red17(s) != (r == col ? 1u : 0u)) return bail(fail(PB_ERR_CUDA, "plonk_b200: h_pows_inv is not the inverse of the Vandermonde matrix"));
+    }
+  // Z_H = prod (x - h_i) must be x^4 - 1: prover.cuh divides by that shape
+  uint8_t zh[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  int zl = 1;
+  for (int i = 0; i < 4; i++) {
+    uint8_t t[8] = {0};
+    for (int k = 0; k < zl; k++) { t[k] = (uint8_t)add17(t[k], mul17(zh[k], neg17(h[i]))); t[k + 1] = (uint8_t)add17(t[k + 1], zh[k]); }
+    zl++;
+    memcpy(zh, t, 8);
+  }
+  const uint8_t zh_expect[5] = {16, 0, 0, 0, 1};
+  if (zl != 5 || memcmp(zh, zh_expect, 5) != 0) return bail(fail(PB_ERR_CUDA, "plonk_b200: Z_H is not x^4 - 1"));
+  memcpy(c->setup, h, 4); memcpy(c->setup + 4, k1h, 4); memcpy(c->setup + 8, k2h, 4); memcpy(c->setup + 12, Vinv, 16);
+  memcpy(c->setup + 28, zh, 8); c->setup[36] = 5;
+
+  CircuitConst& cc = c->cc;
+  for (int s = 0; s < 5; s++) for (int i = 0; i < 4; i++) cc.qv[s][i] = circuit[4 * s + i];
+  for (int r = 0; r < 4; r++) for (int col = 0; col < 4; col++) cc.vinv[r][col] = Vinv[r * 4 + col];
+  cc.srs_len = srs_len;
+  cc.bad_copy = 0;
+  // copy_constraints_to_roots (plonk.h:142-160)
+  uint8_t rows[9][4];
+  for (int s = 0; s < 5; s++) memcpy(rows[s], circuit + 4 * s, 4);
+  for (int s = 0; s < 3; s++)
+    for (int i = 0; i < 4; i++) {
+      uint8_t type = circuit[20 + 8 * s + i], idx = (uint8_t)(circuit[24 + 8 * s + i] - 1);
+      uint8_t v = 0;
+      if (type == 0) v = h[idx]; else if (type == 1) v = k1h[idx]; else if (type == 2) v = k2h[idx]; else cc.bad_copy = 1;
+      rows[5 + s][i] = v;
+      cc.sig[s][i] = v;
+    }
+  rows[8][0] = 1; rows[8][1] = rows[8][2] = rows[8][3] = 0;      // L1 = interpolate([1,0,0,0]), plonk.h:385-391
+  // the nine witness-independent interpolations of plonk.h:268-275,391 -- on the device
+  uint8_t polys[9][4], plens[9];
+  if ((rc = pb_interpolate_at_h(c, &rows[0][0], &polys[0][0], plens, 9))) return bail(rc);
+  for (int s = 0; s < 5; s++) for (int i = 0; i < 4; i++) cc.QP[s][i] = polys[s][i];
+  for (int s = 0; s < 3; s++) for (int i = 0; i < 4; i++) cc.SP[s][i] = polys[5 + s][i];
+  for (int i = 0; i < 4; i++) cc.l1[i] = polys[8][i];
+  for (int s = 0; s < 3; s++) memcpy(c->circuit_dump + 4 * s, rows[5 + s], 4);
+  for (int s = 0; s < 3; s++) memcpy(c->circuit_dump + 12 + 4 * s, polys[5 + s], 4);
+  for (int s = 0; s < 5; s++) memcpy(c->circuit_dump + 24 + 4 * s, polys[s], 4);
+  memcpy(c->circuit_dump + 44, polys[8], 4);
+
+  // SRS fixed-base table T[i][c] = g1_mul(g1s[i], c), and the prover's nine-row copy with the field tables
+  const uint32_t rows_full = srs_len;
+  uint8_t* d_g1s = nullptr;
+  if (cudaMalloc(&d_g1s, 3 * srs_len + 16) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+  cudaMemcpy(d_g1s, srs_g1s, 3 * srs_len, cudaMemcpyHostToDevice);
+  if (cudaMalloc(&c->d_srs_table, rows_full * 17 * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_g1s); return bail(cuda_fail(cudaGetLastError(), "cudaMalloc")); }
+  srs_table_kernel<<<1, 256>>>(d_g1s, srs_len, rows_full, c->d_srs_table);
+  ProverTables pt;
+  memset(&pt, 0, sizeof pt);
+  uint32_t* d_prow = nullptr;
+  if (cudaMalloc(&d_prow, PROVER_SRS_ROWS * 17 * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_g1s); return bail(cuda_fail(cudaGetLastError(), "cudaMalloc")); }
+  srs_table_kernel<<<1, 256>>>(d_g1s, srs_len, PROVER_SRS_ROWS, d_prow);
+  cudaError_t e = cudaMemcpy(pt.T, d_prow, sizeof pt.T, cudaMemcpyDeviceToHost);
+  cudaFree(d_prow);
+  cudaFree(d_g1s);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "srs_table_kernel"));
+  for (uint32_t i = 0; i < 101; i++) pt.ft.inv101[i] = (uint8_t)pow101(i, 99);
+  for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
+  if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+  cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice);
+  std::vector<uint32_t> tab(rows_full * 17);
+  e = cudaMemcpy(tab.data(), c->d_srs_table, tab.size() * 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "srs table read-back"));
+  c->table_bytes.resize(tab.size() * 3);
+  for (size_t k = 0; k < tab.size(); k++) {
+    c->table_bytes[3 * k] = tab[k] & 0xFF; c->table_bytes[3 * k + 1] = (tab[k] >> 8) & 0xFF; c->table_bytes[3 * k + 2] = (tab[k] >> 16) & 1;
+  }
+
+  // verifier key: srs_eval_at_s of q_M q_L q_R q_O q_C S1 S2 S3 (on the device)
+  {
+    const int order[8] = {3, 0, 1, 2, 4, 5, 6, 7};
+    uint8_t kp[8][4];
+    for (int j = 0; j < 8; j++) memcpy(kp[j], polys[order[j]], 4);
+    uint8_t* d_kp = nullptr; uint32_t* d_out = nullptr;
+    if (cudaMalloc(&d_kp, 32) != cudaSuccess || cudaMalloc(&d_out, 32) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    cudaMemcpy(d_kp, kp, 32, cudaMemcpyHostToDevice);
+    verifier_key_kernel<<<1, 32>>>(c->d_srs_table, srs_len, d_kp, d_out);
+    uint32_t packed[8];
+    e = cudaMemcpy(packed, d_out, 32, cudaMemcpyDeviceToHost);
+    cudaFree(d_kp); cudaFree(d_out);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "verifier_key_kernel"));
+    G1* dst[8] = {&c->vk.qm, &c->vk.ql, &c->vk.qr, &c->vk.qo, &c->vk.qc, &c->vk.s1, &c->vk.s2, &c->vk.s3};
+    for (int j = 0; j < 8; j++) {
+      if (packed[j] == 0xFFFFFFFFu) { c->vk_valid = false; packed[j] = pack_g1(0, 0, 1); }
+      *dst[j] = G1{packed[j] & 0xFFu, (packed[j] >> 8) & 0xFFu, (packed[j] >> 16) & 1u};
+      c->vkey_bytes[3 * j] = (uint8_t)dst[j]->x; c->vkey_bytes[3 * j + 1] = (uint8_t)dst[j]->y; c->vkey_bytes[3 * j + 2] = (uint8_t)dst[j]->inf;
+    }
+    c->vk.g1_one = G1{srs_g1s[0], srs_g1s[1], srs_g1s[2] ? 1u : 0u};
+    c->vkey_bytes[24] = srs_g1s[0]; c->vkey_bytes[25] = srs_g1s[1]; c->vkey_bytes[26] = srs_g1s[2] ? 1 : 0;
+    c->vk.g2_one = G2{srs_g2[0], srs_g2[1]};
+    c->vk.g2_s = G2{srs_g2[2], srs_g2[3]};
+  }
+  *out = c;
+  return PB_OK;
+}
+
+int pb_ctx_destroy(pb_ctx* c) {
+  if (!c) return PB_OK;
+  DeviceGuard g(c->device);
+  if (c->d_tables) cudaFree(c->d_tables);
+  if (c->d_srs_table) cudaFree(c->d_srs_table);
+  for (auto& s : c->slots) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    uint8_t* bufs[7] = {s.wit, s.rnd, s.chal, s.u, s.proofs, s.status, s.verdict};
+    for (auto b : bufs) if (b) cudaFree(b);
+  }
+  delete c;
+  return PB_OK;
+}
+int pb_ctx_setup_dump(const pb_ctx* ctx, uint8_t out[37]) { ARG(ctx && out); memcpy(out, ctx->setup, 37); return PB_OK; }
+int pb_ctx_circuit_dump(const pb_ctx* ctx, uint8_t out[48]) { ARG(ctx && out); memcpy(out, ctx->circuit_dump, 48); return PB_OK; }
+int pb_ctx_verifier_key(const pb_ctx* ctx, uint8_t out[27]) { ARG(ctx && out); memcpy(out, ctx->vkey_bytes, 27); return PB_OK; }
+int pb_ctx_srs_table(const pb_ctx* ctx, uint8_t* out) { ARG(ctx && out); memcpy(out, ctx->table_bytes.data(), ctx->table_bytes.size()); return PB_OK; }
+
+// ------------------------------------------------------------------ protocol
+int pb_constraints_satisfy_dev(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n, void* stream) {
+  ARG(ctx && witness && out);
+  if (n == 0) return PB_OK;
+  satisfy_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, witness, out, n);
+  LAUNCH_CHECK("satisfy_kernel");
+  return PB_OK;
+}
+int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n) {
+  ARG(ctx && witness && out);
+  DeviceGuard g(ctx->device);
+  DEV(dw, n * 12); DEV(dout, n);
+  H2D(dw, witness, n * 12);
+  int rc = pb_constraints_satisfy_dev(ctx, dw.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n);
+  return PB_OK;
+}
+
+int pb_plonk_prove_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs,
+                       uint8_t* status, size_t n, void* stream) {
+  ARG(ctx && witness && rnd && chal && proofs && status);
+  ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
+  if (n == 0) return PB_OK;
+  prove_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n);
+  LAUNCH_CHECK("prove_kernel");
+  return PB_OK;
+}
+int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt,
+                        size_t n, void* stream) {
+  ARG(ctx && proofs && chal && u && verdict);
+  ARG(ctx->vk_valid);
+  ARG(aligned16(proofs) && aligned16(chal) && (!gt || aligned16(gt)));
+  if (n == 0) return PB_OK;
+  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, nullptr, verdict, gt, n);
+  LAUNCH_CHECK("verify_kernel");
+  return PB_OK;
+}
+int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                              uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
+  ARG(u && verdict);
+  ARG(ctx && ctx->vk_valid);
+  int rc = pb_plonk_prove_dev(ctx, witness, rnd, chal, proofs, status, n, stream);
+  if (rc) return rc;
+  if (n == 0) return PB_OK;
+  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, status, verdict, nullptr, n);
+  LAUNCH_CHECK("verify_kernel");
+  return PB_OK;
+}
+
+// host-pointer versions: chunks of PIPE_CHUNK items rotate over PIPE_SLOTS streams, so the copy engines and
+// the SMs work on different chunks at the same time
+static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, uint8_t* gt_unused, size_t n, int mode /*0 prove, 1 prove+verify*/) {
+  (void)gt_unused;
+  pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
+  DeviceGuard g(ctx->device);
+  std::lock_guard<std::mutex> lock(ctx->pipe_mu);
+  int rc = pipe_init(ctx);
+  if (rc) return rc;
+  size_t done = 0;
+  int slot = 0;
+  while (done < n) {
+    size_t m = n - done < PIPE_CHUNK ? n - done : PIPE_CHUNK;
+    PipeSlot& s = ctx->slots[slot];
+    CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, s.stream));
+    if (mode == 1) {
+      CU(cudaMemcpyAsync(s.u, u + done, m, cudaMemcpyHostToDevice, s.stream));
+      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, s.u, s.proofs, s.status, s.verdict, m, s.stream);
+    } else {
+      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, s.status, m, s.stream);
+    }
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(status + done, s.status, m, cudaMemcpyDeviceToHost, s.stream));
+    if (mode == 1) CU(cudaMemcpyAsync(verdict + done, s.verdict, m, cudaMemcpyDeviceToHost, s.stream));
+    done += m;
+    slot = (slot + 1) % PIPE_SLOTS;
+  }
+  for (auto& s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  return PB_OK;
+}
+int pb_plonk_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status, size_t n) {
+  ARG(ctx && witness && rnd && chal && proofs && status);
+  return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, nullptr, n, 0);
+}
+int pb_plonk_prove_verify(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                          uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n) {
+  ARG(ctx && witness && rnd && chal && u && proofs && status && verdict);
+  ARG(ctx->vk_valid);
+  return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, nullptr, n, 1);
+}
+int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+  ARG(ctx && proofs && chal && u && verdict);
+  DeviceGuard g(ctx->device);
+  DEV(dp, n * 34); DEV(dc, n * 5); DEV(du, n); DEV(dv, n); DEV(dg, n * 4);
+  H2D(dp, proofs, n * 34); H2D(dc, chal, n * 5); H2D(du, u, n);
+  int rc = pb_plonk_verify_dev(ctx, dp.as<uint8_t>(), dc.as<uint8_t>(), du.as<uint8_t>(), dv.as<uint8_t>(), gt ? dg.as<uint8_t>() : nullptr, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(verdict, dv, n);
+  if (gt) D2H(gt, dg, n * 4);
+  return PB_OK;
+}
+
+int pb_tally_dev(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t n, int64_t* counts, void* stream) {
+  ARG(counts);
+  if (n == 0) return PB_OK;
+  unsigned grid = blocks_for(n, BLOCK_LIGHT);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  tally_kernel<<<grid, BLOCK_LIGHT, 0, S(stream)>>>(proofs, status, verdict, n, reinterpret_cast<unsigned long long*>(counts));
+  LAUNCH_CHECK("tally_kernel");
+  return PB_OK;
+}
+
+}  // extern "C"

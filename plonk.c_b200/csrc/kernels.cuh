@@ -1,0 +1,643 @@
+// kernels.cuh -- __global__ entry points.  One item per thread everywhere: items are independent, a few
+// dozen bytes each, so there is no inter-thread communication beyond staging tables in shared memory.
+#pragma once
+#include "prover.cuh"
+#include "verifier.cuh"
+
+namespace pb {
+
+constexpr int BLOCK = 128;         // threads per block for the heavy kernels (prove / verify / pairing)
+constexpr int BLOCK_LIGHT = 256;   // for the byte-streaming kernels
+constexpr int POLY_MAX = 64;
+
+// Every block derives its own inverse tables: x^15 mod 17 is the reference's table (hf.h:145-180),
+// x^99 mod 101 is literally what gf_inv computes (gf.h:159-162).  ~150 thread-level pow calls per
+// block, amortised over >= 128 items of >= several hundred instructions each.
+PB_D void build_field_tables(FieldTables& ft) {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) ft.inv101[i] = i < 101 ? (uint8_t)pow101((uint32_t)i, 99) : 0;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) ft.inv17[i] = i < 17 ? (uint8_t)pow17((uint32_t)i, 15) : 0;
+}
+
+PB_D G1 load_g1(const uint8_t* p) { return G1{p[0], p[1], p[2] != 0 ? 1u : 0u}; }
+PB_D void store_g1(uint8_t* p, G1 g) { p[0] = (uint8_t)g.x; p[1] = (uint8_t)g.y; p[2] = (uint8_t)g.inf; }
+
+// ------------------------------------------------------------------ family (1)
+template <int FIELD>
+PB_D uint32_t field_apply(const FieldTables& ft, int op, uint32_t a, uint32_t b) {
+  if (FIELD == 17) {
+    switch (op) {
+      case 0: return add17(a, b);
+      case 1: return sub17(a, b);
+      case 2: return mul17(a, b);
+      case 3: return mul17(a, inv17(ft, b));
+      case 4: return neg17(a);
+      case 5: return inv17(ft, a);
+      default: return pow17(a, b);
+    }
+  } else {
+    switch (op) {
+      case 0: return add101(a, b);
+      case 1: return sub101(a, b);
+      case 2: return mul101(a, b);
+      case 3: return mul101(a, inv101(ft, b));
+      case 4: return neg101(a);
+      case 5: return inv101(ft, a);
+      default: return pow101(a, b);
+    }
+  }
+}
+
+// 16 elements per thread through 128-bit loads/stores; the tail (n % 16) is handled byte-wise by the last threads.
+template <int FIELD>
+__global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                               uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  const size_t nvec = n / 16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 va = reinterpret_cast<const uint4*>(a)[i];
+    uint4 vb = b ? reinterpret_cast<const uint4*>(b)[i] : make_uint4(0, 0, 0, 0);
+    uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w}, wo[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      uint32_t r = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        r |= field_apply<FIELD>(ft, op, (wa[w] >> (8 * k)) & 0xFFu, (wb[w] >> (8 * k)) & 0xFFu) << (8 * k);
+      wo[w] = r;
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+  for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (uint8_t)field_apply<FIELD>(ft, op, a[i], b ? b[i] : 0u);
+}
+
+// ------------------------------------------------------------------ family (2), generic shapes
+// Polynomials in per-thread local arrays; dynamic lengths.  (Fixed-shape fast paths: poly_fast.cuh.)
+struct LPoly { uint8_t c[2 * POLY_MAX]; int len; };
+
+PB_D void lp_load(LPoly& p, const uint8_t* row, int len) {      // poly_new: trim while len > 1 (poly.h:20-24)
+  while (len > 1 && row[len - 1] == 0) len--;
+  p.len = len;
+  for (int i = 0; i < len; i++) p.c[i] = row[i];
+}
+PB_D void lp_trim(LPoly& p) { while (p.len > 1 && p.c[p.len - 1] == 0) p.len--; }
+PB_D void lp_store(const LPoly& p, uint8_t* row, int stride, uint8_t* len) {
+  for (int i = 0; i < stride; i++) row[i] = i < p.len ? p.c[i] : 0;
+  *len = (uint8_t)p.len;
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_binop_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ alen, int sa,
+                                                                 const uint8_t* __restrict__ b, const uint8_t* __restrict__ blen, int sb,
+                                                                 uint8_t* __restrict__ out, uint8_t* __restrict__ olen, int so, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LPoly pa, pb, r;
+  lp_load(pa, a + i * sa, alen[i]);
+  lp_load(pb, b + i * sb, blen[i]);
+  if (op == 2) {                                                 // poly_mul, poly.h:106-122
+    r.len = pa.len + pb.len - 1;
+    for (int k = 0; k < r.len; k++) {
+      uint32_t s = 0;
+      int lo = k - (pb.len - 1) > 0 ? k - (pb.len - 1) : 0, hi = k < pa.len - 1 ? k : pa.len - 1;
+      for (int x = lo; x <= hi; x++) s += (uint32_t)pa.c[x] * pb.c[k - x];
+      r.c[k] = (uint8_t)red17(s);
+    }
+  } else {                                                       // poly_add / poly_sub, poly.h:72-104
+    r.len = pa.len > pb.len ? pa.len : pb.len;
+    for (int k = 0; k < r.len; k++) {
+      uint32_t x = k < pa.len ? pa.c[k] : 0u, y = k < pb.len ? pb.c[k] : 0u;
+      r.c[k] = (uint8_t)(op == 0 ? add17(x, y) : sub17(x, y));
+    }
+  }
+  lp_trim(r);
+  lp_store(r, out + i * so, so, olen + i);
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_divide_kernel(const uint8_t* __restrict__ num, const uint8_t* __restrict__ nlen, int sn,
+                                                                  const uint8_t* __restrict__ den, const uint8_t* __restrict__ dlen, int sd,
+                                                                  uint8_t* __restrict__ quot, uint8_t* __restrict__ qlen, int sq,
+                                                                  uint8_t* __restrict__ rem, uint8_t* __restrict__ rlen, int sr,
+                                                                  uint8_t* __restrict__ status, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LPoly pn, pd, q;
+  lp_load(pn, num + i * sn, nlen[i]);
+  lp_load(pd, den + i * sd, dlen[i]);
+  bool zero_den = true;                                          // poly_is_zero, poly.h:55-64
+  for (int k = 0; k < pd.len; k++) zero_den &= pd.c[k] == 0;
+  if (zero_den) {                                                // "Division by zero polynomial", poly.h:125-128
+    status[i] = 1;
+    for (int k = 0; k < sq; k++) quot[i * sq + k] = 0;
+    for (int k = 0; k < sr; k++) rem[i * sr + k] = 0;
+    qlen[i] = 0; rlen[i] = 0;
+    return;
+  }
+  status[i] = 0;
+  const int nl = pn.len, dl = pd.len;
+  for (int k = 0; k < nl; k++) q.c[k] = 0;
+  const uint32_t lead_inv = inv17(ft, pd.c[dl - 1]);
+  for (int k = nl - 1; k >= dl - 1; k--) {                       // long division, poly.h:147-155
+    uint32_t f = mul17(pn.c[k], lead_inv);
+    q.c[k - (dl - 1)] = (uint8_t)f;
+    for (int j = 0; j < dl; j++) pn.c[k - j] = (uint8_t)sub17(pn.c[k - j], mul17(f, pd.c[dl - 1 - j]));
+  }
+  q.len = nl >= dl ? nl - dl + 1 : 1;
+  if (nl < dl) q.c[0] = 0;
+  lp_trim(q);
+  int rl = dl - 1;                                               // poly.h:163-170; 0 when the divisor is a constant
+  if (rl > nl) rl = nl;
+  while (rl > 1 && pn.c[rl - 1] == 0) rl--;
+  pn.len = rl;
+  lp_store(q, quot + i * sq, sq, qlen + i);
+  lp_store(pn, rem + i * sr, sr, rlen + i);
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_eval_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen, int sp,
+                                                                const uint8_t* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* row = p + i * sp;
+  uint32_t y = 0, xv = x[i];
+  for (int k = (int)plen[i] - 1; k >= 0; k--) y = red17(y * xv + row[k]);   // Horner, poly.h:265-272
+  out[i] = (uint8_t)y;
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_unop_kernel(int op, const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen, int sp,
+                                                                const uint8_t* __restrict__ k, uint8_t* __restrict__ out,
+                                                                uint8_t* __restrict__ olen, int so, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LPoly a, r;
+  lp_load(a, p + i * sp, plen[i]);
+  uint32_t kv = k ? k[i] : 0u;
+  if (op == 0) {                                                 // poly_scale, poly.h:179-197: scalar 0 -> [0]
+    if (kv == 0) { r.len = 1; r.c[0] = 0; }
+    else { r.len = a.len; for (int j = 0; j < a.len; j++) r.c[j] = (uint8_t)mul17(a.c[j], kv); lp_trim(r); }
+  } else if (op == 1) {                                          // poly_negate, poly.h:240-254
+    r.len = a.len;
+    for (int j = 0; j < a.len; j++) r.c[j] = (uint8_t)neg17(a.c[j]);
+    lp_trim(r);
+  } else if (op == 2) {                                          // poly_shift, poly.h:199-216: zero stays [0]
+    bool z = true;
+    for (int j = 0; j < a.len; j++) z &= a.c[j] == 0;
+    if (z) { r.len = 1; r.c[0] = 0; }
+    else {
+      r.len = a.len + (int)kv;
+      for (int j = 0; j < r.len; j++) r.c[j] = j >= (int)kv ? a.c[j - kv] : 0;
+      lp_trim(r);
+    }
+  } else {                                                       // poly_add_hf, poly.h:67-70: in place, not trimmed
+    r = a;
+    r.c[0] = (uint8_t)add17(a.c[0], kv);
+  }
+  lp_store(r, out + i * so, so, olen + i);
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_slice_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen, int sp,
+                                                                 const uint8_t* __restrict__ start, const uint8_t* __restrict__ end,
+                                                                 uint8_t* __restrict__ out, uint8_t* __restrict__ olen, int so,
+                                                                 uint8_t* __restrict__ status, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LPoly a, r;
+  lp_load(a, p + i * sp, plen[i]);
+  int s = start[i], e = end[i];
+  if (s >= e || e > a.len) {                                     // "Invalid slice indices", poly.h:219-222
+    status[i] = 1; olen[i] = 0;
+    for (int j = 0; j < so; j++) out[i * so + j] = 0;
+    return;
+  }
+  status[i] = 0;
+  r.len = e - s;
+  for (int j = 0; j < r.len; j++) r.c[j] = a.c[s + j];
+  lp_trim(r);
+  lp_store(r, out + i * so, so, olen + i);
+}
+
+// poly_lagrange, poly.h:288-321 (product form, O(len^3)); len <= 16
+__global__ void __launch_bounds__(BLOCK_LIGHT) poly_lagrange_kernel(const uint8_t* __restrict__ xs, const uint8_t* __restrict__ ys, int len,
+                                                                    uint8_t* __restrict__ out, uint8_t* __restrict__ olen, int so,
+                                                                    uint8_t* __restrict__ status, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* x = xs + i * len;
+  const uint8_t* y = ys + i * len;
+  uint8_t l[17], lj[17], t[17];
+  for (int k = 0; k <= len; k++) l[k] = 0;
+  bool dup = false;
+  for (int j = 0; j < len && !dup; j++) {
+    int ljn = 1;
+    lj[0] = 1;
+    for (int m = 0; m < len; m++) {
+      if (m == j) continue;
+      uint32_t dinv = inv17(ft, sub17(x[j], x[m]));
+      if (dinv == 0) { dup = true; break; }                      // "x points must be unique", poly.h:298-301
+      uint32_t c0 = neg17(mul17(dinv, x[m]));
+      for (int k = 0; k <= ljn; k++) t[k] = 0;                  // lj *= (c0 + dinv x)
+      for (int k = 0; k < ljn; k++) {
+        t[k] = (uint8_t)add17(t[k], mul17(lj[k], c0));
+        t[k + 1] = (uint8_t)add17(t[k + 1], mul17(lj[k], dinv));
+      }
+      ljn++;
+      for (int k = 0; k < ljn; k++) lj[k] = t[k];
+    }
+    if (dup) break;
+    for (int k = 0; k < ljn; k++) l[k] = (uint8_t)add17(l[k], mul17(lj[k], y[j]));
+  }
+  if (dup) {
+    status[i] = 1; olen[i] = 0;
+    for (int k = 0; k < so; k++) out[i * so + k] = 0;
+    return;
+  }
+  status[i] = 0;
+  int ln = len;
+  while (ln > 1 && l[ln - 1] == 0) ln--;
+  for (int k = 0; k < so; k++) out[i * so + k] = k < ln ? l[k] : 0;
+  olen[i] = (uint8_t)ln;
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) interpolate_kernel(const __grid_constant__ CircuitConst cc, const uint8_t* __restrict__ vals,
+                                                                  uint8_t* __restrict__ out, uint8_t* __restrict__ olen, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w = reinterpret_cast<const uint32_t*>(vals)[i];
+  uint32_t v[4] = {w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24}, r[4];
+  interpolate(cc, v, r);
+  reinterpret_cast<uint32_t*>(out)[i] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+  olen[i] = (uint8_t)canon_len(r);
+}
+
+// matrix_mul, matrix.h:81-98; dims <= 8
+__global__ void __launch_bounds__(BLOCK_LIGHT) matrix_mul_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out,
+                                                                 int m, int k, int c, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* A = a + i * m * k;
+  const uint8_t* B = b + i * k * c;
+  uint8_t* O = out + i * m * c;
+  for (int r = 0; r < m; r++)
+    for (int j = 0; j < c; j++) {
+      uint32_t s = 0;
+      for (int x = 0; x < k; x++) s += (uint32_t)A[r * k + x] * B[x * c + j];
+      O[r * c + j] = (uint8_t)red17(s);
+    }
+}
+
+// matrix_inv = Gauss-Jordan on (M | I), matrix.h:100-176, including its pivot search order and its
+// lack of singularity detection; dim <= 8
+__global__ void __launch_bounds__(BLOCK_LIGHT) matrix_inv_kernel(const uint8_t* __restrict__ a, uint8_t* __restrict__ out, int dim, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t M[8 * 16];
+  const int rows = dim, cols = 2 * dim;
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) M[r * cols + c] = c < dim ? a[i * dim * dim + r * dim + c] : (c - dim == r ? 1 : 0);
+  int lead = 0;
+  bool done = false;
+  for (int r = 0; r < rows && !done; r++) {
+    if (cols <= lead) break;
+    int p = r;
+    while (M[p * cols + lead] == 0) {
+      p++;
+      if (p == rows) { p = r; lead++; if (lead == cols) { done = true; break; } }
+    }
+    if (done) break;
+    if (p != r) for (int c = 0; c < cols; c++) { uint8_t t = M[p * cols + c]; M[p * cols + c] = M[r * cols + c]; M[r * cols + c] = t; }
+    uint32_t d = M[r * cols + lead];
+    if (d != 0) { uint32_t di = inv17(ft, d); for (int c = 0; c < cols; c++) M[r * cols + c] = (uint8_t)mul17(M[r * cols + c], di); }
+    for (int q = 0; q < rows; q++) {
+      if (q == r) continue;
+      uint32_t mult = M[q * cols + lead];
+      for (int c = 0; c < cols; c++) M[q * cols + c] = (uint8_t)sub17(M[q * cols + c], mul17(M[r * cols + c], mult));
+    }
+    lead++;
+  }
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < dim; c++) out[i * dim * dim + r * dim + c] = M[r * cols + dim + c];
+}
+
+// ------------------------------------------------------------------ family (3)
+__global__ void __launch_bounds__(BLOCK_LIGHT) g1_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                            uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1 x = load_g1(a + 3 * i), r;
+  if (op == 0) r = g1_add(ft, x, load_g1(b + 3 * i));
+  else if (op == 1) r = g1_double(ft, x);
+  else r = g1_neg(x);
+  store_g1(out + 3 * i, r);
+}
+
+template <typename S>
+__global__ void __launch_bounds__(BLOCK) g1_mul_kernel(const uint8_t* __restrict__ p, const S* __restrict__ s, uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_g1(out + 3 * i, g1_mul(ft, load_g1(p + 3 * i), (uint64_t)s[i]));
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) g1_on_curve_kernel(const uint8_t* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = g1_is_on_curve(load_g1(p + 3 * i)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BLOCK_LIGHT) g2_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                            uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2 x{a[2 * i], a[2 * i + 1]}, r;
+  if (op == 0) r = g2_add(ft, x, G2{b[2 * i], b[2 * i + 1]});
+  else r = g2_neg(x);
+  out[2 * i] = (uint8_t)r.x; out[2 * i + 1] = (uint8_t)r.y;
+}
+
+__global__ void __launch_bounds__(BLOCK) g2_mul_kernel(const uint8_t* __restrict__ p, const uint64_t* __restrict__ s, uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2 r = g2_mul(ft, G2{p[2 * i], p[2 * i + 1]}, s[i]);
+  out[2 * i] = (uint8_t)r.x; out[2 * i + 1] = (uint8_t)r.y;
+}
+
+// T[i][c] = g1_mul(g1s[i], c), the reference's own double-and-add (context creation)
+__global__ void srs_table_kernel(const uint8_t* __restrict__ g1s, uint32_t srs_len, uint32_t rows, uint32_t* __restrict__ T) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < rows * 17u; k += blockDim.x) {
+    uint32_t i = k / 17u, c = k % 17u;
+    G1 r = i < srs_len ? g1_mul(ft, load_g1(g1s + 3 * i), c) : g1_identity();
+    T[k] = pack_g1(r.x, r.y, r.inf);
+  }
+}
+
+// srs_eval_at_s (srs.h:53-68) for arbitrary polynomials against the context's full table
+__global__ void __launch_bounds__(BLOCK) commit_kernel(const uint32_t* __restrict__ Tg, uint32_t srs_len, const uint8_t* __restrict__ polys,
+                                                       const uint8_t* __restrict__ plen, int sp, uint8_t* __restrict__ out,
+                                                       uint8_t* __restrict__ status, size_t n) {
+  extern __shared__ uint32_t Ts[];
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  for (uint32_t k = threadIdx.x; k < srs_len * 17u; k += blockDim.x) Ts[k] = Tg[k];
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* row = polys + i * sp;
+  int len = plen[i];
+  while (len > 1 && row[len - 1] == 0) len--;                   // poly_new trims first
+  if ((uint32_t)len > srs_len) {                                 // "exceeds SRS size", srs.h:54-57
+    status[i] = 1;
+    out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0;
+    return;
+  }
+  status[i] = 0;
+  G1 acc = g1_identity();
+  for (int k = 0; k < len; k++) acc = g1_add(ft, acc, unpack_g1(Ts[k * 17 + row[k]]));
+  store_g1(out + 3 * i, acc);
+}
+
+// ------------------------------------------------------------------ family (4)
+__global__ void __launch_bounds__(BLOCK_LIGHT) gtp_mul_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GT r = gt_mul(GT{a[2 * i], a[2 * i + 1]}, GT{b[2 * i], b[2 * i + 1]});
+  out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b;
+}
+__global__ void __launch_bounds__(BLOCK_LIGHT) gtp_pow_kernel(const uint8_t* __restrict__ a, const uint64_t* __restrict__ e, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GT r = gt_pow(GT{a[2 * i], a[2 * i + 1]}, e[i]);
+  out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b;
+}
+__global__ void __launch_bounds__(BLOCK_LIGHT) line_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Line l = line_through(load_g1(a + 3 * i), load_g1(b + 3 * i));
+  out[3 * i] = (uint8_t)l.x; out[3 * i + 1] = (uint8_t)l.y; out[3 * i + 2] = (uint8_t)l.c;
+}
+__global__ void __launch_bounds__(BLOCK) pairing_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ q, uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GT r = pairing17(ft, load_g1(p + 3 * i), G2{q[2 * i], q[2 * i + 1]});
+  out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b;
+}
+__global__ void __launch_bounds__(BLOCK) pairing_f_kernel(uint64_t r, const uint8_t* __restrict__ p, const uint8_t* __restrict__ q, uint8_t* __restrict__ out, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GT f = miller(ft, r, load_g1(p + 3 * i), G2{q[2 * i], q[2 * i + 1]});
+  out[2 * i] = (uint8_t)f.a; out[2 * i + 1] = (uint8_t)f.b;
+}
+
+// ------------------------------------------------------------------ protocol
+__global__ void __launch_bounds__(BLOCK_LIGHT) satisfy_kernel(const __grid_constant__ CircuitConst cc, const uint8_t* __restrict__ wit,
+                                                              uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* w = wit + 12 * i;
+  bool ok = true;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    uint32_t a = w[g], b = w[4 + g], c = w[8 + g];
+    ok &= red17(cc.qv[0][g] * a + cc.qv[1][g] * b + cc.qv[2][g] * c + cc.qv[3][g] * (a * b) + cc.qv[4][g]) == 0u;
+  }
+  out[i] = ok ? 1 : 0;
+}
+
+// plonk_prove over a batch.  Shared memory: the per-lane-indexed tables, and a staging area through
+// which the block's contiguous slice of every input and output array moves with 128-bit accesses
+// (item records are 12 / 9 / 5 / 34 bytes -- per-thread byte accesses to global memory would cost one
+// sector per byte on the store side).
+template <int ITEM, int NT>
+PB_D void stage_in(uint8_t* smem, const uint8_t* __restrict__ g, size_t first, size_t n) {
+  // bytes [first*ITEM, min(first+NT, n)*ITEM) -> smem[0..]; the block base is 16-byte aligned because
+  // first is a multiple of NT and NT*ITEM is a multiple of 16
+  const size_t cnt = (n - first < (size_t)NT ? n - first : (size_t)NT) * ITEM;
+  const uint8_t* src = g + first * ITEM;
+  const size_t nv = cnt / 16;
+  for (size_t k = threadIdx.x; k < nv; k += NT) reinterpret_cast<uint4*>(smem)[k] = reinterpret_cast<const uint4*>(src)[k];
+  for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) smem[k] = src[k];
+}
+template <int ITEM, int NT>
+PB_D void stage_out(uint8_t* __restrict__ g, const uint8_t* smem, size_t first, size_t n) {
+  const size_t cnt = (n - first < (size_t)NT ? n - first : (size_t)NT) * ITEM;
+  uint8_t* dst = g + first * ITEM;
+  const size_t nv = cnt / 16;
+  for (size_t k = threadIdx.x; k < nv; k += NT) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(smem)[k];
+  for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) dst[k] = smem[k];
+}
+
+struct __align__(16) ProveSmem {
+  __align__(16) ProverTables tb;
+  __align__(16) uint8_t wit[BLOCK * 12];
+  __align__(16) uint8_t rnd[BLOCK * 9];
+  __align__(16) uint8_t chal[BLOCK * 5];
+  __align__(16) uint8_t proof[BLOCK * 34];
+  __align__(16) uint8_t status[BLOCK];
+};
+
+__global__ void __launch_bounds__(BLOCK) prove_kernel(const __grid_constant__ CircuitConst cc, const ProverTables* __restrict__ gtb,
+                                                      const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
+                                                      const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
+                                                      uint8_t* __restrict__ status, size_t n) {
+  __shared__ ProveSmem sm;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < (int)(sizeof(ProverTables) / 4); k += BLOCK)
+    reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
+  const size_t first = (size_t)blockIdx.x * BLOCK;
+  stage_in<12, BLOCK>(sm.wit, wit, first, n);
+  stage_in<9, BLOCK>(sm.rnd, rnd, first, n);
+  stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  __syncthreads();
+  const bool live = first + tid < n;
+  uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { wa[k] = sm.wit[tid * 12 + k]; wb[k] = sm.wit[tid * 12 + 4 + k]; wc[k] = sm.wit[tid * 12 + 8 + k]; }
+#pragma unroll
+  for (int k = 0; k < 9; k++) r[k] = sm.rnd[tid * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) bad |= wa[k] > 16u || wb[k] > 16u || wc[k] > 16u;
+#pragma unroll
+  for (int k = 0; k < 9; k++) bad |= r[k] > 16u;
+#pragma unroll
+  for (int k = 0; k < 5; k++) bad |= ch[k] > 16u;
+  if (bad || !live) {   // keep table indices in range; the item is reported as PB_PROVE_BAD_INPUT
+#pragma unroll
+    for (int k = 0; k < 4; k++) { wa[k] = 0; wb[k] = 0; wc[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = 0;
+  }
+  ProofOut o;
+  prove_one(cc, sm.tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+  if (bad) o.status = 254u;
+  uint8_t* po = sm.proof + tid * 34;
+  const bool okp = o.status == 0u;     // a failed item's PROOF bytes are zero
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    po[3 * j] = okp ? (uint8_t)o.pts[j].x : 0;
+    po[3 * j + 1] = okp ? (uint8_t)o.pts[j].y : 0;
+    po[3 * j + 2] = okp ? (uint8_t)o.pts[j].inf : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < 7; j++) po[27 + j] = okp ? (uint8_t)o.sc[j] : 0;
+  sm.status[tid] = (uint8_t)o.status;
+  __syncthreads();
+  stage_out<34, BLOCK>(proofs, sm.proof, first, n);
+  stage_out<1, BLOCK>(status, sm.status, first, n);
+}
+
+struct __align__(16) VerifySmem {
+  __align__(16) FieldTables ft;
+  __align__(16) uint8_t proof[BLOCK * 34];
+  __align__(16) uint8_t chal[BLOCK * 5];
+};
+
+// status (optional): items whose status byte is non-zero are skipped and get verdict 0xFF
+__global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ VerifyKey key, const uint8_t* __restrict__ proofs,
+                                                       const uint8_t* __restrict__ chal, const uint8_t* __restrict__ u,
+                                                       const uint8_t* __restrict__ status, uint8_t* __restrict__ verdict,
+                                                       uint8_t* __restrict__ gt, size_t n) {
+  __shared__ VerifySmem sm;
+  const int tid = threadIdx.x;
+  build_field_tables(sm.ft);
+  const size_t first = (size_t)blockIdx.x * BLOCK;
+  stage_in<34, BLOCK>(sm.proof, proofs, first, n);
+  stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  __syncthreads();
+  const size_t i = first + tid;
+  if (i >= n) return;
+  if (status && status[i] != 0) {
+    verdict[i] = 0xFF;
+    if (gt) reinterpret_cast<uint32_t*>(gt)[i] = 0u;
+    return;
+  }
+  uint32_t pbytes[27], op[7], ch[5];
+#pragma unroll
+  for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+#pragma unroll
+  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+  VerifyOut o;
+  verify_one(key, sm.ft, pbytes, op, ch, u[i], o);
+  verdict[i] = (uint8_t)o.verdict;
+  if (gt) reinterpret_cast<uint32_t*>(gt)[i] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+}
+
+// the eight preprocessed commitments of the verifier key: srs_eval_at_s of the interpolated selector and
+// permutation polynomials (context creation; one thread each)
+__global__ void verifier_key_kernel(const uint32_t* __restrict__ Tg, uint32_t srs_len, const uint8_t* __restrict__ polys /*[8][4]*/,
+                                    uint32_t* __restrict__ out /*[8] packed, 0xFFFFFFFF = longer than the SRS*/) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  if (threadIdx.x >= 8) return;
+  const uint8_t* row = polys + 4 * threadIdx.x;
+  int len = 4;
+  while (len > 1 && row[len - 1] == 0) len--;
+  if ((uint32_t)len > srs_len) { out[threadIdx.x] = 0xFFFFFFFFu; return; }
+  G1 acc = g1_identity();
+  for (int k = 0; k < len; k++) acc = g1_add(ft, acc, unpack_g1(Tg[k * 17 + row[k]]));
+  out[threadIdx.x] = pack_g1(acc.x, acc.y, acc.inf);
+}
+
+// counts[s] += #status==s (s < 15; 15 = other), counts[16] += #verdict==1, counts[17] += sum of proof bytes
+__global__ void __launch_bounds__(BLOCK_LIGHT) tally_kernel(const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ status,
+                                                            const uint8_t* __restrict__ verdict, size_t n, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long sc[18];
+  if (threadIdx.x < 18) sc[threadIdx.x] = 0ull;
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned long long sum = 0ull;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t s = status ? status[i] : 0u;
+    atomicAdd(&sc[s < 15u ? s : 15u], 1ull);
+    if (verdict && verdict[i] == 1) atomicAdd(&sc[16], 1ull);
+  }
+  if (proofs) {
+    const size_t words = n * 34 / 4;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += stride) {
+      uint32_t w = reinterpret_cast<const uint32_t*>(proofs)[k];
+      sum += (w & 0xFFu) + ((w >> 8) & 0xFFu) + ((w >> 16) & 0xFFu) + (w >> 24);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) for (size_t k = words * 4; k < n * 34; k++) sum += proofs[k];
+    atomicAdd(&sc[17], sum);
+  }
+  __syncthreads();
+  if (threadIdx.x < 18 && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+
+}  // namespace pb

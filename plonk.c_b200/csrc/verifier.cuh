@@ -1,0 +1,102 @@
+// verifier.cuh -- plonk_verify.  NOT in the reference (plonk.h ends at plonk_prove, plonk.h:656-659):
+// parity is unpinned against the reference and pinned against oracle/verify_spec.inc, the textbook
+// PLONK verifier stated over the reference's primitives.  This file follows that specification step
+// by step and performs the same group operations in the same order, each of them the exact
+// emulation of g1_mul / g1_add / g1_neg / pairing from curve.cuh.
+#pragma once
+#include "curve.cuh"
+
+namespace pb {
+
+// Preprocessed verifier key, passed by value (uniform, constant bank).
+struct VerifyKey {
+  G1 qm, ql, qr, qo, qc, s1, s2, s3;   // srs_eval_at_s of the interpolated selector / permutation polynomials
+  G1 g1_one;                           // srs.g1s[0]
+  G2 g2_one, g2_s;                     // srs.g2_1, srs.g2_s
+};
+
+struct VerifyOut {
+  uint32_t verdict;   // 1 accept, 0 pairing mismatch, 2 bad commitment encoding / off curve, 3 bad scalar byte
+  GT lhs, rhs;
+};
+
+// proof: 34 bytes already unpacked into registers (27 commitment bytes, 7 openings)
+PB_HD void verify_one(const VerifyKey& k, const FieldTables& ft, const uint32_t (&pb)[27], const uint32_t (&op)[7],
+                     const uint32_t (&ch)[5], uint32_t u, VerifyOut& out) {
+  out.lhs = GT{0u, 0u};
+  out.rhs = GT{0u, 0u};
+  // step 1: encodings and curve membership (y^2 = x^3 + 3, g1.h:26-31)
+  bool bad_pt = false;
+  G1 P[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    uint32_t x = pb[3 * j], y = pb[3 * j + 1], f = pb[3 * j + 2];
+    bad_pt |= x > 100u || y > 100u || f > 1u || (f == 1u && (x | y) != 0u);
+    P[j] = G1{x > 100u ? 0u : x, y > 100u ? 0u : y, f != 0u ? 1u : 0u};   // clamp so that table look-ups stay in range
+    bad_pt |= !g1_is_on_curve(P[j]);
+  }
+  // step 2: openings and challenges are field elements
+  bool bad_sc = u > 16u;
+#pragma unroll
+  for (int j = 0; j < 7; j++) bad_sc |= op[j] > 16u;
+#pragma unroll
+  for (int j = 0; j < 5; j++) bad_sc |= ch[j] > 16u;
+  if (bad_pt) { out.verdict = 2u; return; }
+  if (bad_sc) { out.verdict = 3u; return; }
+
+  const uint32_t a_z = op[0], b_z = op[1], c_z = op[2], s1_z = op[3], s2_z = op[4], r_z = op[5], zw_z = op[6];
+  const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
+  constexpr uint32_t K1 = 2u, K2 = 3u, OMEGA = 4u;
+
+  // steps 4-6
+  const uint32_t z2 = red17(z * z), z3 = red17(z2 * z), z4 = red17(z2 * z2);
+  const uint32_t zh_z = sub17(z4, 1u);
+  const uint32_t l1_z = red17(13u * (1u + z + z2 + z3));
+  const uint32_t alpha2 = red17(alpha * alpha);
+  // step 7
+  const uint32_t pa = red17(a_z + beta * s1_z + gamma), pbb = red17(b_z + beta * s2_z + gamma);
+  const uint32_t pab = red17(pa * pbb);
+  const uint32_t perm = red17(red17(red17(pab * red17(c_z + gamma)) * zw_z) * alpha);
+  const uint32_t t_num = red17(r_z + 2u * P17 - perm - red17(l1_z * alpha2));
+  const uint32_t t_z = red17(t_num * inv17(ft, zh_z));
+  // step 8 scalars
+  const uint32_t bz = red17(beta * z);
+  const uint32_t ga = red17(a_z + bz + gamma), gb = red17(b_z + K1 * bz + gamma), gc = red17(c_z + K2 * bz + gamma);
+  const uint32_t d_z = red17(red17(red17(red17(red17(ga * gb) * gc) * alpha) * v) + red17(red17(l1_z * alpha2) * v) + u);
+  const uint32_t d_s3 = red17(red17(red17(red17(pab * alpha) * v) * beta) * zw_z);
+
+  G1 D = g1_add(ft, g1_mul(ft, k.qm, red17(red17(a_z * b_z) * v)), g1_mul(ft, k.ql, red17(a_z * v)));
+  D = g1_add(ft, D, g1_mul(ft, k.qr, red17(b_z * v)));
+  D = g1_add(ft, D, g1_mul(ft, k.qo, red17(c_z * v)));
+  D = g1_add(ft, D, g1_mul(ft, k.qc, v));
+  D = g1_add(ft, D, g1_mul(ft, P[3], d_z));
+  D = g1_add(ft, D, g1_neg(g1_mul(ft, k.s3, d_s3)));
+
+  // step 9
+  const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
+  const uint32_t z6 = red17(z4 * z2), z12 = red17(z6 * z6);
+  G1 F = g1_add(ft, P[4], g1_mul(ft, P[5], z6));
+  F = g1_add(ft, F, g1_mul(ft, P[6], z12));
+  F = g1_add(ft, F, D);
+  F = g1_add(ft, F, g1_mul(ft, P[0], v2));
+  F = g1_add(ft, F, g1_mul(ft, P[1], v3));
+  F = g1_add(ft, F, g1_mul(ft, P[2], v4));
+  F = g1_add(ft, F, g1_mul(ft, k.s1, v5));
+  F = g1_add(ft, F, g1_mul(ft, k.s2, v6));
+
+  // step 10
+  const uint32_t e = red17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);
+  G1 E = g1_mul(ft, k.g1_one, e);
+
+  // step 11
+  G1 lhs_p = g1_add(ft, P[7], g1_mul(ft, P[8], u));
+  G1 rhs_p = g1_add(ft, g1_mul(ft, P[7], z), g1_mul(ft, P[8], red17(red17(u * z) * OMEGA)));
+  rhs_p = g1_add(ft, rhs_p, F);
+  rhs_p = g1_add(ft, rhs_p, g1_neg(E));
+
+  out.lhs = pairing17(ft, lhs_p, k.g2_s);
+  out.rhs = pairing17(ft, rhs_p, k.g2_one);
+  out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;   // gtp_equal, pairing.h:9-11
+}
+
+}  // namespace pb

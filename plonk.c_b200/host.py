@@ -1,0 +1,457 @@
+"""ctypes binding of the C ABI (include/plonk_b200.h) -- the host-side mirror of the reference's header API.
+
+Every function takes either numpy arrays (HOST path: the library copies in, launches, copies out) or
+torch CUDA tensors (DEVICE path: `*_dev` entry points, enqueued on torch's current stream, outputs are
+torch tensors).  Names follow the reference: poly_mul, poly_divide, poly_eval, interpolate_at_h, g1_mul,
+srs_eval_at_s, pairing, plonk_prove ... (src/poly.h, src/g1.h, src/srs.h, src/pairing.h, src/plonk.h).
+
+There is no fallback: if the shared library is missing, or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+
+PB_OK, PB_ERR_NO_DEVICE, PB_ERR_CUDA, PB_ERR_ARG = 0, -1, -2, -3
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_INV, OP_POW = range(7)
+POLY_ADD, POLY_SUB, POLY_MUL = range(3)
+POLY_SCALE, POLY_NEGATE, POLY_SHIFT, POLY_ADD_HF = range(4)
+G_ADD, G_DOUBLE, G_NEG = range(3)
+
+
+class PlonkB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libplonk_b200.so (built by __graft_entry__.build()).  Fails loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pb_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PlonkB200Error(rc, lib().pb_last_error().decode())
+
+
+def device_count():
+    n = lib().pb_device_count()
+    if n < 0:
+        _check(n)
+    return n
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Call:
+    """Marshals one C-ABI call: numpy arrays -> host entry point, torch CUDA tensors -> `_dev` entry point."""
+
+    def __init__(self, name, *inputs):
+        self.name = name
+        self.dev = any(_is_torch(x) for x in inputs if x is not None)
+        self.keep = []
+        if self.dev:
+            import torch
+            self.torch = torch
+            self.device = next(x.device for x in inputs if x is not None and _is_torch(x))
+
+    def inp(self, x, dtype=np.uint8):
+        if x is None:
+            return None
+        if self.dev:
+            t = x
+            if not _is_torch(t):
+                t = self.torch.as_tensor(np.ascontiguousarray(x, dtype=dtype), device=self.device)
+            want = self.torch.uint8 if dtype == np.uint8 else self.torch.int64
+            if dtype == np.uint64 and t.dtype in (self.torch.uint64,):
+                pass
+            elif t.dtype != want:
+                t = t.to(want)
+            t = t.contiguous()
+            self.keep.append(t)
+            return C.c_void_p(t.data_ptr())
+        a = np.ascontiguousarray(x, dtype=dtype)
+        self.keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    def out(self, shape, dtype=np.uint8):
+        if self.dev:
+            t = self.torch.empty(shape, dtype=self.torch.uint8 if dtype == np.uint8 else self.torch.int64, device=self.device)
+            self.keep.append(t)
+            return t, C.c_void_p(t.data_ptr())
+        a = np.empty(shape, dtype=dtype)
+        self.keep.append(a)
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    def run(self, *args):
+        fn = getattr(lib(), self.name + ("_dev" if self.dev else ""))
+        fn.restype = C.c_int
+        if self.dev:
+            with self.torch.cuda.device(self.device):
+                stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+                _check(fn(*args, stream))
+        else:
+            _check(fn(*args))
+
+
+def _n(x):
+    return int(x.shape[0])
+
+
+# ---------------------------------------------------------------- family (1): hf.h / gf.h
+def field_op(field, op, a, b=None):
+    c = _Call("pb_field_op", a, b)
+    n = int(np.prod(a.shape))
+    out, po = c.out(tuple(a.shape))
+    c.run(C.c_int(field), C.c_int(op), c.inp(a), c.inp(b), po, C.c_size_t(n))
+    return out
+
+
+def hf_add(a, b): return field_op(17, OP_ADD, a, b)
+def hf_sub(a, b): return field_op(17, OP_SUB, a, b)
+def hf_mul(a, b): return field_op(17, OP_MUL, a, b)
+def hf_div(a, b): return field_op(17, OP_DIV, a, b)
+def hf_neg(a): return field_op(17, OP_NEG, a)
+def hf_inv(a): return field_op(17, OP_INV, a)
+def hf_pow(a, e): return field_op(17, OP_POW, a, e)
+def gf_add(a, b): return field_op(101, OP_ADD, a, b)
+def gf_sub(a, b): return field_op(101, OP_SUB, a, b)
+def gf_mul(a, b): return field_op(101, OP_MUL, a, b)
+def gf_div(a, b): return field_op(101, OP_DIV, a, b)
+def gf_neg(a): return field_op(101, OP_NEG, a)
+def gf_inv(a): return field_op(101, OP_INV, a)
+def gf_pow(a, e): return field_op(101, OP_POW, a, e)
+
+
+# ---------------------------------------------------------------- family (2): poly.h / matrix.h
+def poly_binop(op, a, alen, b, blen, so=None):
+    c = _Call("pb_poly_binop", a, b)
+    n, sa, sb = _n(a), int(a.shape[1]), int(b.shape[1])
+    if so is None:
+        so = sa + sb - 1 if op == POLY_MUL else max(sa, sb)
+    out, po = c.out((n, so))
+    olen, pl = c.out((n,))
+    c.run(C.c_int(op), c.inp(a), c.inp(alen), C.c_size_t(sa), c.inp(b), c.inp(blen), C.c_size_t(sb), po, pl,
+          C.c_size_t(so), C.c_size_t(n))
+    return out, olen
+
+
+def poly_add(a, alen, b, blen, so=None): return poly_binop(POLY_ADD, a, alen, b, blen, so)
+def poly_sub(a, alen, b, blen, so=None): return poly_binop(POLY_SUB, a, alen, b, blen, so)
+def poly_mul(a, alen, b, blen, so=None): return poly_binop(POLY_MUL, a, alen, b, blen, so)
+
+
+def poly_divide(num, nlen, den, dlen, sq=None, sr=None):
+    c = _Call("pb_poly_divide", num, den)
+    n, sn, sd = _n(num), int(num.shape[1]), int(den.shape[1])
+    sq = sn if sq is None else sq
+    sr = max(sd - 1, 1) if sr is None else sr
+    quot, pq = c.out((n, sq))
+    qlen, pql = c.out((n,))
+    rem, pr = c.out((n, sr))
+    rlen, prl = c.out((n,))
+    status, ps = c.out((n,))
+    c.run(c.inp(num), c.inp(nlen), C.c_size_t(sn), c.inp(den), c.inp(dlen), C.c_size_t(sd), pq, pql, C.c_size_t(sq),
+          pr, prl, C.c_size_t(sr), ps, C.c_size_t(n))
+    return quot, qlen, rem, rlen, status
+
+
+def poly_eval(p, plen, x):
+    c = _Call("pb_poly_eval", p, x)
+    n = _n(p)
+    out, po = c.out((n,))
+    c.run(c.inp(p), c.inp(plen), C.c_size_t(int(p.shape[1])), c.inp(x), po, C.c_size_t(n))
+    return out
+
+
+def poly_unop(op, p, plen, k, so):
+    c = _Call("pb_poly_unop", p)
+    n = _n(p)
+    out, po = c.out((n, so))
+    olen, pl = c.out((n,))
+    c.run(C.c_int(op), c.inp(p), c.inp(plen), C.c_size_t(int(p.shape[1])), c.inp(k), po, pl, C.c_size_t(so), C.c_size_t(n))
+    return out, olen
+
+
+def poly_scale(p, plen, k, so=None): return poly_unop(POLY_SCALE, p, plen, k, so or int(p.shape[1]))
+def poly_negate(p, plen, so=None): return poly_unop(POLY_NEGATE, p, plen, None, so or int(p.shape[1]))
+def poly_shift(p, plen, k, so): return poly_unop(POLY_SHIFT, p, plen, k, so)
+def poly_add_hf(p, plen, k, so=None): return poly_unop(POLY_ADD_HF, p, plen, k, so or int(p.shape[1]))
+
+
+def poly_slice(p, plen, start, end, so=None):
+    c = _Call("pb_poly_slice", p)
+    n = _n(p)
+    so = so or int(p.shape[1])
+    out, po = c.out((n, so))
+    olen, pl = c.out((n,))
+    status, ps = c.out((n,))
+    c.run(c.inp(p), c.inp(plen), C.c_size_t(int(p.shape[1])), c.inp(start), c.inp(end), po, pl, C.c_size_t(so), ps, C.c_size_t(n))
+    return out, olen, status
+
+
+def poly_lagrange(xs, ys, so=None):
+    c = _Call("pb_poly_lagrange", xs, ys)
+    n, ln = _n(xs), int(xs.shape[1])
+    so = so or ln
+    out, po = c.out((n, so))
+    olen, pl = c.out((n,))
+    status, ps = c.out((n,))
+    c.run(c.inp(xs), c.inp(ys), C.c_size_t(ln), po, pl, C.c_size_t(so), ps, C.c_size_t(n))
+    return out, olen, status
+
+
+def matrix_mul(a, b):
+    """a: [n][m][k], b: [n][k][c] -> [n][m][c]   (matrix_mul, matrix.h:81-98)"""
+    c = _Call("pb_matrix_mul", a, b)
+    n, m, k, cc = _n(a), int(a.shape[1]), int(a.shape[2]), int(b.shape[2])
+    out, po = c.out((n, m, cc))
+    c.run(c.inp(a), c.inp(b), po, C.c_uint32(m), C.c_uint32(k), C.c_uint32(cc), C.c_size_t(n))
+    return out
+
+
+def matrix_inv(a):
+    """a: [n][d][d] -> [n][d][d]   (matrix_inv, matrix.h:151-176)"""
+    c = _Call("pb_matrix_inv", a)
+    n, d = _n(a), int(a.shape[1])
+    out, po = c.out((n, d, d))
+    c.run(c.inp(a), po, C.c_uint32(d), C.c_size_t(n))
+    return out
+
+
+# ---------------------------------------------------------------- family (3): g1.h / g2.h
+def g1_op(op, a, b=None):
+    c = _Call("pb_g1_op", a, b)
+    n = _n(a)
+    out, po = c.out((n, 3))
+    c.run(C.c_int(op), c.inp(a), c.inp(b), po, C.c_size_t(n))
+    return out
+
+
+def g1_add(a, b): return g1_op(G_ADD, a, b)
+def g1_double(a): return g1_op(G_DOUBLE, a)
+def g1_neg(a): return g1_op(G_NEG, a)
+
+
+def g1_mul(points, scalars):
+    """g1_mul (g1.h:91-103).  scalars: uint64 (raw, never reduced) or uint8."""
+    is_u8 = (scalars.dtype == np.uint8) if not _is_torch(scalars) else (str(scalars.dtype) == "torch.uint8")
+    c = _Call("pb_g1_mul_u8" if is_u8 else "pb_g1_mul", points, scalars)
+    n = _n(points)
+    out, po = c.out((n, 3))
+    c.run(c.inp(points), c.inp(scalars, np.uint8 if is_u8 else np.uint64), po, C.c_size_t(n))
+    return out
+
+
+def g1_is_on_curve(points):
+    c = _Call("pb_g1_is_on_curve", points)
+    n = _n(points)
+    out, po = c.out((n,))
+    c.run(c.inp(points), po, C.c_size_t(n))
+    return out
+
+
+def g2_op(op, a, b=None):
+    c = _Call("pb_g2_op", a, b)
+    n = _n(a)
+    out, po = c.out((n, 2))
+    c.run(C.c_int(op), c.inp(a), c.inp(b), po, C.c_size_t(n))
+    return out
+
+
+def g2_add(a, b): return g2_op(G_ADD, a, b)
+def g2_neg(a): return g2_op(G_NEG, a)
+
+
+def g2_mul(points, scalars):
+    c = _Call("pb_g2_mul", points, scalars)
+    n = _n(points)
+    out, po = c.out((n, 2))
+    c.run(c.inp(points), c.inp(scalars, np.uint64), po, C.c_size_t(n))
+    return out
+
+
+# ---------------------------------------------------------------- family (4): gt.h / pairing.h
+def gtp_mul(a, b):
+    c = _Call("pb_gtp_mul", a, b)
+    n = _n(a)
+    out, po = c.out((n, 2))
+    c.run(c.inp(a), c.inp(b), po, C.c_size_t(n))
+    return out
+
+
+def gtp_pow(a, e):
+    c = _Call("pb_gtp_pow", a, e)
+    n = _n(a)
+    out, po = c.out((n, 2))
+    c.run(c.inp(a), c.inp(e, np.uint64), po, C.c_size_t(n))
+    return out
+
+
+def line(a, b):
+    c = _Call("pb_line", a, b)
+    n = _n(a)
+    out, po = c.out((n, 3))
+    c.run(c.inp(a), c.inp(b), po, C.c_size_t(n))
+    return out
+
+
+def pairing(p, q):
+    c = _Call("pb_pairing", p, q)
+    n = _n(p)
+    out, po = c.out((n, 2))
+    c.run(c.inp(p), c.inp(q), po, C.c_size_t(n))
+    return out
+
+
+def pairing_f(r, p, q):
+    c = _Call("pb_pairing_f", p, q)
+    n = _n(p)
+    out, po = c.out((n, 2))
+    c.run(C.c_uint64(r), c.inp(p), c.inp(q), po, C.c_size_t(n))
+    return out
+
+
+# ---------------------------------------------------------------- context: plonk_new + circuit constants
+class Plonk:
+    """One circuit + one SRS on one device: the batch counterpart of the reference's PLONK struct
+    (plonk.h:43-51) together with CONSTRAINTS (constraints.h:35-47)."""
+
+    def __init__(self, circuit, srs_g1s, srs_g2, device=0):
+        circuit = np.ascontiguousarray(circuit, dtype=np.uint8)
+        g1s = np.ascontiguousarray(srs_g1s, dtype=np.uint8)
+        g2 = np.ascontiguousarray(srs_g2, dtype=np.uint8)
+        assert circuit.size == 44 and g1s.ndim == 2 and g1s.shape[1] == 3 and g2.size == 4
+        self.srs_len = int(g1s.shape[0])
+        self.device = device
+        self._h = C.c_void_p()
+        fn = lib().pb_ctx_create
+        fn.restype = C.c_int
+        _check(fn(C.byref(self._h), C.c_int(device), circuit.ctypes.data_as(u8p), g1s.ctypes.data_as(u8p),
+                  C.c_uint32(self.srs_len), g2.ctypes.data_as(u8p)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().pb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setup_dump(self):
+        out = np.zeros(37, np.uint8)
+        _check(lib().pb_ctx_setup_dump(self._h, out.ctypes.data_as(u8p)))
+        return dict(h=out[0:4].copy(), k1_h=out[4:8].copy(), k2_h=out[8:12].copy(),
+                    h_pows_inv=out[12:28].reshape(4, 4).copy(), z_h=out[28:28 + out[36]].copy())
+
+    def circuit_dump(self):
+        out = np.zeros(48, np.uint8)
+        _check(lib().pb_ctx_circuit_dump(self._h, out.ctypes.data_as(u8p)))
+        return dict(sigma=out[0:12].reshape(3, 4).copy(), s_sigma=out[12:24].reshape(3, 4).copy(),
+                    q_polys=out[24:44].reshape(5, 4).copy(), l1=out[44:48].copy())
+
+    def verifier_key(self):
+        out = np.zeros(27, np.uint8)
+        _check(lib().pb_ctx_verifier_key(self._h, out.ctypes.data_as(u8p)))
+        return out.reshape(9, 3)
+
+    def srs_table(self):
+        out = np.zeros((self.srs_len, 17, 3), np.uint8)
+        _check(lib().pb_ctx_srs_table(self._h, out.ctypes.data_as(u8p)))
+        return out
+
+    def interpolate_at_h(self, vals):
+        c = _Call("pb_interpolate_at_h", vals)
+        n = _n(vals)
+        out, po = c.out((n, 4))
+        olen, pl = c.out((n,))
+        c.run(self._h, c.inp(vals), po, pl, C.c_size_t(n))
+        return out, olen
+
+    def srs_eval_at_s(self, polys, plen):
+        c = _Call("pb_srs_eval_at_s", polys)
+        n = _n(polys)
+        out, po = c.out((n, 3))
+        status, ps = c.out((n,))
+        c.run(self._h, c.inp(polys), c.inp(plen), C.c_size_t(int(polys.shape[1])), po, ps, C.c_size_t(n))
+        return out, status
+
+    def constraints_satisfy(self, witness):
+        c = _Call("pb_constraints_satisfy", witness)
+        n = _n(witness)
+        out, po = c.out((n,))
+        c.run(self._h, c.inp(witness), po, C.c_size_t(n))
+        return out
+
+    def prove(self, witness, rnd, chal):
+        """plonk_prove over a batch -> (proofs[n][34], status[n])."""
+        c = _Call("pb_plonk_prove", witness, rnd, chal)
+        n = _n(witness)
+        proofs, pp = c.out((n, 34))
+        status, ps = c.out((n,))
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), pp, ps, C.c_size_t(n))
+        return proofs, status
+
+    def verify(self, proofs, chal, u, want_gt=False):
+        c = _Call("pb_plonk_verify", proofs, chal, u)
+        n = _n(proofs)
+        verdict, pv = c.out((n,))
+        if want_gt:
+            gt, pg = c.out((n, 4))
+        else:
+            gt, pg = None, None
+        c.run(self._h, c.inp(proofs), c.inp(chal), c.inp(u), pv, pg, C.c_size_t(n))
+        return (verdict, gt) if want_gt else verdict
+
+    def prove_verify(self, witness, rnd, chal, u):
+        """prove, then verify every completed proof -> (proofs, status, verdict); verdict 0xFF where status != 0."""
+        c = _Call("pb_plonk_prove_verify", witness, rnd, chal, u)
+        n = _n(witness)
+        proofs, pp = c.out((n, 34))
+        status, ps = c.out((n,))
+        verdict, pv = c.out((n,))
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), pp, ps, pv, C.c_size_t(n))
+        return proofs, status, verdict
+
+    def prove_verify_into(self, witness, rnd, chal, u, proofs, status, verdict):
+        """Same with caller-owned buffers (numpy arrays over pinned memory, or torch CUDA tensors): no allocation
+        on the call path.  This is what bench.py times."""
+        c = _Call("pb_plonk_prove_verify", witness, rnd, chal, u, proofs, status, verdict)
+        n = _n(witness)
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), c.inp(proofs), c.inp(status), c.inp(verdict),
+              C.c_size_t(n))
+
+
+def tally(proofs, status, verdict, counts):
+    """counts (torch int64[18], CUDA) += per-status histogram, accept count, proof-byte checksum."""
+    import torch
+    with torch.cuda.device(counts.device):
+        fn = lib().pb_tally_dev
+        fn.restype = C.c_int
+        n = int(status.shape[0])
+        _check(fn(C.c_void_p(proofs.data_ptr()) if proofs is not None else None, C.c_void_p(status.data_ptr()),
+                  C.c_void_p(verdict.data_ptr()) if verdict is not None else None, C.c_size_t(n),
+                  C.c_void_p(counts.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))

@@ -1,0 +1,110 @@
+// tests/hostcheck/hostcheck.cu -- TEST INFRASTRUCTURE.  Compiles the product's __host__ __device__ source
+// (field.cuh, curve.cuh, prover.cuh, verifier.cuh) for the HOST, so that the exact code the GPU runs
+// can be diffed against the oracle in this GPU-less container.  Never linked into the product library and
+// never used as a fallback: libplonk_b200.so has no host execution path.
+#include <cstdint>
+#include <cstring>
+#include "../../plonk.c_b200/csrc/prover.cuh"
+#include "../../plonk.c_b200/csrc/verifier.cuh"
+
+using namespace pb;
+
+static FieldTables make_ft() {
+  FieldTables ft;
+  memset(&ft, 0, sizeof ft);
+  for (uint32_t i = 0; i < 101; i++) ft.inv101[i] = (uint8_t)pow101(i, 99);
+  for (uint32_t i = 0; i < 17; i++) ft.inv17[i] = (uint8_t)pow17(i, 15);
+  return ft;
+}
+static G1 ld(const uint8_t* p) { return G1{p[0], p[1], p[2] ? 1u : 0u}; }
+static void st(uint8_t* p, G1 g) { p[0] = (uint8_t)g.x; p[1] = (uint8_t)g.y; p[2] = (uint8_t)g.inf; }
+
+extern "C" {
+
+void hc_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) {
+    G1 r = op == 0 ? g1_add(ft, ld(a + 3 * i), ld(b + 3 * i)) : op == 1 ? g1_double(ft, ld(a + 3 * i)) : g1_neg(ld(a + 3 * i));
+    st(out + 3 * i, r);
+  }
+}
+void hc_g1_mul(const uint8_t* p, const uint64_t* s, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) st(out + 3 * i, g1_mul(ft, ld(p + 3 * i), s[i]));
+}
+void hc_g1_on_curve(const uint8_t* p, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = g1_is_on_curve(ld(p + 3 * i)) ? 1 : 0;
+}
+void hc_g2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) {
+    G2 r = op == 0 ? g2_add(ft, G2{a[2 * i], a[2 * i + 1]}, G2{b[2 * i], b[2 * i + 1]}) : g2_neg(G2{a[2 * i], a[2 * i + 1]});
+    out[2 * i] = (uint8_t)r.x; out[2 * i + 1] = (uint8_t)r.y;
+  }
+}
+void hc_g2_mul(const uint8_t* p, const uint64_t* s, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) { G2 r = g2_mul(ft, G2{p[2 * i], p[2 * i + 1]}, s[i]); out[2 * i] = (uint8_t)r.x; out[2 * i + 1] = (uint8_t)r.y; }
+}
+void hc_gtp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) { GT r = gt_mul(GT{a[2 * i], a[2 * i + 1]}, GT{b[2 * i], b[2 * i + 1]}); out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b; }
+}
+void hc_gtp_pow(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) { GT r = gt_pow(GT{a[2 * i], a[2 * i + 1]}, e[i]); out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b; }
+}
+void hc_line(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) { Line l = line_through(ld(a + 3 * i), ld(b + 3 * i)); out[3 * i] = (uint8_t)l.x; out[3 * i + 1] = (uint8_t)l.y; out[3 * i + 2] = (uint8_t)l.c; }
+}
+void hc_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) { GT r = pairing17(ft, ld(p + 3 * i), G2{q[2 * i], q[2 * i + 1]}); out[2 * i] = (uint8_t)r.a; out[2 * i + 1] = (uint8_t)r.b; }
+}
+void hc_pairing_f(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  FieldTables ft = make_ft();
+  for (size_t i = 0; i < n; i++) { GT f = miller(ft, r, ld(p + 3 * i), G2{q[2 * i], q[2 * i + 1]}); out[2 * i] = (uint8_t)f.a; out[2 * i + 1] = (uint8_t)f.b; }
+}
+// cc: CircuitConst as 86 uint32 (struct order); table: [9][17] packed
+void hc_prove(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
+              uint8_t* proofs, uint8_t* status, size_t n) {
+  CircuitConst cc;
+  memcpy(&cc, cc_words, sizeof cc);
+  ProverTables tb;
+  tb.ft = make_ft();
+  memcpy(tb.T, table, sizeof tb.T);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t wa[4], wb[4], wc[4], r[9];
+    for (int k = 0; k < 4; k++) { wa[k] = wit[12 * i + k]; wb[k] = wit[12 * i + 4 + k]; wc[k] = wit[12 * i + 8 + k]; }
+    for (int k = 0; k < 9; k++) r[k] = rnd[9 * i + k];
+    const uint8_t* ch = chal + 5 * i;
+    ProofOut o;
+    prove_one(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+    uint8_t* po = proofs + 34 * i;
+    memset(po, 0, 34);
+    if (o.status == 0) {
+      for (int j = 0; j < 9; j++) st(po + 3 * j, o.pts[j]);
+      for (int j = 0; j < 7; j++) po[27 + j] = (uint8_t)o.sc[j];
+    }
+    status[i] = (uint8_t)o.status;
+  }
+}
+int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
+// key: 9 G1 as bytes [27] + g2[4]
+void hc_verify(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+  FieldTables ft = make_ft();
+  VerifyKey k;
+  G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
+  for (int j = 0; j < 9; j++) *dst[j] = ld(key + 3 * j);
+  k.g2_one = G2{key[27], key[28]};
+  k.g2_s = G2{key[29], key[30]};
+  for (size_t i = 0; i < n; i++) {
+    uint32_t pbv[27], op[7], ch[5];
+    for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
+    for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
+    for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j];
+    VerifyOut o;
+    verify_one(k, ft, pbv, op, ch, u[i], o);
+    verdict[i] = (uint8_t)o.verdict;
+    if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
+  }
+}
+}

@@ -1,0 +1,303 @@
+"""One parity suite for every implementation: `impl` is the thing under test, `oracle` the checker; both
+have oracle._binding.OracleLib's call signatures (see impls.py).  Bar: BIT-EXACT (integer / byte work)."""
+import os
+
+import numpy as np
+
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def eq(name, got, want):
+    if isinstance(want, tuple):
+        assert isinstance(got, tuple) and len(got) == len(want), name
+        for i, (g, w) in enumerate(zip(got, want)):
+            eq(f"{name}[{i}]", g, w)
+        return
+    if isinstance(want, dict):
+        for k in want:
+            eq(f"{name}.{k}", got[k], want[k])
+        return
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    if not np.array_equal(got, want):
+        bad = np.argwhere(got != want)
+        first = tuple(bad[0])
+        raise AssertionError(f"{name}: {len(bad)} mismatching bytes, first at {first}: got {got[first]}, want {want[first]}")
+
+
+def golden(name):
+    return np.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+# ------------------------------------------------------------------ family (1)
+def check_fields_exhaustive(impl, oracle):
+    """All of F17 x F17 and F101 x F101 for every operation, as hf-test.c does for F17 (hf-test.c:48-198)."""
+    for p in (17, 101):
+        a, b = np.meshgrid(np.arange(p, dtype=np.uint8), np.arange(p, dtype=np.uint8))
+        a, b = np.ascontiguousarray(a.ravel()), np.ascontiguousarray(b.ravel())
+        for op in range(7):
+            want = oracle.field_op(p, op, a, b)
+            eq(f"F{p} op{op}", impl.field_op(p, op, a, b if op not in (4, 5) else None), want)
+            # independent recomputation with `%`, the reference's own definition (hf.h:105-109, gf.h:115-120)
+            ai, bi = a.astype(np.int64), b.astype(np.int64)
+            if op == 0:
+                eq(f"F{p} add vs %", want, ((ai + bi) % p).astype(np.uint8))
+            elif op == 1:
+                eq(f"F{p} sub vs %", want, ((ai - bi) % p).astype(np.uint8))
+            elif op == 2:
+                eq(f"F{p} mul vs %", want, ((ai * bi) % p).astype(np.uint8))
+            elif op == 5:
+                inv = np.array([pow(int(x), p - 2, p) for x in a], np.uint8)
+                eq(f"F{p} inv vs Fermat", want, inv)
+
+
+def check_fields_ragged(impl, oracle):
+    """Sizes around the 16-byte vector width and the block size, including empty."""
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 16, 17, 255, 4097, 100003):
+        a = rng.integers(0, 101, n, dtype=np.uint8)
+        b = rng.integers(0, 101, n, dtype=np.uint8)
+        if n == 0:
+            assert impl.field_op(101, 2, a, b).shape == (0,)
+            continue
+        eq(f"gf_mul n={n}", impl.field_op(101, 2, a, b), oracle.field_op(101, 2, a, b))
+        eq(f"hf_div n={n}", impl.field_op(17, 3, a % 17, b % 17), oracle.field_op(17, 3, a % 17, b % 17))
+
+
+# ------------------------------------------------------------------ family (2)
+POLY_SHAPES = ((6, 6), (11, 6), (16, 7), (11, 5), (22, 5), (10, 2), (3, 9))
+
+
+def check_polys(impl, oracle, n=20000):
+    for la, lb in POLY_SHAPES:
+        a, al, b, bl = util.poly_cases(n, la, lb)
+        for op in range(3):
+            eq(f"poly_binop{op} {la}x{lb}", impl.poly_binop(op, a, al, b, bl, la + lb), oracle.poly_binop(op, a, al, b, bl, la + lb))
+        eq(f"poly_divide {la}/{lb}", impl.poly_divide(a, al, b, bl, la, lb), oracle.poly_divide(a, al, b, bl, la, lb))
+        x = np.ascontiguousarray(a[:, 0])
+        eq(f"poly_eval {la}", impl.poly_eval(a, al, x), oracle.poly_eval(a, al, x))
+        rng = np.random.default_rng(la)
+        for op in range(4):
+            k = rng.integers(0, 17 if op != 2 else 5, n, dtype=np.uint8)
+            eq(f"poly_unop{op} {la}", impl.poly_unop(op, a, al, k, la + 8), oracle.poly_unop(op, a, al, k, la + 8))
+        s = rng.integers(0, la + 1, n, dtype=np.uint8)
+        e = rng.integers(0, la + 2, n, dtype=np.uint8)
+        eq(f"poly_slice {la}", impl.poly_slice(a, al, s, e, la), oracle.poly_slice(a, al, s, e, la))
+    vals = util.poly_cases(n, 4, 4)[0]
+    eq("interpolate_at_h", impl.interpolate_at_h(vals), oracle.interpolate_at_h(vals))
+    rng = np.random.default_rng(9)
+    xs = rng.integers(0, 17, (4000, 4), dtype=np.uint8)
+    ys = rng.integers(0, 17, (4000, 4), dtype=np.uint8)
+    xs[:2000] = np.array([1, 4, 16, 13], np.uint8)          # the domain H: agrees with interpolate_at_h
+    eq("poly_lagrange", impl.poly_lagrange(xs, ys, 8), oracle.poly_lagrange(xs, ys, 8))
+    eq("lagrange == interpolate on H", impl.poly_lagrange(xs[:2000], ys[:2000], 4)[:2], impl.interpolate_at_h(ys[:2000]))
+    for _ in range(20):
+        m = rng.integers(0, 17, (4, 4), dtype=np.uint8)
+        eq("matrix_inv", impl.matrix_inv(m), oracle.matrix_inv(m))
+        m2 = rng.integers(0, 17, (4, 3), dtype=np.uint8)
+        eq("matrix_mul", impl.matrix_mul(m, m2), oracle.matrix_mul(m, m2))
+    eq("plonk_new", impl.plonk_setup_dump(), oracle.plonk_setup_dump())
+
+
+def check_polys_golden(impl, n=2048):
+    g = golden("polys")
+    for la, lb in POLY_SHAPES:
+        a, al, b, bl = util.poly_cases(n, la, lb)
+        k = f"{la}x{lb}"
+        for op, nm in ((0, "add"), (1, "sub"), (2, "mul")):
+            eq(f"golden {nm} {k}", impl.poly_binop(op, a, al, b, bl, la + lb), (g[f"{nm}_{k}"], g[f"{nm}_{k}_len"]))
+        eq(f"golden div {k}", impl.poly_divide(a, al, b, bl, la, lb),
+           (g[f"div_{k}_q"], g[f"div_{k}_ql"], g[f"div_{k}_r"], g[f"div_{k}_rl"], g[f"div_{k}_st"]))
+        eq(f"golden eval {k}", impl.poly_eval(a, al, np.ascontiguousarray(a[:, 0])), g[f"eval_{k}"])
+    vals = util.poly_cases(n, 4, 4)[0]
+    eq("golden interp", impl.interpolate_at_h(vals), (g["interp"], g["interp_len"]))
+
+
+# ------------------------------------------------------------------ families (3) and (4)
+def check_groups(impl, oracle, n=200000):
+    a, b = util.g1_cases(n)
+    for op in range(3):
+        eq(f"g1_op{op}", impl.g1_op(op, a, b if op == 0 else None), oracle.g1_op(op, a, b))
+    s = util.scalars_u64(n)
+    eq("g1_mul", impl.g1_mul(a, s), oracle.g1_mul(a, s))
+    eq("g1_is_on_curve", impl.g1_is_on_curve(a), oracle.g1_is_on_curve(a))
+    a2, b2 = np.ascontiguousarray(a[:, :2]), np.ascontiguousarray(b[:, :2])
+    eq("g2_add", impl.g2_op(0, a2, b2), oracle.g2_op(0, a2, b2))
+    eq("g2_neg", impl.g2_op(2, a2), oracle.g2_op(2, a2))
+    s2 = s.copy()
+    s2[s2 == 0] = 1
+    eq("g2_mul", impl.g2_mul(a2, s2), oracle.g2_mul(a2, s2))
+    eq("gtp_mul", impl.gtp_mul(a2, b2), oracle.gtp_mul(a2, b2))
+    e = s.copy()
+    e[n // 2:] %= 20000
+    e[:100] = np.arange(100, dtype=np.uint64) * 101
+    eq("gtp_pow", impl.gtp_pow(a2, e), oracle.gtp_pow(a2, e))
+    eq("line", impl.line(a, b), oracle.line(a, b))
+
+
+def check_pairing(impl, oracle, W, n=100000):
+    a, b = util.g1_cases(n)
+    b2 = np.ascontiguousarray(b[:, :2])
+    eq("pairing arbitrary bytes", impl.pairing(a, b2), oracle.pairing(a, b2, 8))
+    P, Q, _ = util.subgroup_points(W, oracle, n)
+    eq("pairing subgroup", impl.pairing(P, Q), oracle.pairing(P, Q, 8))
+    for r in (1, 2, 3, 5, 16, 17, 23, 100):
+        eq(f"pairing_f r={r}", impl.pairing_f(r, a[:3000], b2[:3000]), oracle.pairing_f(r, a[:3000], b2[:3000]))
+
+
+def check_groups_golden(impl, W, oracle_for_inputs, n=2048):
+    g = golden("groups")
+    a, b = util.g1_cases(n)
+    s = util.scalars_u64(n)
+    s2 = s.copy()
+    s2[s2 == 0] = 1
+    e = s.copy()
+    e[n // 2:] %= 20000
+    a2, b2 = np.ascontiguousarray(a[:, :2]), np.ascontiguousarray(b[:, :2])
+    eq("golden g1_add", impl.g1_op(0, a, b), g["g1_add"])
+    eq("golden g1_double", impl.g1_op(1, a), g["g1_double"])
+    eq("golden g1_neg", impl.g1_op(2, a), g["g1_neg"])
+    eq("golden g1_mul", impl.g1_mul(a, s), g["g1_mul"])
+    eq("golden on_curve", impl.g1_is_on_curve(a), g["g1_on_curve"])
+    eq("golden g2_add", impl.g2_op(0, a2, b2), g["g2_add"])
+    eq("golden g2_neg", impl.g2_op(2, a2), g["g2_neg"])
+    eq("golden g2_mul", impl.g2_mul(a2, s2), g["g2_mul"])
+    eq("golden gtp_mul", impl.gtp_mul(a2, b2), g["gtp_mul"])
+    eq("golden gtp_pow", impl.gtp_pow(a2, e), g["gtp_pow"])
+    eq("golden line", impl.line(a, b), g["line"])
+    eq("golden pairing arbitrary", impl.pairing(a, b2), g["pairing_any"])
+    eq("golden pairing_f5", impl.pairing_f(5, a, b2), g["pairing_f5"])
+    P, Q, sc = util.subgroup_points(W, oracle_for_inputs, n)
+    eq("golden pairing subgroup", impl.pairing(P, Q), g["pairing_subgroup"])
+    eq("golden g1_mul subgroup", impl.g1_mul(P, sc.astype(np.uint64)), g["g1_mul_subgroup"])
+
+
+def check_reference_known_answers(impl):
+    """The known answers the reference's own tests assert, restated as data."""
+    G = np.array([[1, 2, 0]], np.uint8)
+
+    def g1(x, y):
+        return np.array([[x, y, 0]], np.uint8)
+    two = impl.g1_op(0, G, G)
+    eq("2G (g1-test.c:27)", two, g1(68, 74))
+    three = impl.g1_op(0, two, G)
+    eq("3G (g1-test.c:29)", three, g1(26, 45))
+    four = impl.g1_op(0, two, two)
+    eq("4G (g1-test.c:30)", four, g1(65, 98))
+    eq("5G (g1-test.c:32)", impl.g1_op(0, four, G), g1(12, 32))
+    eight = impl.g1_op(0, four, four)
+    eq("8G (g1-test.c:33)", eight, g1(18, 49))
+    eq("9G (g1-test.c:35)", impl.g1_op(0, eight, G), g1(18, 52))
+    eq("16G = -G (g1-test.c:36)", impl.g1_op(0, eight, eight), g1(1, 99))
+    eq("-G (g1-test.c:26)", impl.g1_op(2, G), g1(1, 99))
+    eq("g1_mul(G,6) (g1-test.c:41)", impl.g1_mul(G, np.array([6], np.uint64)), impl.g1_op(0, impl.g1_op(0, four, G), G))
+    Hh = np.array([[36, 31]], np.uint8)
+    h2 = impl.g2_op(0, Hh, Hh)
+    eq("2H (g2-test.c:17)", h2, np.array([[90, 82]], np.uint8))
+    h3 = impl.g2_op(0, h2, Hh)
+    h4 = impl.g2_op(0, h2, h2)
+    eq("3H + H = 4H (g2-test.c:18)", impl.g2_op(0, h3, Hh), h4)
+    eq("g2_mul(H,6) (g2-test.c:19)", impl.g2_mul(Hh, np.array([6], np.uint64)), impl.g2_op(0, h4, h2))
+
+    def gt(a, b):
+        return np.array([[a, b]], np.uint8)
+    eq("gtp_mul (gt-test.c:13)", impl.gtp_mul(gt(26, 97), gt(93, 76)), gt(97, 89))
+    eq("gtp_pow 6 (gt-test.c:15-16)", impl.gtp_pow(gt(42, 49), np.array([6], np.uint64)), gt(97, 89))
+    eq("x^101 = conj (gt-test.c:22)", impl.gtp_pow(gt(93, 76), np.array([101], np.uint64)), gt(93, 25))
+    eq("gtp_pow 600 (gt-test.c:25-26)", impl.gtp_pow(gt(68, 47), np.array([600], np.uint64)), gt(97, 89))
+    # pairing-test.c:5-27: bilinearity with P = G, R = 4G, Q = 3H, a = 5
+    q3 = impl.g2_mul(Hh, np.array([3], np.uint64))
+    p5 = impl.g1_mul(G, np.array([5], np.uint64))
+    q15 = impl.g2_mul(q3, np.array([5], np.uint64))
+    e_pq = impl.pairing(G, q3)
+    eq("e(5P,Q) = e(P,5Q)", impl.pairing(p5, q3), impl.pairing(G, q15))
+    eq("e(5P,Q) = e(P,Q)^5", impl.pairing(p5, q3), impl.gtp_pow(e_pq, np.array([5], np.uint64)))
+    eq("e(P+R,Q) = e(P,Q) e(R,Q)", impl.pairing(impl.g1_op(0, G, four), q3), impl.gtp_mul(e_pq, impl.pairing(four, q3)))
+    # SURVEY.md Appendix A.3 (absolute values the reference's tests do not pin)
+    eq("e(G,H) = (7,28)", impl.pairing(G, Hh), gt(7, 28))
+    eq("pairing_f(17,G,H) = (15,26)", impl.pairing_f(17, G, Hh), gt(15, 26))
+    eq("e(identity,H) = (0,0)", impl.pairing(np.array([[0, 0, 1]], np.uint8), Hh), gt(0, 0))
+
+
+# ------------------------------------------------------------------ protocol
+def check_protocol(impl, oracle, W, n=60000, modes=None, seed=11):
+    C = W.PLONK_TEST_CIRCUIT
+    rng = np.random.default_rng(seed)
+    for mode, mk in (modes or list(util.SRS_MODES.items()) + [("garbage10", lambda W: util.garbage_srs())]):
+        g1s, g2 = mk(W)
+        for var in ("U17", "NZ"):
+            wit, rnd, chal, u = W.make_batch(seed, 0, n, var)
+            want = oracle.plonk_prove_batch(C, g1s, g2, wit, rnd, chal, 8)
+            got = impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal)
+            eq(f"plonk_prove {mode} {var}", got, want)
+            proofs = want[0]
+            eq(f"plonk_verify {mode} {var}", impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u),
+               oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8))
+            bad = proofs.copy()                       # one corrupted byte per proof, out-of-range values included
+            bad[np.arange(n), rng.integers(0, 34, n)] = rng.integers(0, 120, n)
+            eq(f"plonk_verify corrupted {mode} {var}", impl.plonk_verify_batch(C, g1s, g2, bad, chal, u),
+               oracle.plonk_verify_batch(C, g1s, g2, bad, chal, u, 8))
+    # a witness that violates the gates: assert(constraints_satisfy) (plonk.h:231) -> status 1
+    g1s, g2 = W.generator_srs(9)
+    wit, rnd, chal, u = W.make_batch(seed + 1, 0, 3000, "U17")
+    wit[:, 8] = (wit[:, 8] + 1) % 17
+    eq("plonk_prove unsatisfied", impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal), oracle.plonk_prove_batch(C, g1s, g2, wit, rnd, chal))
+
+
+def check_protocol_golden(impl, W, n=2048):
+    g = golden("protocol")
+    C = W.PLONK_TEST_CIRCUIT
+    for mode in list(util.SRS_MODES) + ["garbage10"]:
+        g1s, g2 = g[mode + "_g1s"], g[mode + "_g2"]
+        if hasattr(impl, "verifier_key"):
+            eq(f"golden verifier key {mode}", impl.verifier_key(C, g1s, g2), g[mode + "_vkey"])
+        for var in ("U17", "NZ"):
+            wit, rnd, chal, u = W.make_batch(77, 0, n, var)
+            wit[0], rnd[0], chal[0], u[0] = W.GOLDEN_WITNESS[0], W.GOLDEN_RAND[0], W.GOLDEN_CHALLENGE[0], W.GOLDEN_U[0]
+            k = f"{mode}_{var}"
+            eq(f"golden prove {k}", impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal), (g[k + "_proofs"], g[k + "_status"]))
+            eq(f"golden verify {k}", impl.plonk_verify_batch(C, g1s, g2, g[k + "_proofs"], chal, u), (g[k + "_verdict"], g[k + "_gt"]))
+
+
+def check_golden_transcript(impl, W):
+    """the shipped test vector (plonk-test.c:125-270)."""
+    C = W.PLONK_TEST_CIRCUIT
+    wit, rnd, chal, u = W.GOLDEN_WITNESS, W.GOLDEN_RAND, W.GOLDEN_CHALLENGE, W.GOLDEN_U
+    scalars = [15, 13, 5, 1, 12, 15, 15]
+    # A.1: as-shipped identity SRS, srs_create(2, 6)
+    g1s, g2 = W.identity_srs(6)
+    proofs, status = impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal)
+    assert status[0] == 0
+    eq("A.1 commitments are the identity", proofs[0, :27].reshape(9, 3), np.tile(np.array([0, 0, 1], np.uint8), (9, 1)))
+    eq("A.1 openings", proofs[0, 27:], np.array(scalars, np.uint8))
+    verdict, gt = impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u)
+    assert verdict[0] == 1 and list(gt[0]) == [0, 0, 0, 0]         # identity SRS accepts everything
+    # A.2: generator SRS through the public struct
+    g1s, g2 = W.generator_srs(6)
+    proofs, status = impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal)
+    assert status[0] == 0
+    want = [(91, 66), (26, 45), (91, 35), (32, 59), (12, 32), (26, 45), (91, 66), (91, 35), (65, 98)]
+    eq("A.2 commitments", proofs[0, :27].reshape(9, 3), np.array([[x, y, 0] for x, y in want], np.uint8))
+    eq("A.2 openings", proofs[0, 27:], np.array(scalars, np.uint8))
+    # A.3: verifier known answers, u = 4
+    verdict, gt = impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u)
+    assert verdict[0] == 1 and list(gt[0]) == [93, 76, 93, 76]
+    bad = proofs.copy()
+    bad[0, 27] = 16
+    verdict, gt = impl.plonk_verify_batch(C, g1s, g2, bad, chal, u)
+    assert verdict[0] == 0 and list(gt[0]) == [93, 76, 59, 52]
+
+
+def check_commitments(impl, oracle, W, n=20000):
+    rng = np.random.default_rng(21)
+    for mode, mk in list(util.SRS_MODES.items()) + [("garbage10", lambda W: util.garbage_srs())]:
+        g1s, g2 = mk(W)
+        polys = rng.integers(0, 17, (n, 12), dtype=np.uint8)
+        polys[rng.random((n, 12)) < 0.3] = 0
+        plen = rng.integers(1, 13, n).astype(np.uint8)
+        eq(f"srs_eval_at_s {mode}", impl.srs_eval_at_s(g1s, g2, polys, plen), oracle.srs_eval_at_s(g1s, g2, polys, plen))
+    g1s, g2 = W.generator_srs(6)
+    p = np.array([[1, 2, 3, 4, 5, 6]], np.uint8)
+    eq("srs_eval_at_s known answer (SURVEY A.2)", impl.srs_eval_at_s(g1s, g2, p, np.array([6], np.uint8))[0], np.array([[68, 27, 0]], np.uint8))

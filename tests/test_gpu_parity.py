@@ -1,0 +1,148 @@
+"""GPU parity tests: libplonk_b200.so through its C ABI against the CPU oracle, bit-exact.  Both boundary
+flavours are exercised: the `_dev` entry points on torch CUDA tensors (device path) and the host-pointer
+entry points on numpy arrays (host path).  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import parity_suite as ps
+from impls import GpuImpl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(host):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return GpuImpl(host, "device")
+
+
+@pytest.fixture(scope="module")
+def hostpath(host):
+    return GpuImpl(host, "host")
+
+
+def test_reference_known_answers(dev):
+    ps.check_reference_known_answers(dev)
+
+
+def test_reference_known_answers_host_path(hostpath):
+    ps.check_reference_known_answers(hostpath)
+
+
+def test_golden_transcript(dev, hostpath, W):
+    ps.check_golden_transcript(dev, W)
+    ps.check_golden_transcript(hostpath, W)
+
+
+def test_fields(dev, oracle):
+    ps.check_fields_exhaustive(dev, oracle)
+    ps.check_fields_ragged(dev, oracle)
+
+
+def test_fields_host_path(hostpath, oracle):
+    ps.check_fields_ragged(hostpath, oracle)
+
+
+def test_polys(dev, oracle):
+    ps.check_polys(dev, oracle)
+
+
+def test_polys_golden(dev, hostpath):
+    ps.check_polys_golden(dev)
+    ps.check_polys_golden(hostpath)
+
+
+def test_groups(dev, oracle):
+    ps.check_groups(dev, oracle)
+
+
+def test_pairing(dev, oracle, W):
+    ps.check_pairing(dev, oracle, W)
+
+
+def test_groups_golden(dev, hostpath, oracle, W):
+    ps.check_groups_golden(dev, W, oracle)
+    ps.check_groups_golden(hostpath, W, oracle)
+
+
+def test_commitments(dev, oracle, W):
+    ps.check_commitments(dev, oracle, W)
+
+
+def test_protocol(dev, oracle, W):
+    ps.check_protocol(dev, oracle, W)
+
+
+def test_protocol_host_path(hostpath, oracle, W):
+    ps.check_protocol(hostpath, oracle, W, n=20000, modes=[("generator9", lambda W: W.generator_srs(9)), ("identity6", lambda W: W.identity_srs(6))])
+
+
+def test_protocol_golden(dev, hostpath, W):
+    ps.check_protocol_golden(dev, W)
+    ps.check_protocol_golden(hostpath, W)
+
+
+def test_setup_constants(host, oracle, W):
+    """plonk_new + the witness-independent part of plonk_prove, as computed by the context's setup kernels."""
+    for mk in (W.identity_srs, W.generator_srs):
+        g1s, g2 = mk(9)
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+        ps.eq("plonk_new", pk.setup_dump(), oracle.plonk_setup_dump())
+        d = pk.circuit_dump()
+        assert d["sigma"].tolist() == [[2, 8, 15, 3], [1, 4, 16, 12], [13, 9, 5, 14]]          # plonk-test.c:105-112
+        assert d["s_sigma"].tolist() == [[7, 13, 10, 6], [4, 0, 13, 1], [6, 7, 3, 14]]
+        assert d["l1"].tolist() == [13, 13, 13, 13]
+        ps.eq("verifier key", pk.verifier_key(), oracle.verifier_key(W.PLONK_TEST_CIRCUIT, g1s, g2))
+        tab = pk.srs_table()
+        want = np.stack([oracle.g1_mul(np.tile(g1s[i:i + 1], (17, 1)), np.arange(17, dtype=np.uint64)) for i in range(10)])
+        ps.eq("fixed-base table = g1_mul(g1s[i], c)", tab, want)
+        sat = pk.constraints_satisfy(W.satisfying_witnesses())
+        assert sat.all()
+        bad = W.satisfying_witnesses().copy()
+        bad[:, 11] = (bad[:, 11] + 1) % 17
+        assert not pk.constraints_satisfy(bad).any()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 1000, 4097])
+def test_ragged_batch_sizes(host, oracle, W, n):
+    """Empty, single and non-multiple-of-block batches through prove, verify and the fused prove_verify."""
+    import torch
+    g1s, g2 = W.generator_srs(9)
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+    wit, rnd, chal, u = W.make_batch(31, 1000, n, "U17")
+    d = [torch.from_numpy(x).cuda() for x in (wit, rnd, chal, u)]
+    proofs, status, verdict = pk.prove_verify(*d)
+    hp, hs, hv = pk.prove_verify(wit, rnd, chal, u)                     # host-pointer pipeline
+    if n == 0:
+        assert proofs.shape == (0, 34) and hp.shape == (0, 34)
+        return
+    rp, rs = oracle.plonk_prove_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal)
+    rv, _ = oracle.plonk_verify_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, rp, chal, u)
+    rv = np.where(rs == 0, rv, 0xFF).astype(np.uint8)
+    ps.eq("device path", (proofs.cpu().numpy(), status.cpu().numpy(), verdict.cpu().numpy()), (rp, rs, rv))
+    ps.eq("host path", (hp, hs, hv), (rp, rs, rv))
+
+
+def test_bad_input_bytes_are_flagged_not_undefined(host, W):
+    """Bytes outside [0,17) are not a reference path (HF is 'always kept in range', hf.h:11-14): status 254."""
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    wit, rnd, chal, u = W.make_batch(3, 0, 512)
+    wit[5, 3] = 17
+    rnd[77, 0] = 255
+    chal[300, 4] = 200
+    proofs, status = pk.prove(wit, rnd, chal)
+    assert status[5] == 254 and status[77] == 254 and status[300] == 254
+    assert (status[[5, 77, 300]] == 254).all() and not proofs[[5, 77, 300]].any()
+    assert (np.delete(status, [5, 77, 300]) != 254).all()
+
+
+def test_misaligned_device_pointer_is_rejected(host, W):
+    import torch
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    wit, rnd, chal, u = W.make_batch(3, 0, 64)
+    big = torch.zeros(64 * 12 + 1, dtype=torch.uint8, device="cuda")
+    view = big[1:].view(64, 12)
+    with pytest.raises(host.PlonkB200Error) as e:
+        pk.prove(view, torch.from_numpy(rnd).cuda(), torch.from_numpy(chal).cuda())
+    assert e.value.code == host.PB_ERR_ARG

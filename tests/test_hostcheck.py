@@ -1,0 +1,34 @@
+"""CPU tests of the PRODUCT's kernel source: field.cuh / curve.cuh / prover.cuh / verifier.cuh are
+__host__ __device__, so the exact code the GPU runs is compiled for the host (tests/hostcheck) and diffed
+against the oracle here, where there is no GPU.  This is a debugging aid, not a product path."""
+import pytest
+
+import parity_suite as ps
+from impls import HostcheckImpl
+
+
+@pytest.fixture(scope="module")
+def hc(oracle):
+    return HostcheckImpl(oracle)
+
+
+def test_hostcheck_known_answers(hc):
+    ps.check_reference_known_answers(hc)
+
+
+def test_hostcheck_groups(hc, oracle):
+    ps.check_groups(hc, oracle)
+
+
+def test_hostcheck_pairing(hc, oracle, W):
+    ps.check_pairing(hc, oracle, W, n=30000)
+
+
+def test_hostcheck_protocol(hc, oracle, W):
+    ps.check_protocol(hc, oracle, W, n=20000)
+
+
+def test_hostcheck_golden(hc, oracle, W):
+    ps.check_golden_transcript(hc, W)
+    ps.check_groups_golden(hc, W, oracle)
+    ps.check_protocol_golden(hc, W)
