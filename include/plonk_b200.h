@@ -201,6 +201,9 @@ int pb_plonk_verify_dev(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t 
                         uint8_t *verdict, uint8_t *gt, size_t n, void *stream);
 int pb_plonk_verify(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
                     uint8_t *verdict, uint8_t *gt, size_t n);
+/* verify only the items whose prove status is 0; verdict[i] = 0xFF elsewhere (device pointers only) */
+int pb_plonk_verify_completed_dev(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
+                                  const uint8_t *status, uint8_t *verdict, size_t n, void *stream);
 /* prove then verify every completed proof (status 0); verdict[i] = 0xFF where status[i] != 0.
  * Host-pointer version: chunked, copies overlapped with compute on internal streams. */
 int pb_plonk_prove_verify_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
@@ -211,6 +214,12 @@ int pb_plonk_prove_verify(const pb_ctx *ctx, const uint8_t *witness, const uint8
  * counts[16] += verdict==1, counts[17] += a 64-bit sum of all proof bytes (checksum). counts: int64[18] device ptr */
 int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *verdict, size_t n, int64_t *counts, void *stream);
 
+
+/* ---- roofline denominators measured on the device the caller is on (MEASURED_PEAKS.json
+ * has no integer peak).  Each runs a dependency-free instruction stream on every SM and reports how many
+ * thread-level operations it issued; the caller times it.  kind 0: 32-bit IMAD (fma pipe); kind 1: IADD3/LOP3
+ * (alu pipe); kind 2: IMAD and LOP3 interleaved 1:1 (both pipes); kind 3: shared-memory byte look-ups (LDS.U8). */
+int pb_peak_probe_dev(int kind, uint32_t iters, uint64_t *ops_out_host, uint32_t *sink_dev, void *stream);
 #ifdef __cplusplus
 }
 #endif

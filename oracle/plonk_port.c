@@ -24,12 +24,23 @@
 
 typedef uint8_t fe; /* a field element, always stored reduced */
 
+/* Optional operation counters (-DPORT_COUNT_OPS, single-threaded use): the algorithmic field-operation
+ * counts of the reference's algorithm, from which bench.py derives `roofline.achieved` on the integer side
+ * (SURVEY.md section 8(d)).  0 hf_mul 1 hf_add 2 hf_sub 3 hf_inv 4 gf_mul 5 gf_add 6 gf_sub 7 gf_inv (calls;
+ * each is also 11 gf_mul, counted under 4). */
+#ifdef PORT_COUNT_OPS
+static uint64_t g_ops[8];
+#define CNT(i) (g_ops[i]++)
+#else
+#define CNT(i) ((void)0)
+#endif
+
 /* ================================================================ F17  (src/hf.h) */
 #define P17 17
 static fe hf_new_(int64_t v) { int64_t t = v % P17; if (t < 0) t += P17; return (fe)t; }      /* hf.h:25-35 */
-static fe hf_add_(fe a, fe b) { uint8_t s = (uint8_t)(a + b); if (s >= P17) s -= P17; return s; } /* hf.h:79-84 */
-static fe hf_sub_(fe a, fe b) { int8_t d = (int8_t)a - (int8_t)b; if (d < 0) d += P17; return (fe)d; } /* hf.h:92-97 */
-static fe hf_mul_(fe a, fe b) { return (fe)((uint16_t)a * (uint16_t)b % P17); }              /* hf.h:105-109 */
+static fe hf_add_(fe a, fe b) { CNT(1); uint8_t s = (uint8_t)(a + b); if (s >= P17) s -= P17; return s; } /* hf.h:79-84 */
+static fe hf_sub_(fe a, fe b) { CNT(2); int8_t d = (int8_t)a - (int8_t)b; if (d < 0) d += P17; return (fe)d; } /* hf.h:92-97 */
+static fe hf_mul_(fe a, fe b) { CNT(0); return (fe)((uint16_t)a * (uint16_t)b % P17); }              /* hf.h:105-109 */
 static fe hf_neg_(fe a) { return a == 0 ? 0 : (fe)(P17 - a); }                                /* hf.h:116-119 */
 static fe hf_pow_(fe base, uint64_t e) {                                                      /* hf.h:127-137 */
   fe r = 1;
@@ -37,22 +48,22 @@ static fe hf_pow_(fe base, uint64_t e) {                                        
   return r;
 }
 /* hf.h:145-191: table lookup, inv(0) = 0.  Restated as "the j with a*j = 1, else 0". */
-static fe hf_inv_(fe a) { for (fe j = 1; j < P17; j++) if (hf_mul_(a, j) == 1) return j; return 0; }
+static fe hf_inv_(fe a) { CNT(3); for (fe j = 1; j < P17; j++) if ((uint16_t)a * j % P17 == 1) return j; return 0; }
 static fe hf_div_(fe a, fe b) { return hf_mul_(a, hf_inv_(b)); }                              /* hf.h:201-203 */
 
 /* ================================================================ F101 (src/gf.h) */
 #define P101 101
 static fe gf_new_(int64_t v) { int64_t t = v % P101; if (t < 0) t += P101; return (fe)t; }    /* gf.h:24-34 */
-static fe gf_add_(fe a, fe b) { uint16_t s = (uint16_t)(a + b); if (s >= P101) s -= P101; return (fe)s; } /* gf.h:87-93 */
-static fe gf_sub_(fe a, fe b) { int16_t d = (int16_t)a - (int16_t)b; if (d < 0) d += P101; return (fe)d; } /* gf.h:101-107 */
-static fe gf_mul_(fe a, fe b) { return (fe)((uint16_t)a * (uint16_t)b % P101); }              /* gf.h:115-120 */
+static fe gf_add_(fe a, fe b) { CNT(5); uint16_t s = (uint16_t)(a + b); if (s >= P101) s -= P101; return (fe)s; } /* gf.h:87-93 */
+static fe gf_sub_(fe a, fe b) { CNT(6); int16_t d = (int16_t)a - (int16_t)b; if (d < 0) d += P101; return (fe)d; } /* gf.h:101-107 */
+static fe gf_mul_(fe a, fe b) { CNT(4); return (fe)((uint16_t)a * (uint16_t)b % P101); }              /* gf.h:115-120 */
 static fe gf_neg_(fe a) { return a == 0 ? 0 : (fe)(P101 - a); }                               /* gf.h:127-132 */
 static fe gf_pow_(fe base, uint64_t e) {                                                      /* gf.h:140-151 */
   fe r = 1;
   while (e > 0) { if (e & 1) r = gf_mul_(r, base); e >>= 1; base = gf_mul_(base, base); }
   return r;
 }
-static fe gf_inv_(fe a) { return gf_pow_(a, P101 - 2); }   /* gf.h:159-162: Fermat, so inv(0) = 0 */
+static fe gf_inv_(fe a) { CNT(7); return gf_pow_(a, P101 - 2); }   /* gf.h:159-162: Fermat, so inv(0) = 0 */
 static fe gf_div_(fe a, fe b) { return gf_mul_(a, gf_inv_(b)); }                              /* gf.h:170-172 */
 
 /* ================================================================ polynomials over F17 (src/poly.h) */
@@ -606,6 +617,10 @@ static srs_t srs_from(const uint8_t *g1s, uint32_t len, const uint8_t *g2b) {
 }
 
 int port_abi_version(void) { return 1; }
+#ifdef PORT_COUNT_OPS
+void port_ops_reset(void) { memset(g_ops, 0, sizeof g_ops); }
+void port_ops_get(uint64_t out[8]) { memcpy(out, g_ops, sizeof g_ops); }
+#endif
 
 void port_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n) {
   for (size_t i = 0; i < n; i++) {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -64,8 +65,17 @@ struct Dev {
 #define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
-constexpr size_t PIPE_CHUNK = 1u << 18;   // items per pipeline chunk of the host-pointer prove/verify
-constexpr int PIPE_SLOTS = 3;
+constexpr size_t PIPE_CHUNK_MAX = 1u << 18;   // device scratch per slot is sized for this many items
+constexpr int PIPE_SLOTS = 4;
+// items per pipeline chunk of the host-pointer prove/verify (PB_PIPE_CHUNK overrides, for tuning; multiple of 128)
+size_t pipe_chunk() {
+  static size_t v = [] {
+    size_t c = 1u << 17;
+    if (const char* e = getenv("PB_PIPE_CHUNK")) { size_t x = strtoull(e, nullptr, 10); if (x >= 128 && x <= PIPE_CHUNK_MAX) c = x & ~(size_t)127; }
+    return c;
+  }();
+  return v;
+}
 
 struct PipeSlot {
   cudaStream_t stream = nullptr;
@@ -108,13 +118,13 @@ int pipe_init(pb_ctx* c) {
   if (c->pipe_ready) return PB_OK;
   for (auto& s : c->slots) {
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&s.wit, PIPE_CHUNK * 12));
-    CU(cudaMalloc(&s.rnd, PIPE_CHUNK * 9));
-    CU(cudaMalloc(&s.chal, PIPE_CHUNK * 5));
-    CU(cudaMalloc(&s.u, PIPE_CHUNK));
-    CU(cudaMalloc(&s.proofs, PIPE_CHUNK * 34));
-    CU(cudaMalloc(&s.status, PIPE_CHUNK));
-    CU(cudaMalloc(&s.verdict, PIPE_CHUNK));
+    CU(cudaMalloc(&s.wit, PIPE_CHUNK_MAX * 12));
+    CU(cudaMalloc(&s.rnd, PIPE_CHUNK_MAX * 9));
+    CU(cudaMalloc(&s.chal, PIPE_CHUNK_MAX * 5));
+    CU(cudaMalloc(&s.u, PIPE_CHUNK_MAX));
+    CU(cudaMalloc(&s.proofs, PIPE_CHUNK_MAX * 34));
+    CU(cudaMalloc(&s.status, PIPE_CHUNK_MAX));
+    CU(cudaMalloc(&s.verdict, PIPE_CHUNK_MAX));
   }
   c->pipe_ready = true;
   return PB_OK;
@@ -146,6 +156,7 @@ int pb_host_free(void* p) {
 
 // ------------------------------------------------------------------ family (1)
 int pb_field_op_dev(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(field == 17 || field == 101);
   ARG(op >= 0 && op <= 6);
   ARG(a && out);
@@ -160,6 +171,7 @@ int pb_field_op_dev(int field, int op, const uint8_t* a, const uint8_t* b, uint8
   return PB_OK;
 }
 int pb_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && out);
@@ -176,6 +188,7 @@ int pb_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* 
 // ------------------------------------------------------------------ family (2)
 int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
                       uint8_t* out, uint8_t* olen, size_t so, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(op >= 0 && op <= 2);
   ARG(a && alen && b && blen && out && olen);
   ARG(sa >= 1 && sb >= 1 && sa <= PB_POLY_MAX && sb <= PB_POLY_MAX);
@@ -187,6 +200,7 @@ int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, 
 }
 int pb_poly_binop(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
                   uint8_t* out, uint8_t* olen, size_t so, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && alen && b && blen && out && olen);
@@ -203,6 +217,7 @@ int pb_poly_binop(int op, const uint8_t* a, const uint8_t* alen, size_t sa, cons
 int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
                        uint8_t* quot, uint8_t* qlen, size_t sq, uint8_t* rem, uint8_t* rlen, size_t sr,
                        uint8_t* status, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
   ARG(sn >= 1 && sd >= 1 && sn <= PB_POLY_MAX && sd <= PB_POLY_MAX && sq >= 1 && sr >= 1);
   if (n == 0) return PB_OK;
@@ -213,6 +228,7 @@ int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const
 }
 int pb_poly_divide(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
                    uint8_t* quot, uint8_t* qlen, size_t sq, uint8_t* rem, uint8_t* rlen, size_t sr, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
@@ -227,6 +243,7 @@ int pb_poly_divide(const uint8_t* num, const uint8_t* nlen, size_t sn, const uin
 }
 
 int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && plen && x && out && sp >= 1);
   if (n == 0) return PB_OK;
   poly_eval_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(p, plen, (int)sp, x, out, n);
@@ -234,6 +251,7 @@ int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uin
   return PB_OK;
 }
 int pb_poly_eval(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(p && plen && x && out);
@@ -248,6 +266,7 @@ int pb_poly_eval(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t
 
 int pb_poly_unop_dev(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen,
                      size_t so, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(op >= 0 && op <= 3);
   ARG(p && plen && out && olen && sp >= 1 && sp <= PB_POLY_MAX && so >= sp && so <= 2 * PB_POLY_MAX);
   ARG(k || op == PB_POLY_NEGATE);
@@ -257,6 +276,7 @@ int pb_poly_unop_dev(int op, const uint8_t* p, const uint8_t* plen, size_t sp, c
   return PB_OK;
 }
 int pb_poly_unop(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen, size_t so, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(p && plen && out && olen);
@@ -272,6 +292,7 @@ int pb_poly_unop(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const
 
 int pb_poly_slice_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
                       uint8_t* olen, size_t so, uint8_t* status, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && plen && start && end && out && olen && status && sp >= 1 && sp <= PB_POLY_MAX && so >= sp);
   if (n == 0) return PB_OK;
   poly_slice_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(p, plen, (int)sp, start, end, out, olen, (int)so, status, n);
@@ -280,6 +301,7 @@ int pb_poly_slice_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const ui
 }
 int pb_poly_slice(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
                   uint8_t* olen, size_t so, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(p && plen && start && end && out && olen && status);
@@ -295,6 +317,7 @@ int pb_poly_slice(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_
 
 int pb_poly_lagrange_dev(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status,
                          size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(xs && ys && out && olen && status && len >= 1 && len <= 16 && so >= len);
   if (n == 0) return PB_OK;
   poly_lagrange_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(xs, ys, (int)len, out, olen, (int)so, status, n);
@@ -302,6 +325,7 @@ int pb_poly_lagrange_dev(const uint8_t* xs, const uint8_t* ys, size_t len, uint8
   return PB_OK;
 }
 int pb_poly_lagrange(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(xs && ys && out && olen && status);
@@ -315,6 +339,7 @@ int pb_poly_lagrange(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* 
 }
 
 int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && vals && out && olen);
   ARG(aligned16(vals) && aligned16(out));
   if (n == 0) return PB_OK;
@@ -323,6 +348,7 @@ int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out
   return PB_OK;
 }
 int pb_interpolate_at_h(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && vals && out && olen);
   DeviceGuard g(ctx->device);
   DEV(dv, n * 4); DEV(dout, n * 4); DEV(dol, n);
@@ -335,6 +361,7 @@ int pb_interpolate_at_h(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, ui
 }
 
 int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && b && out && m >= 1 && k >= 1 && c >= 1 && m <= 8 && k <= 8 && c <= 8);
   if (n == 0) return PB_OK;
   matrix_mul_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, (int)m, (int)k, (int)c, n);
@@ -342,6 +369,7 @@ int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t
   return PB_OK;
 }
 int pb_matrix_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && b && out);
@@ -354,6 +382,7 @@ int pb_matrix_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, 
   return PB_OK;
 }
 int pb_matrix_inv_dev(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && out && dim >= 1 && dim <= 8);
   if (n == 0) return PB_OK;
   matrix_inv_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, out, (int)dim, n);
@@ -361,6 +390,7 @@ int pb_matrix_inv_dev(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n, vo
   return PB_OK;
 }
 int pb_matrix_inv(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && out);
@@ -375,6 +405,7 @@ int pb_matrix_inv(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n) {
 
 // ------------------------------------------------------------------ family (3)
 int pb_g1_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(op >= 0 && op <= 2 && a && out && (b || op != PB_G_ADD));
   if (n == 0) return PB_OK;
   g1_op_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
@@ -382,6 +413,7 @@ int pb_g1_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_
   return PB_OK;
 }
 int pb_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && out);
@@ -395,6 +427,7 @@ int pb_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n)
   return PB_OK;
 }
 int pb_g1_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(points && scalars && out);
   if (n == 0) return PB_OK;
   g1_mul_kernel<uint64_t><<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
@@ -402,6 +435,7 @@ int pb_g1_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, 
   return PB_OK;
 }
 int pb_g1_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(points && scalars && out);
@@ -414,6 +448,7 @@ int pb_g1_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size
   return PB_OK;
 }
 int pb_g1_mul_u8_dev(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(points && scalars && out);
   if (n == 0) return PB_OK;
   g1_mul_kernel<uint8_t><<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
@@ -421,6 +456,7 @@ int pb_g1_mul_u8_dev(const uint8_t* points, const uint8_t* scalars, uint8_t* out
   return PB_OK;
 }
 int pb_g1_mul_u8(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(points && scalars && out);
@@ -433,6 +469,7 @@ int pb_g1_mul_u8(const uint8_t* points, const uint8_t* scalars, uint8_t* out, si
   return PB_OK;
 }
 int pb_g1_is_on_curve_dev(const uint8_t* points, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(points && out);
   if (n == 0) return PB_OK;
   g1_on_curve_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(points, out, n);
@@ -440,6 +477,7 @@ int pb_g1_is_on_curve_dev(const uint8_t* points, uint8_t* out, size_t n, void* s
   return PB_OK;
 }
 int pb_g1_is_on_curve(const uint8_t* points, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(points && out);
@@ -452,6 +490,7 @@ int pb_g1_is_on_curve(const uint8_t* points, uint8_t* out, size_t n) {
   return PB_OK;
 }
 int pb_g2_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG((op == PB_G_ADD || op == PB_G_NEG) && a && out && (b || op != PB_G_ADD));
   if (n == 0) return PB_OK;
   g2_op_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
@@ -459,6 +498,7 @@ int pb_g2_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_
   return PB_OK;
 }
 int pb_g2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && out);
@@ -472,6 +512,7 @@ int pb_g2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n)
   return PB_OK;
 }
 int pb_g2_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(points && scalars && out);
   if (n == 0) return PB_OK;
   g2_mul_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(points, scalars, out, n);
@@ -479,6 +520,7 @@ int pb_g2_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, 
   return PB_OK;
 }
 int pb_g2_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(points && scalars && out);
@@ -493,6 +535,7 @@ int pb_g2_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size
 
 int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status,
                          size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && polys && plen && out && status && sp >= 1 && sp <= PB_POLY_MAX);
   if (n == 0) return PB_OK;
   commit_kernel<<<blocks_for(n, BLOCK), BLOCK, ctx->srs_len * 17 * sizeof(uint32_t), S(stream)>>>(ctx->d_srs_table, ctx->srs_len, polys, plen,
@@ -501,6 +544,7 @@ int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t*
   return PB_OK;
 }
 int pb_srs_eval_at_s(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && polys && plen && out && status);
   DeviceGuard g(ctx->device);
   DEV(dp, n * sp); DEV(dl, n); DEV(dout, n * 3); DEV(dst, n);
@@ -514,6 +558,7 @@ int pb_srs_eval_at_s(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* ple
 
 // ------------------------------------------------------------------ family (4)
 int pb_gtp_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && b && out);
   if (n == 0) return PB_OK;
   gtp_mul_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
@@ -521,6 +566,7 @@ int pb_gtp_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, v
   return PB_OK;
 }
 int pb_gtp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && b && out);
@@ -533,6 +579,7 @@ int pb_gtp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   return PB_OK;
 }
 int pb_gtp_pow_dev(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && e && out);
   if (n == 0) return PB_OK;
   gtp_pow_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, e, out, n);
@@ -540,6 +587,7 @@ int pb_gtp_pow_dev(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n, 
   return PB_OK;
 }
 int pb_gtp_pow(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && e && out);
@@ -552,6 +600,7 @@ int pb_gtp_pow(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n) {
   return PB_OK;
 }
 int pb_line_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && b && out);
   if (n == 0) return PB_OK;
   line_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
@@ -559,6 +608,7 @@ int pb_line_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void
   return PB_OK;
 }
 int pb_line(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(a && b && out);
@@ -571,6 +621,7 @@ int pb_line(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   return PB_OK;
 }
 int pb_pairing_dev(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && q && out);
   if (n == 0) return PB_OK;
   pairing_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(p, q, out, n);
@@ -578,6 +629,7 @@ int pb_pairing_dev(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, v
   return PB_OK;
 }
 int pb_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(p && q && out);
@@ -590,6 +642,7 @@ int pb_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
   return PB_OK;
 }
 int pb_pairing_f_dev(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && q && out && r >= 1);
   if (n == 0) return PB_OK;
   pairing_f_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(r, p, q, out, n);
@@ -597,6 +650,7 @@ int pb_pairing_f_dev(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* ou
   return PB_OK;
 }
 int pb_pairing_f(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   int rc = require_device();
   if (rc) return rc;
   ARG(p && q && out);
@@ -761,6 +815,7 @@ int pb_ctx_srs_table(const pb_ctx* ctx, uint8_t* out) { ARG(ctx && out); memcpy(
 
 // ------------------------------------------------------------------ protocol
 int pb_constraints_satisfy_dev(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && out);
   if (n == 0) return PB_OK;
   satisfy_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, witness, out, n);
@@ -768,6 +823,7 @@ int pb_constraints_satisfy_dev(const pb_ctx* ctx, const uint8_t* witness, uint8_
   return PB_OK;
 }
 int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && out);
   DeviceGuard g(ctx->device);
   DEV(dw, n * 12); DEV(dout, n);
@@ -781,6 +837,7 @@ int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* o
 
 int pb_plonk_prove_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs,
                        uint8_t* status, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
   if (n == 0) return PB_OK;
@@ -790,6 +847,7 @@ int pb_plonk_prove_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t*
 }
 int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt,
                         size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal && u && verdict);
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && aligned16(chal) && (!gt || aligned16(gt)));
@@ -798,8 +856,20 @@ int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t*
   LAUNCH_CHECK("verify_kernel");
   return PB_OK;
 }
+int pb_plonk_verify_completed_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
+                                  uint8_t* verdict, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && proofs && chal && u && status && verdict);
+  ARG(ctx->vk_valid);
+  ARG(aligned16(proofs) && aligned16(chal));
+  if (n == 0) return PB_OK;
+  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, status, verdict, nullptr, n);
+  LAUNCH_CHECK("verify_kernel");
+  return PB_OK;
+}
 int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                               uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(u && verdict);
   ARG(ctx && ctx->vk_valid);
   int rc = pb_plonk_prove_dev(ctx, witness, rnd, chal, proofs, status, n, stream);
@@ -810,7 +880,7 @@ int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const u
   return PB_OK;
 }
 
-// host-pointer versions: chunks of PIPE_CHUNK items rotate over PIPE_SLOTS streams, so the copy engines and
+// host-pointer versions: chunks of pipe_chunk() items rotate over PIPE_SLOTS streams, so the copy engines and
 // the SMs work on different chunks at the same time
 static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                     uint8_t* proofs, uint8_t* status, uint8_t* verdict, uint8_t* gt_unused, size_t n, int mode /*0 prove, 1 prove+verify*/) {
@@ -823,7 +893,8 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
   size_t done = 0;
   int slot = 0;
   while (done < n) {
-    size_t m = n - done < PIPE_CHUNK ? n - done : PIPE_CHUNK;
+    const size_t chunk = pipe_chunk();
+    size_t m = n - done < chunk ? n - done : chunk;
     PipeSlot& s = ctx->slots[slot];
     CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, s.stream));
@@ -845,16 +916,19 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
   return PB_OK;
 }
 int pb_plonk_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
   return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, nullptr, n, 0);
 }
 int pb_plonk_prove_verify(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                           uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && u && proofs && status && verdict);
   ARG(ctx->vk_valid);
   return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, nullptr, n, 1);
 }
 int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal && u && verdict);
   DeviceGuard g(ctx->device);
   DEV(dp, n * 34); DEV(dc, n * 5); DEV(du, n); DEV(dv, n); DEV(dg, n * 4);
@@ -868,12 +942,22 @@ int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* cha
 }
 
 int pb_tally_dev(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t n, int64_t* counts, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(counts);
   if (n == 0) return PB_OK;
   unsigned grid = blocks_for(n, BLOCK_LIGHT);
   if (grid > 148u * 8u) grid = 148u * 8u;
   tally_kernel<<<grid, BLOCK_LIGHT, 0, S(stream)>>>(proofs, status, verdict, n, reinterpret_cast<unsigned long long*>(counts));
   LAUNCH_CHECK("tally_kernel");
+  return PB_OK;
+}
+
+int pb_peak_probe_dev(int kind, uint32_t iters, uint64_t* ops_out_host, uint32_t* sink_dev, void* stream) {
+  ARG(kind >= 0 && kind <= 3 && ops_out_host && sink_dev);
+  const unsigned grid = 148u * 8u, block = 256u;
+  peak_probe_kernel<<<grid, block, 0, S(stream)>>>(kind, iters, sink_dev);
+  LAUNCH_CHECK("peak_probe_kernel");
+  *ops_out_host = (uint64_t)grid * block * iters * (uint64_t)PROBE_OPS_PER_ITER;
   return PB_OK;
 }
 

@@ -640,4 +640,51 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) tally_kernel(const uint8_t* __res
   if (threadIdx.x < 18 && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------ roofline probes
+// Dependency-free instruction streams (16 independent chains per thread) to measure the issue-rate ceilings the
+// integer kernels are charged against.  PROBE_OPS_PER_ITER thread-level operations per loop iteration.
+constexpr int PROBE_OPS_PER_ITER = 64;
+__global__ void __launch_bounds__(256) peak_probe_kernel(int kind, uint32_t iters, uint32_t* __restrict__ sink) {
+  __shared__ uint8_t lut[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = (uint8_t)((i * 7 + 3) & 0xFF);
+  __syncthreads();
+  uint32_t r[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) r[k] = threadIdx.x * 16u + k + blockIdx.x;
+  const uint32_t m = 2654435761u + blockIdx.x, c = 40503u + threadIdx.x;
+  if (kind == 0) {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = r[k] * m + c;                       // IMAD
+    }
+  } else if (kind == 1) {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = (r[k] ^ m) + (r[(k + 1) & 15] & c);  // LOP3 + IADD3 -> counted as one op each, 2 per statement
+    }
+  } else if (kind == 2) {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 2; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) { r[k] = r[k] * m + c; r[k] ^= (r[k] >> 7); }   // IMAD + (SHF, LOP3)
+    }
+  } else {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = lut[(r[k] + k * 61u) & 1023u] + (r[k] >> 3);   // LDS.U8 + address math
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) x ^= r[k];
+  if (x == 0xDEADBEEFu) sink[0] = x;
+}
+
 }  // namespace pb
