@@ -146,6 +146,10 @@ int pb_matrix_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, 
 int pb_matrix_inv_dev(const uint8_t *a, uint8_t *out, uint32_t dim, size_t n, void *stream);
 int pb_matrix_inv(const uint8_t *a, uint8_t *out, uint32_t dim, size_t n);
 
+/* matrix_gauss_jordan (matrix.h:100-149): in-place reduced row echelon form, rows <= 8, cols <= 16 */
+int pb_matrix_gauss_jordan_dev(uint8_t *a, uint32_t rows, uint32_t cols, size_t n, void *stream);
+int pb_matrix_gauss_jordan(uint8_t *a, uint32_t rows, uint32_t cols, size_t n);
+
 /* ---- kernel family (3): g1.h, g2.h, srs.h */
 /* g1_add / g1_double / g1_neg (g1.h:37-89); b is ignored for DOUBLE and NEG */
 int pb_g1_op_dev(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream);

@@ -403,6 +403,27 @@ int pb_matrix_inv(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n) {
   return PB_OK;
 }
 
+int pb_matrix_gauss_jordan_dev(uint8_t* a, uint32_t rows, uint32_t cols, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(a && rows >= 1 && cols >= 1 && rows <= 8 && cols <= 16);
+  matrix_rref_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(a, (int)rows, (int)cols, n);
+  LAUNCH_CHECK("matrix_rref_kernel");
+  return PB_OK;
+}
+int pb_matrix_gauss_jordan(uint8_t* a, uint32_t rows, uint32_t cols, size_t n) {
+  if (n == 0) return PB_OK;
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(a);
+  DEV(da, n * rows * cols);
+  H2D(da, a, n * rows * cols);
+  rc = pb_matrix_gauss_jordan_dev(da.as<uint8_t>(), rows, cols, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(a, da, n * rows * cols);
+  return PB_OK;
+}
+
 // ------------------------------------------------------------------ family (3)
 int pb_g1_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer

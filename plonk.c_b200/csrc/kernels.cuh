@@ -292,28 +292,17 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) matrix_mul_kernel(const uint8_t* 
     }
 }
 
-// matrix_inv = Gauss-Jordan on (M | I), matrix.h:100-176, including its pivot search order and its
-// lack of singularity detection; dim <= 8
-__global__ void __launch_bounds__(BLOCK_LIGHT) matrix_inv_kernel(const uint8_t* __restrict__ a, uint8_t* __restrict__ out, int dim, size_t n) {
-  __shared__ FieldTables ft;
-  build_field_tables(ft);
-  __syncthreads();
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint8_t M[8 * 16];
-  const int rows = dim, cols = 2 * dim;
-  for (int r = 0; r < rows; r++)
-    for (int c = 0; c < cols; c++) M[r * cols + c] = c < dim ? a[i * dim * dim + r * dim + c] : (c - dim == r ? 1 : 0);
+// matrix_gauss_jordan, matrix.h:100-149: in-place RREF with the reference's pivot search (walk down the rows of the
+// lead column, then advance the column), row swap, normalisation by 1/pivot and elimination of every other row.
+PB_D void rref(const FieldTables& ft, uint8_t* M, int rows, int cols) {
   int lead = 0;
-  bool done = false;
-  for (int r = 0; r < rows && !done; r++) {
-    if (cols <= lead) break;
+  for (int r = 0; r < rows; r++) {
+    if (cols <= lead) return;
     int p = r;
     while (M[p * cols + lead] == 0) {
       p++;
-      if (p == rows) { p = r; lead++; if (lead == cols) { done = true; break; } }
+      if (p == rows) { p = r; lead++; if (lead == cols) return; }
     }
-    if (done) break;
     if (p != r) for (int c = 0; c < cols; c++) { uint8_t t = M[p * cols + c]; M[p * cols + c] = M[r * cols + c]; M[r * cols + c] = t; }
     uint32_t d = M[r * cols + lead];
     if (d != 0) { uint32_t di = inv17(ft, d); for (int c = 0; c < cols; c++) M[r * cols + c] = (uint8_t)mul17(M[r * cols + c], di); }
@@ -324,6 +313,33 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) matrix_inv_kernel(const uint8_t* 
     }
     lead++;
   }
+}
+
+// rows <= 8, cols <= 16
+__global__ void __launch_bounds__(BLOCK_LIGHT) matrix_rref_kernel(uint8_t* __restrict__ a, int rows, int cols, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t M[8 * 16];
+  for (int k = 0; k < rows * cols; k++) M[k] = a[i * rows * cols + k];
+  rref(ft, M, rows, cols);
+  for (int k = 0; k < rows * cols; k++) a[i * rows * cols + k] = M[k];
+}
+
+// matrix_inv = Gauss-Jordan on (M | I), matrix.h:151-176, without singularity detection; dim <= 8
+__global__ void __launch_bounds__(BLOCK_LIGHT) matrix_inv_kernel(const uint8_t* __restrict__ a, uint8_t* __restrict__ out, int dim, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t M[8 * 16];
+  const int rows = dim, cols = 2 * dim;
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) M[r * cols + c] = c < dim ? a[i * dim * dim + r * dim + c] : (c - dim == r ? 1 : 0);
+  rref(ft, M, rows, cols);
   for (int r = 0; r < rows; r++)
     for (int c = 0; c < dim; c++) out[i * dim * dim + r * dim + c] = M[r * cols + dim + c];
 }
