@@ -212,6 +212,11 @@ int pb_plonk_verify_completed_dev(const pb_ctx *ctx, const uint8_t *proofs, cons
  * Host-pointer version: chunked, copies overlapped with compute on internal streams. */
 int pb_plonk_prove_verify_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                               const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n, void *stream);
+/* same, recording the CUDA event `mid_event` (a cudaEvent_t passed as void*, may be NULL) between the prover and the
+ * verifier launch, so that a caller can time the two kernels of one call separately */
+int pb_plonk_prove_verify_ex_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                                 const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n, void *stream,
+                                 void *mid_event);
 int pb_plonk_prove_verify(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                           const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n);
 /* on-device tally: counts[0..15] += number of items per status byte (0..14, 15 = anything else),

@@ -89,7 +89,12 @@ struct pb_ctx {
   CircuitConst cc{};
   VerifyKey vk{};
   bool vk_valid = true;               // false when a selector polynomial is longer than the SRS
-  ProverTables* d_tables = nullptr;   // device
+  ProverTables* d_tables = nullptr;   // device: exact sequential path (any SRS)
+  ProverPairTables* d_pair_tables = nullptr;   // device: fast path, only when srs_canonical
+  VerifyTables* d_verify_tables = nullptr;     // device: fast path, only when key_canonical
+  bool srs_canonical = false;         // every SRS point is a canonically encoded point of E(F_101)
+  bool key_canonical = false;         // same for the nine verifier-key points
+  bool force_exact = false;           // PB_FORCE_EXACT=1: always take the sequential path (tests)
   uint32_t* d_srs_table = nullptr;    // device, [srs_len][17]
   uint32_t srs_len = 0;
   std::vector<uint8_t> srs_g1s;       // host copy, [srs_len][3]
@@ -780,6 +785,33 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
   if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
   cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice);
+  {
+    // fast-path eligibility: canonical encodings (checked here) and curve membership (checked on the device)
+    std::vector<uint8_t> on(srs_len);
+    if ((rc = pb_g1_is_on_curve(srs_g1s, on.data(), srs_len))) return bail(rc);
+    bool canon = true;
+    for (uint32_t i = 0; i < srs_len; i++) {
+      const uint8_t* g = srs_g1s + 3 * i;
+      canon = canon && on[i] && g[2] <= 1 && !(g[2] == 1 && (g[0] | g[1]));
+    }
+    c->srs_canonical = canon;
+    if (const char* e2 = getenv("PB_FORCE_EXACT")) c->force_exact = e2[0] == '1';
+    if (canon) {
+      ProverPairTables ppt;
+      memset(&ppt, 0, sizeof ppt);
+      ppt.ft = pt.ft;
+      uint32_t *d_single = nullptr, *d_pairs = nullptr;
+      if (cudaMalloc(&d_single, sizeof pt.T) != cudaSuccess || cudaMalloc(&d_pairs, sizeof ppt.T2) != cudaSuccess)
+        return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+      cudaMemcpy(d_single, pt.T, sizeof pt.T, cudaMemcpyHostToDevice);
+      pair_table_kernel<<<8, 256>>>(d_single, PROVER_SRS_ROWS, PROVER_PAIR_ROWS, d_pairs);
+      cudaError_t e3 = cudaMemcpy(ppt.T2, d_pairs, sizeof ppt.T2, cudaMemcpyDeviceToHost);
+      cudaFree(d_single); cudaFree(d_pairs);
+      if (e3 != cudaSuccess) return bail(cuda_fail(e3, "pair_table_kernel"));
+      if (cudaMalloc(&c->d_pair_tables, sizeof ppt) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+      cudaMemcpy(c->d_pair_tables, &ppt, sizeof ppt, cudaMemcpyHostToDevice);
+    }
+  }
   std::vector<uint32_t> tab(rows_full * 17);
   e = cudaMemcpy(tab.data(), c->d_srs_table, tab.size() * 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return bail(cuda_fail(e, "srs table read-back"));
@@ -811,6 +843,27 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
     c->vkey_bytes[24] = srs_g1s[0]; c->vkey_bytes[25] = srs_g1s[1]; c->vkey_bytes[26] = srs_g1s[2] ? 1 : 0;
     c->vk.g2_one = G2{srs_g2[0], srs_g2[1]};
     c->vk.g2_s = G2{srs_g2[2], srs_g2[3]};
+    // fast-path verifier tables: only when all nine key points are canonically encoded curve points
+    uint8_t on[9];
+    if ((rc = pb_g1_is_on_curve(c->vkey_bytes, on, 9))) return bail(rc);
+    bool canon = c->vk_valid;
+    for (int j = 0; j < 9; j++) {
+      const uint8_t* g = c->vkey_bytes + 3 * j;
+      canon = canon && on[j] && g[2] <= 1 && !(g[2] == 1 && (g[0] | g[1]));
+    }
+    c->key_canonical = canon;
+    if (canon) {
+      uint8_t* d_key = nullptr; uint32_t* d_kt = nullptr;
+      if (cudaMalloc(&d_key, 32) != cudaSuccess || cudaMalloc(&d_kt, 9 * 17 * 4) != cudaSuccess ||
+          cudaMalloc(&c->d_verify_tables, sizeof(VerifyTables)) != cudaSuccess)
+        return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+      cudaMemcpy(d_key, c->vkey_bytes, 27, cudaMemcpyHostToDevice);
+      srs_table_kernel<<<1, 256>>>(d_key, 9, 9, d_kt);                  // rows c * K_j by the reference's g1_mul
+      verify_tables_kernel<<<1, 256>>>(d_kt, c->d_verify_tables);
+      cudaError_t e4 = cudaDeviceSynchronize();
+      cudaFree(d_key); cudaFree(d_kt);
+      if (e4 != cudaSuccess) return bail(cuda_fail(e4, "verify_tables_kernel"));
+    }
   }
   *out = c;
   return PB_OK;
@@ -820,6 +873,8 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (!c) return PB_OK;
   DeviceGuard g(c->device);
   if (c->d_tables) cudaFree(c->d_tables);
+  if (c->d_pair_tables) cudaFree(c->d_pair_tables);
+  if (c->d_verify_tables) cudaFree(c->d_verify_tables);
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -856,15 +911,35 @@ int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* o
   return PB_OK;
 }
 
+// prove launch: pair tables when the SRS is canonical, the sequential tables otherwise
+static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status,
+                        size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict) {
+  if (ctx->srs_canonical && !ctx->force_exact)
+    prove_kernel<ProverPairTables><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, chal, proofs, status, n,
+                                                                           done_list, done_count, verdict);
+  else
+    prove_kernel<ProverTables><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n,
+                                                                       done_list, done_count, verdict);
+  LAUNCH_CHECK("prove_kernel");
+  return PB_OK;
+}
+static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
+                         const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st) {
+  if (ctx->key_canonical && !ctx->force_exact && !(status && !done_list))
+    verify_fast_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n);
+  else
+    verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n);
+  LAUNCH_CHECK("verify_kernel");
+  return PB_OK;
+}
+
 int pb_plonk_prove_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs,
                        uint8_t* status, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
   if (n == 0) return PB_OK;
-  prove_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n);
-  LAUNCH_CHECK("prove_kernel");
-  return PB_OK;
+  return launch_prove(ctx, witness, rnd, chal, proofs, status, n, S(stream), nullptr, nullptr, nullptr);
 }
 int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt,
                         size_t n, void* stream) {
@@ -873,9 +948,7 @@ int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t*
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && aligned16(chal) && (!gt || aligned16(gt)));
   if (n == 0) return PB_OK;
-  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, nullptr, verdict, gt, n);
-  LAUNCH_CHECK("verify_kernel");
-  return PB_OK;
+  return launch_verify(ctx, proofs, chal, u, nullptr, nullptr, nullptr, verdict, gt, n, S(stream));
 }
 int pb_plonk_verify_completed_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
                                   uint8_t* verdict, size_t n, void* stream) {
@@ -883,22 +956,40 @@ int pb_plonk_verify_completed_dev(const pb_ctx* ctx, const uint8_t* proofs, cons
   ARG(ctx && proofs && chal && u && status && verdict);
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && aligned16(chal));
-  if (n == 0) return PB_OK;
-  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, status, verdict, nullptr, n);
-  LAUNCH_CHECK("verify_kernel");
-  return PB_OK;
+  ARG(n < 0xFFFFFFFFull);
+  cudaStream_t st = S(stream);
+  if (!(ctx->key_canonical && !ctx->force_exact)) return launch_verify(ctx, proofs, chal, u, status, nullptr, nullptr, verdict, nullptr, n, st);
+  uint32_t* scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (n + 4) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
+  compact_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, st>>>(status, n, scratch + 4, scratch, verdict);
+  int rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                               uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
+  return pb_plonk_prove_verify_ex_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, nullptr);
+}
+int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                                 uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(u && verdict);
   ARG(ctx && ctx->vk_valid);
-  int rc = pb_plonk_prove_dev(ctx, witness, rnd, chal, proofs, status, n, stream);
-  if (rc) return rc;
-  if (n == 0) return PB_OK;
-  verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, S(stream)>>>(ctx->vk, proofs, chal, u, status, verdict, nullptr, n);
-  LAUNCH_CHECK("verify_kernel");
-  return PB_OK;
+  ARG(witness && rnd && chal && proofs && status);
+  ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
+  ARG(n < 0xFFFFFFFFull);
+  // The prover appends the indices of the completed proofs to a dense list (stream-ordered scratch), the verifier walks
+  // that list: no lane idles on the ~40% of random inputs on which the reference exits.
+  cudaStream_t st = S(stream);
+  uint32_t* scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (n + 4) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
+  int rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict);
+  if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
+  if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 // host-pointer versions: chunks of pipe_chunk() items rotate over PIPE_SLOTS streams, so the copy engines and

@@ -511,8 +511,9 @@ PB_D void stage_out(uint8_t* __restrict__ g, const uint8_t* smem, size_t first, 
   for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) dst[k] = smem[k];
 }
 
+template <typename Tables>
 struct __align__(16) ProveSmem {
-  __align__(16) ProverTables tb;
+  __align__(16) Tables tb;
   __align__(16) uint8_t wit[BLOCK * 12];
   __align__(16) uint8_t rnd[BLOCK * 9];
   __align__(16) uint8_t chal[BLOCK * 5];
@@ -520,13 +521,18 @@ struct __align__(16) ProveSmem {
   __align__(16) uint8_t status[BLOCK];
 };
 
-__global__ void __launch_bounds__(BLOCK) prove_kernel(const __grid_constant__ CircuitConst cc, const ProverTables* __restrict__ gtb,
+// Tables = ProverTables (any SRS, the reference's order of additions) or ProverPairTables (canonical on-curve SRS).
+// done_list / done_count (optional): indices of the completed proofs (status 0) are appended, one atomic per warp,
+// so that the verifier runs on a dense list; verdict (optional) gets 0xFF for every item that did not complete.
+template <typename Tables>
+__global__ void __launch_bounds__(BLOCK) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
                                                       const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
-                                                      uint8_t* __restrict__ status, size_t n) {
-  __shared__ ProveSmem sm;
+                                                      uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
+                                                      uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict) {
+  __shared__ ProveSmem<Tables> sm;
   const int tid = threadIdx.x;
-  for (int k = tid; k < (int)(sizeof(ProverTables) / 4); k += BLOCK)
+  for (int k = tid; k < (int)(sizeof(Tables) / 4); k += BLOCK)
     reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
   const size_t first = (size_t)blockIdx.x * BLOCK;
   stage_in<12, BLOCK>(sm.wit, wit, first, n);
@@ -570,6 +576,16 @@ __global__ void __launch_bounds__(BLOCK) prove_kernel(const __grid_constant__ Ci
 #pragma unroll
   for (int j = 0; j < 7; j++) po[27 + j] = okp ? (uint8_t)o.sc[j] : 0;
   sm.status[tid] = (uint8_t)o.status;
+  if (done_list) {
+    const bool done = live && okp;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, done);
+    const int lane = tid & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (m && lane == leader) base = atomicAdd(done_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader < 0 ? 0 : leader);
+    if (done) done_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(first + tid);
+    if (live && !okp && verdict) verdict[first + tid] = 0xFF;
+  }
   __syncthreads();
   stage_out<34, BLOCK>(proofs, sm.proof, first, n);
   stage_out<1, BLOCK>(status, sm.status, first, n);
@@ -611,6 +627,111 @@ __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ V
   verify_one(key, sm.ft, pbytes, op, ch, u[i], o);
   verdict[i] = (uint8_t)o.verdict;
   if (gt) reinterpret_cast<uint32_t*>(gt)[i] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+}
+
+// Fast-path verifier (canonical on-curve key).  Two addressing modes: dense (item = global thread index, records
+// staged through shared memory) or list (done_list/done_count from the prover: thread t handles item done_list[t],
+// so that no lane idles on a proof that never completed).
+struct __align__(16) VerifyFastSmem {
+  __align__(16) FieldTables ft;
+  __align__(16) VerifyTables vt;
+  __align__(16) uint8_t proof[BLOCK * 34];
+  __align__(16) uint8_t chal[BLOCK * 5];
+};
+
+__global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constant__ VerifyKey key, const VerifyTables* __restrict__ gvt,
+                                                            const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
+                                                            const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
+                                                            const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
+                                                            uint8_t* __restrict__ gt, size_t n) {
+  __shared__ VerifyFastSmem sm;
+  const int tid = threadIdx.x;
+  const size_t first = (size_t)blockIdx.x * BLOCK;
+  const size_t limit = done_list ? (size_t)*done_count : n;
+  if (first >= limit) return;                                             // whole block beyond the dense list
+  build_field_tables(sm.ft);
+  for (int k = tid; k < (int)(sizeof(VerifyTables) / 4); k += BLOCK)
+    reinterpret_cast<uint32_t*>(&sm.vt)[k] = reinterpret_cast<const uint32_t*>(gvt)[k];
+  size_t item = first + tid;
+  const bool live = item < limit;
+  if (done_list) {
+    item = live ? done_list[item] : 0;
+    const uint8_t* pr = proofs + item * 34;                               // gather: 34 + 5 contiguous bytes per item
+    const uint8_t* cr = chal + item * 5;
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 34; k++) sm.proof[tid * 34 + k] = pr[k];
+#pragma unroll
+      for (int k = 0; k < 5; k++) sm.chal[tid * 5 + k] = cr[k];
+    }
+  } else {
+    stage_in<34, BLOCK>(sm.proof, proofs, first, n);
+    stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  }
+  __syncthreads();
+  if (!live) return;
+  uint32_t pbytes[27], op[7], ch[5];
+#pragma unroll
+  for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+#pragma unroll
+  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+  VerifyOut o;
+  verify_one_fast(key, sm.vt, sm.ft, pbytes, op, ch, u[item], o);
+  verdict[item] = (uint8_t)o.verdict;
+  if (gt) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+}
+
+// status bytes -> dense list of the completed items (for pb_plonk_verify_completed_dev, where the list does not come
+// from the prover); verdict gets 0xFF elsewhere
+__global__ void __launch_bounds__(BLOCK_LIGHT) compact_kernel(const uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
+                                                              uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const bool done = live && status[i] == 0;
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, done);
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (m && lane == leader) base = atomicAdd(done_count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader < 0 ? 0 : leader);
+  if (done) done_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+  if (live && !done) verdict[i] = 0xFF;
+}
+
+// pair tables from single-point rows: out[j][c0*17 + c1] = g1_add(T[2j][c0], T[2j+1][c1]) (row beyond `rows`: identity)
+__global__ void pair_table_kernel(const uint32_t* __restrict__ T, uint32_t rows, uint32_t pairs, uint32_t* __restrict__ out) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < pairs * 289u; k += gridDim.x * blockDim.x) {
+    const uint32_t j = k / 289u, c0 = (k % 289u) / 17u, c1 = k % 17u;
+    const G1 p = 2 * j < rows ? unpack_g1(T[(2 * j) * 17 + c0]) : g1_identity();
+    const G1 q = 2 * j + 1 < rows ? unpack_g1(T[(2 * j + 1) * 17 + c1]) : g1_identity();
+    const G1 r = g1_add(ft, p, q);
+    out[k] = pack_g1(r.x, r.y, r.inf);
+  }
+}
+
+// VerifyTables from the single-point rows of the nine key points, in VerifyKey order qm ql qr qo qc s1 s2 s3 one
+__global__ void verify_tables_kernel(const uint32_t* __restrict__ KT /*[9][17]*/, VerifyTables* __restrict__ out) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < 4u * 289u + 17u; k += blockDim.x) {
+    G1 r;
+    if (k < 4u * 289u) {
+      const uint32_t t = k / 289u, a = (k % 289u) / 17u, b = k % 17u;
+      const int ia[4] = {0, 2, 4, 5}, ib[4] = {1, 3, 7, 6};            // (qm,ql) (qr,qo) (qc,s3) (s1,s2)
+      G1 p = unpack_g1(KT[ia[t] * 17 + a]), q = unpack_g1(KT[ib[t] * 17 + b]);
+      if (t == 2) q = g1_neg(q);                                        // - d_s3 [S3]
+      r = g1_add(ft, p, q);
+      out->P2[t][k % 289u] = pack_g1(r.x, r.y, r.inf);
+    } else {
+      r = g1_neg(unpack_g1(KT[8 * 17 + (k - 4u * 289u)]));              // - e [1]
+      out->one_neg[k - 4u * 289u] = pack_g1(r.x, r.y, r.inf);
+    }
+  }
 }
 
 // the eight preprocessed commitments of the verifier key: srs_eval_at_s of the interpolated selector and

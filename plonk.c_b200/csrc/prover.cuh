@@ -43,6 +43,18 @@ struct ProverTables {
   uint32_t T[PROVER_SRS_ROWS][17];
 };
 
+// Fast-path tables, used when every SRS point is a canonically encoded point of E(F_101) (context creation checks
+// it; true for both benchmark SRS modes).  The reference's additions are then the exact group law of a finite
+// abelian group with a canonical representation per element, so the ORDER of the additions no longer matters and
+// neither does adding the (canonical) identity.  T2[j][c0*17 + c1] = c0*g1s[2j] + c1*g1s[2j+1], built on the device
+// with the reference's own g1_add from the single-point rows -- for a 2-term polynomial it is literally the
+// reference's srs_eval_at_s.  Halves the number of additions per commitment.
+constexpr int PROVER_PAIR_ROWS = (PROVER_SRS_ROWS + 1) / 2;
+struct ProverPairTables {
+  FieldTables ft;
+  uint32_t T2[PROVER_PAIR_ROWS][289];
+};
+
 PB_HD G1 unpack_g1(uint32_t w) { return G1{w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 1u}; }
 PB_HD uint32_t pack_g1(uint32_t x, uint32_t y, uint32_t inf) { return x | (y << 8) | (inf << 16); }
 
@@ -106,13 +118,26 @@ PB_HD G1 commit(const ProverTables& tb, const uint32_t (&c)[N], uint32_t len) {
   return acc;
 }
 
+template <int N>
+PB_HD G1 commit(const ProverPairTables& tb, const uint32_t (&c)[N], uint32_t /*len: zero coefficients are no-ops here*/) {
+  static_assert(N >= 2 && N <= PROVER_SRS_ROWS, "prover polynomial shape");
+  G1 acc = unpack_g1(tb.T2[0][c[0] * 17u + c[1]]);
+#pragma unroll
+  for (int j = 1; j < (N + 1) / 2; j++) {
+    const uint32_t idx = c[2 * j] * 17u + (2 * j + 1 < N ? c[2 * j + 1] : 0u);
+    acc = g1_add(tb.ft, acc, unpack_g1(tb.T2[j][idx]));
+  }
+  return acc;
+}
+
 struct ProofOut {
   G1 pts[9];        // a b c z t_lo t_mid t_hi W_z W_zw   (PROOF field order, plonk.h:24-41)
   uint32_t sc[7];   // a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z
   uint32_t status;  // SURVEY.md Appendix B row of the first exit that fires, 0 = completed
 };
 
-PB_HD void prove_one(const CircuitConst& cc, const ProverTables& tb,
+template <typename Tables>
+PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
                     const uint32_t (&wa)[4], const uint32_t (&wb)[4], const uint32_t (&wc)[4],
                     const uint32_t (&rnd)[9], uint32_t alpha, uint32_t beta, uint32_t gamma,
                     uint32_t z, uint32_t v, ProofOut& out) {

@@ -5,6 +5,7 @@
 // emulation of g1_mul / g1_add / g1_neg / pairing from curve.cuh.
 #pragma once
 #include "curve.cuh"
+#include "prover.cuh"   // pack_g1 / unpack_g1
 
 namespace pb {
 
@@ -97,6 +98,98 @@ PB_HD void verify_one(const VerifyKey& k, const FieldTables& ft, const uint32_t 
   out.lhs = pairing17(ft, lhs_p, k.g2_s);
   out.rhs = pairing17(ft, rhs_p, k.g2_one);
   out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;   // gtp_equal, pairing.h:9-11
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path.  Preconditions (checked at context creation / per proof): every key point and srs.g1s[0] is a canonically
+// encoded point of E(F_101), and the proof's nine commitments passed step 1.  Every value below is then an element of
+// one finite abelian group with a canonical encoding, the reference's g1_add / g1_mul / g1_neg ARE that group's law,
+// and the two points handed to the pairing are the same triples whatever the order of the additions.  That allows:
+//   - fixed-base pair tables for the nine preprocessed points (two scalars -> one look-up + one addition),
+//   - one joint double-and-add (Straus, 2 points per 4-entry sub-table) for the eight proof points of step 11's
+//     right-hand side instead of eight separate g1_mul calls.
+struct VerifyTables {
+  uint32_t P2[4][289];     // [0] a*qM + b*qL   [1] a*qR + b*qO   [2] a*qC - b*S3   [3] a*S1 + b*S2   (index a*17 + b)
+  uint32_t one_neg[17];    // -(c * g1s[0])
+};
+
+PB_HD G1 pick4(uint32_t sel, G1 p, G1 q, G1 pq) {   // sel: 0 -> identity, 1 -> p, 2 -> q, 3 -> p + q
+  G1 r = g1_identity();
+  if (sel == 1u) r = p;
+  if (sel == 2u) r = q;
+  if (sel == 3u) r = pq;
+  return r;
+}
+
+PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const FieldTables& ft, const uint32_t (&pb)[27],
+                          const uint32_t (&op)[7], const uint32_t (&ch)[5], uint32_t u, VerifyOut& out) {
+  out.lhs = GT{0u, 0u};
+  out.rhs = GT{0u, 0u};
+  bool bad_pt = false;
+  G1 P[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    uint32_t x = pb[3 * j], y = pb[3 * j + 1], f = pb[3 * j + 2];
+    bad_pt |= x > 100u || y > 100u || f > 1u || (f == 1u && (x | y) != 0u);
+    P[j] = G1{x > 100u ? 0u : x, y > 100u ? 0u : y, f != 0u ? 1u : 0u};
+    bad_pt |= !g1_is_on_curve(P[j]);
+  }
+  bool bad_sc = u > 16u;
+#pragma unroll
+  for (int j = 0; j < 7; j++) bad_sc |= op[j] > 16u;
+#pragma unroll
+  for (int j = 0; j < 5; j++) bad_sc |= ch[j] > 16u;
+  if (bad_pt) { out.verdict = 2u; return; }
+  if (bad_sc) { out.verdict = 3u; return; }
+
+  const uint32_t a_z = op[0], b_z = op[1], c_z = op[2], s1_z = op[3], s2_z = op[4], r_z = op[5], zw_z = op[6];
+  const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
+  constexpr uint32_t K1 = 2u, K2 = 3u, OMEGA = 4u;
+  const uint32_t z2 = red17(z * z), z3 = red17(z2 * z), z4 = red17(z2 * z2);
+  const uint32_t zh_z = sub17(z4, 1u);
+  const uint32_t l1_z = red17(13u * (1u + z + z2 + z3));
+  const uint32_t alpha2 = red17(alpha * alpha);
+  const uint32_t pa = red17(a_z + beta * s1_z + gamma), pbb = red17(b_z + beta * s2_z + gamma);
+  const uint32_t pab = red17(pa * pbb);
+  const uint32_t perm = red17(red17(red17(pab * red17(c_z + gamma)) * zw_z) * alpha);
+  const uint32_t t_num = red17(r_z + 2u * P17 - perm - red17(l1_z * alpha2));
+  const uint32_t t_z = red17(t_num * inv17(ft, zh_z));
+  const uint32_t bz = red17(beta * z);
+  const uint32_t ga = red17(a_z + bz + gamma), gb = red17(b_z + K1 * bz + gamma), gc = red17(c_z + K2 * bz + gamma);
+  const uint32_t d_z = red17(red17(red17(red17(red17(ga * gb) * gc) * alpha) * v) + red17(red17(l1_z * alpha2) * v) + u);
+  const uint32_t d_s3 = red17(red17(red17(red17(pab * alpha) * v) * beta) * zw_z);
+  const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
+  const uint32_t z6 = red17(z4 * z2), z12 = red17(z6 * z6);
+  const uint32_t e = red17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);
+
+  // the preprocessed part of [D] + [F] - [E]: five look-ups
+  G1 acc = unpack_g1(vt.P2[0][red17(red17(a_z * b_z) * v) * 17u + red17(a_z * v)]);
+  acc = g1_add(ft, acc, unpack_g1(vt.P2[1][red17(b_z * v) * 17u + red17(c_z * v)]));
+  acc = g1_add(ft, acc, unpack_g1(vt.P2[2][v * 17u + d_s3]));
+  acc = g1_add(ft, acc, unpack_g1(vt.P2[3][v5 * 17u + v6]));
+  acc = g1_add(ft, acc, unpack_g1(vt.one_neg[e]));
+  acc = g1_add(ft, acc, P[4]);                                         // [t_lo]
+
+  // z[W_z] + u z omega [W_zw] + z^6[t_mid] + z^12[t_hi] + v^2[a] + v^3[b] + v^4[c] + d_z[z]: joint double-and-add,
+  // most significant bit first, two points per 4-entry sub-table
+  const G1 A0 = P[7], B0 = P[8], A1 = P[5], B1 = P[6], A2 = P[0], B2 = P[1], A3 = P[2], B3 = P[3];
+  const uint32_t sa0 = z, sb0 = red17(red17(u * z) * OMEGA), sa1 = z6, sb1 = z12, sa2 = v2, sb2 = v3, sa3 = v4, sb3 = d_z;
+  const G1 S0 = g1_add(ft, A0, B0), S1 = g1_add(ft, A1, B1), S2 = g1_add(ft, A2, B2), S3 = g1_add(ft, A3, B3);
+  G1 s = g1_identity(), l = g1_identity();
+  for (int bit = 4; bit >= 0; --bit) {
+    s = g1_double(ft, s);
+    s = g1_add(ft, s, pick4(((sa0 >> bit) & 1u) | (((sb0 >> bit) & 1u) << 1), A0, B0, S0));
+    s = g1_add(ft, s, pick4(((sa1 >> bit) & 1u) | (((sb1 >> bit) & 1u) << 1), A1, B1, S1));
+    s = g1_add(ft, s, pick4(((sa2 >> bit) & 1u) | (((sb2 >> bit) & 1u) << 1), A2, B2, S2));
+    s = g1_add(ft, s, pick4(((sa3 >> bit) & 1u) | (((sb3 >> bit) & 1u) << 1), A3, B3, S3));
+    l = g1_double(ft, l);                                              // u [W_zw] for the left-hand side
+    l = g1_add(ft, l, pick4((u >> bit) & 1u, B0, B0, B0));
+  }
+  const G1 rhs_p = g1_add(ft, acc, s);
+  const G1 lhs_p = g1_add(ft, P[7], l);
+  out.lhs = pairing17(ft, lhs_p, k.g2_s);
+  out.rhs = pairing17(ft, rhs_p, k.g2_one);
+  out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;
 }
 
 }  // namespace pb

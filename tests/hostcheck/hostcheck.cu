@@ -87,6 +87,69 @@ void hc_prove(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wi
     status[i] = (uint8_t)o.status;
   }
 }
+// fast path: pair tables built from the single-point rows exactly as pair_table_kernel does
+void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
+                    uint8_t* proofs, uint8_t* status, size_t n) {
+  CircuitConst cc;
+  memcpy(&cc, cc_words, sizeof cc);
+  static ProverPairTables tb;
+  tb.ft = make_ft();
+  for (uint32_t k = 0; k < PROVER_PAIR_ROWS * 289u; k++) {
+    const uint32_t j = k / 289u, c0 = (k % 289u) / 17u, c1 = k % 17u;
+    const G1 p = unpack_g1(table[(2 * j) * 17 + c0]);
+    const G1 q = 2 * j + 1 < (uint32_t)PROVER_SRS_ROWS ? unpack_g1(table[(2 * j + 1) * 17 + c1]) : g1_identity();
+    const G1 r = g1_add(tb.ft, p, q);
+    tb.T2[j][k % 289u] = pack_g1(r.x, r.y, r.inf);
+  }
+  for (size_t i = 0; i < n; i++) {
+    uint32_t wa[4], wb[4], wc[4], r[9];
+    for (int k = 0; k < 4; k++) { wa[k] = wit[12 * i + k]; wb[k] = wit[12 * i + 4 + k]; wc[k] = wit[12 * i + 8 + k]; }
+    for (int k = 0; k < 9; k++) r[k] = rnd[9 * i + k];
+    const uint8_t* ch = chal + 5 * i;
+    ProofOut o;
+    prove_one(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+    uint8_t* po = proofs + 34 * i;
+    memset(po, 0, 34);
+    if (o.status == 0) {
+      for (int j = 0; j < 9; j++) st(po + 3 * j, o.pts[j]);
+      for (int j = 0; j < 7; j++) po[27 + j] = (uint8_t)o.sc[j];
+    }
+    status[i] = (uint8_t)o.status;
+  }
+}
+// fast-path verifier: tables built exactly as verify_tables_kernel does, from g1_mul rows of the nine key points
+void hc_verify_fast(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+  FieldTables ft = make_ft();
+  VerifyKey k;
+  G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
+  for (int j = 0; j < 9; j++) *dst[j] = ld(key + 3 * j);
+  k.g2_one = G2{key[27], key[28]};
+  k.g2_s = G2{key[29], key[30]};
+  static uint32_t KT[9][17];
+  for (int j = 0; j < 9; j++)
+    for (uint32_t c = 0; c < 17; c++) { G1 r = g1_mul(ft, *dst[j], c); KT[j][c] = pack_g1(r.x, r.y, r.inf); }
+  static VerifyTables vt;
+  const int ia[4] = {0, 2, 4, 5}, ib[4] = {1, 3, 7, 6};
+  for (uint32_t t = 0; t < 4; t++)
+    for (uint32_t a = 0; a < 17; a++)
+      for (uint32_t b = 0; b < 17; b++) {
+        G1 p = unpack_g1(KT[ia[t]][a]), q = unpack_g1(KT[ib[t]][b]);
+        if (t == 2) q = g1_neg(q);
+        G1 r = g1_add(ft, p, q);
+        vt.P2[t][a * 17 + b] = pack_g1(r.x, r.y, r.inf);
+      }
+  for (uint32_t c = 0; c < 17; c++) { G1 r = g1_neg(unpack_g1(KT[8][c])); vt.one_neg[c] = pack_g1(r.x, r.y, r.inf); }
+  for (size_t i = 0; i < n; i++) {
+    uint32_t pbv[27], op[7], ch[5];
+    for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
+    for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
+    for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j];
+    VerifyOut o;
+    verify_one_fast(k, vt, ft, pbv, op, ch, u[i], o);
+    verdict[i] = (uint8_t)o.verdict;
+    if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
+  }
+}
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]
 void hc_verify(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {

@@ -142,7 +142,8 @@ class HostcheckImpl:
     Per-circuit constants and tables are taken from `setup` (an oracle), as cabi.cu takes them from its setup kernels."""
     kind = "hostcheck"
 
-    def __init__(self, setup_oracle):
+    def __init__(self, setup_oracle, fast=False):
+        self.fast = fast          # fast=True: pair-table prover + joint double-and-add verifier (canonical on-curve SRS only)
         path = os.path.join(HERE, "hostcheck", "libpb_hostcheck.so")
         if not os.path.exists(path):
             import __graft_entry__ as g
@@ -244,7 +245,7 @@ class HostcheckImpl:
         wit, rnd, chal = (np.ascontiguousarray(x, np.uint8) for x in (wit, rnd, chal))
         n = wit.shape[0]
         proofs, status = np.zeros((n, 34), np.uint8), np.zeros(n, np.uint8)
-        self.lib.hc_prove(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), _p(chal),
+        (self.lib.hc_prove_pairs if self.fast else self.lib.hc_prove)(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), _p(chal),
                           _p(proofs), _p(status), C.c_size_t(n))
         return proofs, status
 
@@ -253,5 +254,5 @@ class HostcheckImpl:
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        self.lib.hc_verify(_p(key), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt

@@ -146,3 +146,30 @@ def test_misaligned_device_pointer_is_rejected(host, W):
     with pytest.raises(host.PlonkB200Error) as e:
         pk.prove(view, torch.from_numpy(rnd).cuda(), torch.from_numpy(chal).cuda())
     assert e.value.code == host.PB_ERR_ARG
+
+
+def test_protocol_exact_path_forced(host, oracle, W):
+    """PB_FORCE_EXACT=1 makes a context take the sequential (any-SRS) prover and verifier even for a canonical SRS:
+    both code paths must agree with the oracle on the same inputs."""
+    import os
+    os.environ["PB_FORCE_EXACT"] = "1"
+    try:
+        impl = GpuImpl(host, "device")
+        ps.check_protocol(impl, oracle, W, n=30000, modes=[("generator9", lambda W: W.generator_srs(9)), ("identity6", lambda W: W.identity_srs(6))])
+        ps.check_golden_transcript(impl, W)
+    finally:
+        del os.environ["PB_FORCE_EXACT"]
+
+
+def test_prove_verify_fused_matches_separate_calls(host, W):
+    """pb_plonk_prove_verify (prover-fed dense list) == pb_plonk_prove + pb_plonk_verify on the completed proofs."""
+    import torch
+    for mk in (W.generator_srs, W.identity_srs):
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *mk(9))
+        wit, rnd, chal, u = W.make_batch(123, 0, 50000, "U17")
+        d = [torch.from_numpy(x).cuda() for x in (wit, rnd, chal, u)]
+        proofs, status, verdict = pk.prove_verify(*d)
+        p2, s2 = pk.prove(d[0], d[1], d[2])
+        v2 = pk.verify(p2, d[2], d[3])
+        v2 = torch.where(s2 == 0, v2, torch.full_like(v2, 0xFF))
+        assert torch.equal(proofs, p2) and torch.equal(status, s2) and torch.equal(verdict, v2)

@@ -32,3 +32,13 @@ def test_hostcheck_golden(hc, oracle, W):
     ps.check_golden_transcript(hc, W)
     ps.check_groups_golden(hc, W, oracle)
     ps.check_protocol_golden(hc, W)
+
+
+def test_hostcheck_fast_paths(oracle, W):
+    """The fast paths (pair-table commitments, fixed-base verifier tables, joint double-and-add) are only taken for a
+    canonically encoded on-curve SRS; on that domain they must still be byte-identical to the oracle."""
+    import util
+    hcf = HostcheckImpl(oracle, fast=True)
+    modes = [(m, f) for m, f in util.SRS_MODES.items()]
+    ps.check_protocol(hcf, oracle, W, n=20000, modes=modes)
+    ps.check_golden_transcript(hcf, W)
