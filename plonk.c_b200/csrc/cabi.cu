@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -103,6 +104,10 @@ struct pb_ctx {
   uint8_t circuit_dump[48] = {0};
   uint8_t vkey_bytes[27] = {0};
   std::vector<uint8_t> table_bytes;   // [srs_len][17][3]
+  // scratch for the dense list of completed proofs: one buffer per stream (work on one stream is ordered, so a
+  // buffer can be reused by the next call on that stream), grown on demand, freed with the context
+  std::mutex scratch_mu;
+  std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
   std::mutex pipe_mu;
   bool pipe_ready = false;
   PipeSlot slots[PIPE_SLOTS];
@@ -118,6 +123,22 @@ struct DeviceGuard {
   }
   ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
 };
+
+// device scratch of (n + 4) words for `stream`: [0] = counter, [4..] = list
+int scratch_for(const pb_ctx* cctx, cudaStream_t st, size_t n, uint32_t** out) {
+  pb_ctx* c = const_cast<pb_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(c->scratch_mu);
+  auto& slot = c->scratch[st];
+  if (slot.second < n + 4) {
+    if (slot.first) { CU(cudaStreamSynchronize(st)); CU(cudaFree(slot.first)); slot.first = nullptr; slot.second = 0; }
+    size_t cap = n + 4;
+    if (cap < (1u << 16)) cap = 1u << 16;
+    CU(cudaMalloc(reinterpret_cast<void**>(&slot.first), cap * sizeof(uint32_t)));
+    slot.second = cap;
+  }
+  *out = slot.first;
+  return PB_OK;
+}
 
 int pipe_init(pb_ctx* c) {
   if (c->pipe_ready) return PB_OK;
@@ -874,6 +895,7 @@ int pb_ctx_destroy(pb_ctx* c) {
   DeviceGuard g(c->device);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_pair_tables) cudaFree(c->d_pair_tables);
+  for (auto& kv : c->scratch) if (kv.second.first) cudaFree(kv.second.first);
   if (c->d_verify_tables) cudaFree(c->d_verify_tables);
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
@@ -960,12 +982,11 @@ int pb_plonk_verify_completed_dev(const pb_ctx* ctx, const uint8_t* proofs, cons
   cudaStream_t st = S(stream);
   if (!(ctx->key_canonical && !ctx->force_exact)) return launch_verify(ctx, proofs, chal, u, status, nullptr, nullptr, verdict, nullptr, n, st);
   uint32_t* scratch = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (n + 4) * sizeof(uint32_t), st));
+  int rc = scratch_for(ctx, st, n, &scratch);
+  if (rc) return rc;
   CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
   compact_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, st>>>(status, n, scratch + 4, scratch, verdict);
-  int rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
-  cudaFreeAsync(scratch, st);
-  return rc;
+  return launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
 }
 int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                               uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
@@ -983,12 +1004,12 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, cons
   // that list: no lane idles on the ~40% of random inputs on which the reference exits.
   cudaStream_t st = S(stream);
   uint32_t* scratch = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (n + 4) * sizeof(uint32_t), st));
+  int rc = scratch_for(ctx, st, n, &scratch);
+  if (rc) return rc;
   CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
-  int rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict);
+  rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict);
   if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
   if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
-  cudaFreeAsync(scratch, st);
   return rc;
 }
 
