@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--variant", default="U17", choices=["U17", "NZ"])
     ap.add_argument("--ref-items", type=int, default=1 << 18, help="proofs per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "poly", "g1_mul", "pairing"],
+                    help="prove_verify = BASELINE config 5 (the headline, what the driver runs); poly / g1_mul / pairing = "
+                         "configs 2 / 3 / 4 (single GPU, device-resident; extra lines for profiles/)")
     return ap.parse_args()
 
 
@@ -240,6 +243,11 @@ def run_b200(args):
     from plonk_c_b200 import host, shard, workload as W
 
     rank, local_rank, world = rank_info()
+    # stdout must carry exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) is sent to
+    # stderr by pointing fd 1 at fd 2 for the whole run; the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. This path has no CPU fallback (use --impl reference for the CPU arm).")
     torch.cuda.set_device(local_rank)
@@ -419,13 +427,141 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline(args, W, srs)
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ configs 2-4 (secondary metrics of BASELINE.json)
+def run_config(args):
+    """BASELINE configs 2 (poly mul/div/eval + interpolation, 2^22 items), 3 (2^24 G1 scalar-muls against the test SRS) and
+    4 (2^22 pairings) on one GPU, device-resident, CUDA-event timed.  One JSON line; not the driver's headline."""
+    import ctypes as C
+    import torch
+    from plonk_c_b200 import host, workload as W
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    lib, (oracle, okind) = host.lib(), load_cpu_oracle()
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    cores = os.cpu_count() or 1
+
+    def T(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / args.steps
+
+    peaks, peak_src = measured_peaks()
+    if args.workload == "poly":
+        n = 1 << 22
+        a, b, x, vals = W.make_poly_items(SEED, 0, n)
+        six, five = np.full(n, 6, np.uint8), np.full(n, 5, np.uint8)
+        zh = np.tile(np.array([16, 0, 0, 0, 1], np.uint8), (n, 1))
+        A, B, X, V, L6, L5, ZH = T(a), T(b), T(x), T(vals), T(six), T(five), T(zh)
+        ctx = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
+        prod, plen = host.poly_mul(A, L6, B, L6)
+        parts = {
+            "poly_mul 6x6": (lambda: host.poly_mul(A, L6, B, L6), 12 + 2 + 11 + 1),
+            "poly_divide 11/Z_H": (lambda: host.poly_divide(prod, plen, ZH, L5, sq=7, sr=4), 11 + 1 + 5 + 1 + 7 + 4 + 3),
+            "poly_eval len 6": (lambda: host.poly_eval(A, L6, X), 6 + 1 + 1 + 1),
+            "interpolate_at_h": (lambda: ctx.interpolate_at_h(V), 4 + 4 + 1),
+        }
+        ms = {k: timed(f) for k, (f, _) in parts.items()}
+        total_ms = sum(ms.values())
+        dom = max(ms, key=ms.get)
+        t0 = time.perf_counter()
+        m = 1 << 18
+        oracle.poly_binop(2, a[:m], six[:m], b[:m], six[:m], 11)
+        oracle.poly_divide(prod[:m].cpu().numpy(), plen[:m].cpu().numpy(), zh[:m], five[:m], 7, 4)
+        oracle.poly_eval(a[:m], six[:m], x[:m])
+        oracle.interpolate_at_h(vals[:m])
+        cpu_rate = m / (time.perf_counter() - t0)
+        line = {"metric": "poly_items_per_s", "unit": "items/s", "value": n / (total_ms * 1e-3), "config": {
+            "workload": "BASELINE config 2: poly_mul 6x6 + poly_divide(A*B, Z_H) + poly_eval + interpolate_at_h, 2^22 items, 4 launches per step"},
+            "kernel_ms": ms,
+            "roofline": {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peak_src,
+                         "achieved": parts[dom][1] * n / (ms[dom] * 1e-3) / 1e9, "traffic": None,
+                         "per_kernel_gbs": {k: parts[k][1] * n / (ms[k] * 1e-3) / 1e9 for k in ms}},
+            "cpu_baseline": {"value": cpu_rate, "unit": "items/s", "cores": 1, "kind": okind, "sample": f"first {m} items, single thread"}}
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / peaks["hbm_gbs"]
+        gpu_launches = 4 * args.steps
+    elif args.workload == "g1_mul":
+        n = 1 << 24
+        g1s, _ = W.generator_srs(9)
+        ai, bi, sc = W.make_group_items(SEED, 0, n)
+        P, S = T(g1s[ai % 10]), T(sc)
+        out = torch.empty((n, 3), dtype=torch.uint8, device=dev)
+        ms = timed(lambda: host._check(lib.pb_g1_mul_u8_dev(C.c_void_p(P.data_ptr()), C.c_void_p(S.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(n), sp)))
+        m = 1 << 21
+        t0 = time.perf_counter()
+        oracle.g1_mul(g1s[ai[:m] % 10], sc[:m].astype(np.uint64), cores)
+        cpu_rate = m / (time.perf_counter() - t0)
+        int_ops = 74.5 * INT_OPS_PER_MUL + 15.6 * INT_OPS_PER_ADD
+        line = {"metric": "g1_scalar_muls_per_s", "unit": "smul/s", "value": n / (ms * 1e-3), "config": {
+            "workload": "BASELINE config 3: 2^24 g1_mul(P, s), P drawn from the generator SRS (n=9), s uniform on [0,17)"},
+            "kernel_ms": {"g1_mul_kernel": ms},
+            "roofline": {"bound": "int32", "kernel": "g1_mul_kernel", "unit": "TIOP/s", "achieved": int_ops * n / (ms * 1e-3) / 1e12,
+                         "algorithmic_int_ops_per_item": int_ops, "traffic": None,
+                         "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
+            "cpu_baseline": {"value": cpu_rate, "unit": "smul/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
+        gpu_launches = args.steps
+    else:
+        n = 1 << 22
+        ai, bi, sc = W.make_group_items(SEED, 0, n)
+        Pn = W.g1_subgroup_table()[ai]
+        Hn = np.tile(np.array([[36, 31]], np.uint8), (n, 1))
+        P = T(Pn)
+        Q = host.g2_mul(T(Hn), T(bi.astype(np.int64)))
+        out = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+        ms = timed(lambda: host._check(lib.pb_pairing_dev(C.c_void_p(P.data_ptr()), C.c_void_p(Q.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(n), sp)))
+        m = 1 << 20
+        Qh = Q[:m].cpu().numpy()
+        t0 = time.perf_counter()
+        oracle.pairing(Pn[:m], Qh, cores)
+        cpu_rate = m / (time.perf_counter() - t0)
+        int_ops = 592 * INT_OPS_PER_MUL + 143 * INT_OPS_PER_ADD
+        line = {"metric": "pairings_per_s", "unit": "pairings/s", "value": n / (ms * 1e-3), "config": {
+            "workload": "BASELINE config 4: 2^22 pairings e(aG, bH), a, b uniform on [1,17)"},
+            "kernel_ms": {"pairing_kernel": ms},
+            "roofline": {"bound": "int32", "kernel": "pairing_kernel", "unit": "TIOP/s", "achieved": int_ops * n / (ms * 1e-3) / 1e12,
+                         "algorithmic_int_ops_per_item": int_ops, "traffic": None, "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
+            "cpu_baseline": {"value": cpu_rate, "unit": "pairings/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
+        gpu_launches = args.steps
+    if line["roofline"]["bound"] == "int32":
+        sink = torch.zeros(4, dtype=torch.int32, device=dev)
+        ops = C.c_uint64(0)
+        best = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            host._check(lib.pb_peak_probe_dev(0, 1024, C.byref(ops), C.c_void_p(sink.data_ptr()), sp))
+            b.record(stream)
+            torch.cuda.synchronize()
+            best = max(best, ops.value / (a.elapsed_time(b) * 1e-3))
+        line["roofline"]["peak"] = best / 1e12
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    line.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
+                 "gpu_launches": gpu_launches, "vs_baseline": None, "scaling": "weak"})
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    if args.workload != "prove_verify":
+        return run_config(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -66,12 +66,12 @@ struct Dev {
 #define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
-constexpr size_t PIPE_CHUNK_MAX = 1u << 18;   // device scratch per slot is sized for this many items
+constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // device scratch per slot is sized for this many items
 constexpr int PIPE_SLOTS = 4;
 // items per pipeline chunk of the host-pointer prove/verify (PB_PIPE_CHUNK overrides, for tuning; multiple of 128)
 size_t pipe_chunk() {
   static size_t v = [] {
-    size_t c = 1u << 17;
+    size_t c = 1u << 18;
     if (const char* e = getenv("PB_PIPE_CHUNK")) { size_t x = strtoull(e, nullptr, 10); if (x >= 128 && x <= PIPE_CHUNK_MAX) c = x & ~(size_t)127; }
     return c;
   }();
@@ -80,7 +80,8 @@ size_t pipe_chunk() {
 
 struct PipeSlot {
   cudaStream_t stream = nullptr;
-  uint8_t *wit = nullptr, *rnd = nullptr, *chal = nullptr, *u = nullptr, *proofs = nullptr, *status = nullptr, *verdict = nullptr;
+  cudaEvent_t done = nullptr;
+  uint8_t *wit = nullptr, *rnd = nullptr, *chal = nullptr, *proofs = nullptr;
 };
 
 }  // namespace
@@ -110,6 +111,9 @@ struct pb_ctx {
   std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
   std::mutex pipe_mu;
   bool pipe_ready = false;
+  cudaEvent_t ev_u = nullptr;
+  uint8_t *d_u = nullptr, *d_status = nullptr, *d_verdict = nullptr;   // whole-batch one-byte arrays of the host-pointer pipeline
+  size_t small_cap = 0;
   PipeSlot slots[PIPE_SLOTS];
 };
 
@@ -147,11 +151,10 @@ int pipe_init(pb_ctx* c) {
     CU(cudaMalloc(&s.wit, PIPE_CHUNK_MAX * 12));
     CU(cudaMalloc(&s.rnd, PIPE_CHUNK_MAX * 9));
     CU(cudaMalloc(&s.chal, PIPE_CHUNK_MAX * 5));
-    CU(cudaMalloc(&s.u, PIPE_CHUNK_MAX));
     CU(cudaMalloc(&s.proofs, PIPE_CHUNK_MAX * 34));
-    CU(cudaMalloc(&s.status, PIPE_CHUNK_MAX));
-    CU(cudaMalloc(&s.verdict, PIPE_CHUNK_MAX));
+    CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
+  CU(cudaEventCreateWithFlags(&c->ev_u, cudaEventDisableTiming));
   c->pipe_ready = true;
   return PB_OK;
 }
@@ -900,9 +903,12 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
     if (s.stream) cudaStreamDestroy(s.stream);
-    uint8_t* bufs[7] = {s.wit, s.rnd, s.chal, s.u, s.proofs, s.status, s.verdict};
+    if (s.done) cudaEventDestroy(s.done);
+    uint8_t* bufs[4] = {s.wit, s.rnd, s.chal, s.proofs};
     for (auto b : bufs) if (b) cudaFree(b);
   }
+  if (c->ev_u) cudaEventDestroy(c->ev_u);
+  for (uint8_t* p : {c->d_u, c->d_status, c->d_verdict}) if (p) cudaFree(p);
   delete c;
   return PB_OK;
 }
@@ -1013,52 +1019,70 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, cons
   return rc;
 }
 
-// host-pointer versions: chunks of pipe_chunk() items rotate over PIPE_SLOTS streams, so the copy engines and
-// the SMs work on different chunks at the same time
+// host-pointer versions.  Chunks of pipe_chunk() items rotate over PIPE_SLOTS streams so that the two copy engines and
+// the SMs work on different chunks at the same time.  PCIe throughput on the B200 hosts drops sharply for pieces below
+// ~1 MB (profiles/r1/pcie_probe.txt), so the one-byte-per-item arrays (u in, status and verdict out) are NOT chunked:
+// u goes up once before the first chunk, status and verdict come back once after the last one.
 static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
-                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, uint8_t* gt_unused, size_t n, int mode /*0 prove, 1 prove+verify*/) {
-  (void)gt_unused;
+                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, int mode /*0 prove, 1 prove+verify*/) {
   pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
   DeviceGuard g(ctx->device);
   std::lock_guard<std::mutex> lock(ctx->pipe_mu);
   int rc = pipe_init(ctx);
   if (rc) return rc;
+  if (ctx->small_cap < n) {
+    for (uint8_t** p : {&ctx->d_u, &ctx->d_status, &ctx->d_verdict}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
+    size_t cap = (n + 255) & ~(size_t)255;
+    CU(cudaMalloc(&ctx->d_u, cap)); CU(cudaMalloc(&ctx->d_status, cap)); CU(cudaMalloc(&ctx->d_verdict, cap));
+    ctx->small_cap = cap;
+  }
+  cudaStream_t s0 = ctx->slots[0].stream;
+  if (mode == 1) {
+    CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, s0));
+    CU(cudaEventRecord(ctx->ev_u, s0));
+  }
+  const size_t chunk = pipe_chunk();
   size_t done = 0;
-  int slot = 0;
+  int slot = 0, used = 0;
   while (done < n) {
-    const size_t chunk = pipe_chunk();
     size_t m = n - done < chunk ? n - done : chunk;
     PipeSlot& s = ctx->slots[slot];
     CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, s.stream));
     if (mode == 1) {
-      CU(cudaMemcpyAsync(s.u, u + done, m, cudaMemcpyHostToDevice, s.stream));
-      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, s.u, s.proofs, s.status, s.verdict, m, s.stream);
+      if (slot != 0 && used < PIPE_SLOTS) CU(cudaStreamWaitEvent(s.stream, ctx->ev_u, 0));
+      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, ctx->d_u + done, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.stream);
     } else {
-      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, s.status, m, s.stream);
+      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, ctx->d_status + done, m, s.stream);
     }
     if (rc) return rc;
     CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaMemcpyAsync(status + done, s.status, m, cudaMemcpyDeviceToHost, s.stream));
-    if (mode == 1) CU(cudaMemcpyAsync(verdict + done, s.verdict, m, cudaMemcpyDeviceToHost, s.stream));
     done += m;
     slot = (slot + 1) % PIPE_SLOTS;
+    if (used < PIPE_SLOTS) used++;
   }
-  for (auto& s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  // every slot's work must be finished before the two small arrays come back on slot 0's stream
+  for (int k = 1; k < used; k++) {
+    CU(cudaEventRecord(ctx->slots[k].done, ctx->slots[k].stream));
+    CU(cudaStreamWaitEvent(s0, ctx->slots[k].done, 0));
+  }
+  CU(cudaMemcpyAsync(status, ctx->d_status, n, cudaMemcpyDeviceToHost, s0));
+  if (mode == 1) CU(cudaMemcpyAsync(verdict, ctx->d_verdict, n, cudaMemcpyDeviceToHost, s0));
+  for (int k = 0; k < used; k++) CU(cudaStreamSynchronize(ctx->slots[k].stream));
   return PB_OK;
 }
 int pb_plonk_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
-  return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, nullptr, n, 0);
+  return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, n, 0);
 }
 int pb_plonk_prove_verify(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                           uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && u && proofs && status && verdict);
   ARG(ctx->vk_valid);
-  return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, nullptr, n, 1);
+  return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, n, 1);
 }
 int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
