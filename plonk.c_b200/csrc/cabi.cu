@@ -14,6 +14,7 @@
 
 #include "../../include/plonk_b200.h"
 #include "kernels.cuh"
+#include "poly_fast.cuh"
 
 using namespace pb;
 
@@ -223,6 +224,18 @@ int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, 
   ARG(sa >= 1 && sb >= 1 && sa <= PB_POLY_MAX && sb <= PB_POLY_MAX);
   ARG(so >= (op == 2 ? sa + sb - 1 : (sa > sb ? sa : sb)) && so <= 2 * PB_POLY_MAX);
   if (n == 0) return PB_OK;
+  // register-resident fast path for the shapes of BASELINE config 2 and of the prover (natural output stride, aligned)
+  const bool al = aligned16(a) && aligned16(alen) && aligned16(b) && aligned16(blen) && aligned16(out) && aligned16(olen);
+  if (op == PB_POLY_MUL && al && so == sa + sb - 1) {
+#define PB_MUL_FAST(A_, B_)                                                                                         \
+    if (sa == A_ && sb == B_) {                                                                                     \
+      poly_mul_fast_kernel<A_, B_><<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(a, alen, b, blen, out, olen, n); \
+      LAUNCH_CHECK("poly_mul_fast_kernel");                                                                         \
+      return PB_OK;                                                                                                 \
+    }
+    PB_MUL_FAST(6, 6) PB_MUL_FAST(11, 6) PB_MUL_FAST(16, 7) PB_MUL_FAST(11, 4) PB_MUL_FAST(6, 4) PB_MUL_FAST(7, 4)
+#undef PB_MUL_FAST
+  }
   poly_binop_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(op, a, alen, (int)sa, b, blen, (int)sb, out, olen, (int)so, n);
   LAUNCH_CHECK("poly_binop_kernel");
   return PB_OK;
@@ -250,6 +263,18 @@ int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const
   ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
   ARG(sn >= 1 && sd >= 1 && sn <= PB_POLY_MAX && sd <= PB_POLY_MAX && sq >= 1 && sr >= 1);
   if (n == 0) return PB_OK;
+  const bool al = aligned16(num) && aligned16(nlen) && aligned16(den) && aligned16(dlen) && aligned16(quot) && aligned16(qlen) &&
+                  aligned16(rem) && aligned16(rlen) && aligned16(status);
+  if (al && sn >= sd && sq == sn - sd + 1 && sr == sd - 1) {
+#define PB_DIV_FAST(N_, D_)                                                                                                       \
+    if (sn == N_ && sd == D_) {                                                                                                   \
+      poly_divide_fast_kernel<N_, D_><<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(num, nlen, den, dlen, quot, qlen, rem, rlen, status, n); \
+      LAUNCH_CHECK("poly_divide_fast_kernel");                                                                                    \
+      return PB_OK;                                                                                                               \
+    }
+    PB_DIV_FAST(11, 5) PB_DIV_FAST(22, 5) PB_DIV_FAST(10, 2) PB_DIV_FAST(7, 2)
+#undef PB_DIV_FAST
+  }
   poly_divide_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(num, nlen, (int)sn, den, dlen, (int)sd, quot, qlen, (int)sq,
                                                                               rem, rlen, (int)sr, status, n);
   LAUNCH_CHECK("poly_divide_kernel");
@@ -275,6 +300,16 @@ int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uin
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && plen && x && out && sp >= 1);
   if (n == 0) return PB_OK;
+  if (aligned16(p) && aligned16(plen) && aligned16(x) && aligned16(out)) {
+#define PB_EVAL_FAST(P_)                                                                                   \
+    if (sp == P_) {                                                                                        \
+      poly_eval_fast_kernel<P_><<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(p, plen, x, out, n);  \
+      LAUNCH_CHECK("poly_eval_fast_kernel");                                                               \
+      return PB_OK;                                                                                        \
+    }
+    PB_EVAL_FAST(4) PB_EVAL_FAST(6) PB_EVAL_FAST(7) PB_EVAL_FAST(11) PB_EVAL_FAST(18) PB_EVAL_FAST(22)
+#undef PB_EVAL_FAST
+  }
   poly_eval_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(p, plen, (int)sp, x, out, n);
   LAUNCH_CHECK("poly_eval_kernel");
   return PB_OK;
@@ -807,6 +842,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   if (e != cudaSuccess) return bail(cuda_fail(e, "srs_table_kernel"));
   for (uint32_t i = 0; i < 101; i++) pt.ft.inv101[i] = (uint8_t)pow101(i, 99);
   for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
+  for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) pt.pow17[zz][k] = (uint8_t)pow17(zz, k);
   if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
   cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice);
   {
@@ -824,6 +860,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
       ProverPairTables ppt;
       memset(&ppt, 0, sizeof ppt);
       ppt.ft = pt.ft;
+      memcpy(ppt.pow17, pt.pow17, sizeof ppt.pow17);
       uint32_t *d_single = nullptr, *d_pairs = nullptr;
       if (cudaMalloc(&d_single, sizeof pt.T) != cudaSuccess || cudaMalloc(&d_pairs, sizeof ppt.T2) != cudaSuccess)
         return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));

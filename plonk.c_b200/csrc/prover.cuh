@@ -37,6 +37,7 @@ struct CircuitConst {
 // Tables that are indexed per lane (so they live in shared memory, not in the constant bank).
 struct ProverTables {
   FieldTables ft;
+  uint8_t pow17[17][20];   // pow17[z][k] = z^k (hf_pow, 0^0 = 1): the powers of the evaluation point are look-ups, not a 17-step chain
   // fixed-base table: T[i][c] = g1_mul(srs.g1s[i], c) for c in [0,17), packed x | y<<8 | inf<<16,
   // computed with the reference's own double-and-add on the device at context creation.
   // Rows >= srs_len are the identity {0,0,1}.
@@ -52,6 +53,7 @@ struct ProverTables {
 constexpr int PROVER_PAIR_ROWS = (PROVER_SRS_ROWS + 1) / 2;
 struct ProverPairTables {
   FieldTables ft;
+  uint8_t pow17[17][20];
   uint32_t T2[PROVER_PAIR_ROWS][289];
 };
 
@@ -202,8 +204,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   {  // t1 = a b q_M + a q_L + b q_R + c q_O + PI + q_C      (PI = 0, plonk.h:398)
     uint32_t ab[11];
     zero(ab);
-    mul_acc<6, 6>(ab, A, B);
-    reduce(ab);
+    mul_acc<6, 6>(ab, A, B);            // raw < 6 * 2^8; times q_M below < 2^17: no reduction needed in between
     mul_acc<11, 4>(tn, ab, cc.QP[3]);
     mul_acc<6, 4>(tn, A, cc.QP[0]);
     mul_acc<6, 4>(tn, B, cc.QP[1]);
@@ -288,9 +289,8 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
 
   // ---- round 4 (plonk.h:527-574): openings at z and the (non-standard) linearisation r(x)
   uint32_t zp[18];
-  zp[0] = 1u;
 #pragma unroll
-  for (int i = 1; i < 18; i++) zp[i] = red17(zp[i - 1] * z);
+  for (int i = 0; i < 18; i++) zp[i] = tb.pow17[z][i];
   const uint32_t a_z = dot(A, zp), b_z = dot(B, zp), c_z = dot(C, zp);
   const uint32_t s1_z = dot(cc.SP[0], zp), s2_z = dot(cc.SP[1], zp);
   const uint32_t t_z = dot(T, zp), zw_z = dot(Zw, zp), l1_z = dot(cc.l1, zp);

@@ -70,6 +70,7 @@ void hc_prove(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wi
   memcpy(&cc, cc_words, sizeof cc);
   ProverTables tb;
   tb.ft = make_ft();
+  for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
   memcpy(tb.T, table, sizeof tb.T);
   for (size_t i = 0; i < n; i++) {
     uint32_t wa[4], wb[4], wc[4], r[9];
@@ -94,6 +95,7 @@ void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8
   memcpy(&cc, cc_words, sizeof cc);
   static ProverPairTables tb;
   tb.ft = make_ft();
+  for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
   for (uint32_t k = 0; k < PROVER_PAIR_ROWS * 289u; k++) {
     const uint32_t j = k / 289u, c0 = (k % 289u) / 17u, c1 = k % 17u;
     const G1 p = unpack_g1(table[(2 * j) * 17 + c0]);

@@ -101,6 +101,28 @@ def check_polys(impl, oracle, n=20000):
     eq("plonk_new", impl.plonk_setup_dump(), oracle.plonk_setup_dump())
 
 
+def check_polys_fast_shapes(impl, oracle, n=30011):
+    """The register-resident fast paths (poly_fast.cuh) are selected by (stride, natural output stride, alignment): the
+    shapes of BASELINE config 2 and of the prover.  Same inputs as the generic test: random lengths (masking), zero
+    polynomials, zero divisors, divisors shorter than the stride (quotient longer than its columns -> truncated rows)."""
+    for la, lb in ((6, 6), (11, 6), (16, 7), (11, 4), (6, 4), (7, 4)):
+        a, al, b, bl = util.poly_cases(n, la, lb)
+        eq(f"fast poly_mul {la}x{lb}", impl.poly_binop(2, a, al, b, bl, la + lb - 1), oracle.poly_binop(2, a, al, b, bl, la + lb - 1))
+        full = np.full(n, la, np.uint8)
+        eq(f"fast poly_mul {la}x{lb} full length", impl.poly_binop(2, a, full, b, bl, la + lb - 1), oracle.poly_binop(2, a, full, b, bl, la + lb - 1))
+    for sn, sd in ((11, 5), (22, 5), (10, 2), (7, 2)):
+        a, al, b, bl = util.poly_cases(n, sn, sd)
+        eq(f"fast poly_divide {sn}/{sd}", impl.poly_divide(a, al, b, bl, sn - sd + 1, sd - 1), oracle.poly_divide(a, al, b, bl, sn - sd + 1, sd - 1))
+        zh = np.zeros((n, sd), np.uint8)
+        zh[:, 0], zh[:, -1] = 16, 1                                   # x^(sd-1) - 1 (Z_H for sd = 5), full-length numerators
+        full, dl = np.full(n, sn, np.uint8), np.full(n, sd, np.uint8)
+        eq(f"fast poly_divide {sn}/monic", impl.poly_divide(a, full, zh, dl, sn - sd + 1, sd - 1), oracle.poly_divide(a, full, zh, dl, sn - sd + 1, sd - 1))
+    for sp in (4, 6, 7, 11, 18, 22):
+        a, al, _, _ = util.poly_cases(n, sp, 2)
+        x = np.ascontiguousarray(a[:, 0] ^ 5) % 17
+        eq(f"fast poly_eval {sp}", impl.poly_eval(a, al, x.astype(np.uint8)), oracle.poly_eval(a, al, x.astype(np.uint8)))
+
+
 def check_polys_golden(impl, n=2048):
     g = golden("polys")
     for la, lb in POLY_SHAPES:

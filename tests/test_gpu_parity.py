@@ -48,6 +48,10 @@ def test_polys(dev, oracle):
     ps.check_polys(dev, oracle)
 
 
+def test_polys_fast_shapes(dev, oracle):
+    ps.check_polys_fast_shapes(dev, oracle)
+
+
 def test_polys_golden(dev, hostpath):
     ps.check_polys_golden(dev)
     ps.check_polys_golden(hostpath)
