@@ -369,7 +369,7 @@ def run_b200(args):
     probe = {}
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
     ops = C.c_uint64(0)
-    for kind, name in ((0, "imad"), (1, "alu"), (2, "imad+alu"), (3, "lds_u8")):
+    for kind, name in ((0, "imad"), (1, "lop3"), (2, "imad+lop3"), (3, "lds_u8"), (4, "ffma"), (5, "hfma2"), (6, "idp4a"), (7, "imad_wide")):
         best = 0.0
         for _ in range(3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -404,6 +404,15 @@ def run_b200(args):
                 / (min(verify_ms, prove_ms) * 1e-3) / 1e12 / roof["peak"]}
     else:
         roof["achieved"], roof["frac"] = None, None
+    try:        # hardware-side view of the same kernels, from the committed ncu capture (not measurable without a profiler)
+        with open(os.path.join(ROOT, "profiles", "ncu_headline.json")) as f:
+            roof["ncu"] = json.load(f)
+    except Exception:
+        roof["ncu"] = None
+    roof["note"] = ("achieved/frac follow SURVEY 8(d): algorithmic INT32 ops of the REFERENCE's algorithm per launch / kernel time. The kernels need far "
+                    "fewer operations than the reference (fixed-base tables instead of per-term double-and-add with Fermat inversions, joint "
+                    "double-and-add), so frac > 1 is speed-up over the reference's operation count, not hardware efficiency; the hardware view is "
+                    "roofline.ncu (issue-slot and IMAD-pipe utilisation).")
     bytes_item = {"prove_kernel": 26 + 35, "verify_kernel": 34 + 5 + 1 + 1 + 1}
     roof["hbm"] = {"peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
                    "achieved": {k: bytes_item[k] * n / (ms * 1e-3) / 1e9 for k, ms in (("prove_kernel", prove_ms), ("verify_kernel", verify_ms))},
@@ -452,17 +461,23 @@ def run_config(args):
     def T(x):
         return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
 
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
     def timed(fn):
+        """mean device time of fn over --steps launches; L2 is flushed (256 MiB written) before every timed launch"""
         for _ in range(args.warmup):
             fn()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
+        tot = 0.0
         for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
             fn()
-        b.record(stream)
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / args.steps
+            b.record(stream)
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / args.steps
 
     peaks, peak_src = measured_peaks()
     if args.workload == "poly":
@@ -553,6 +568,7 @@ def run_config(args):
             best = max(best, ops.value / (a.elapsed_time(b) * 1e-3))
         line["roofline"]["peak"] = best / 1e12
         line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    line["config"]["l2"] = "L2 flushed (256 MiB written) before every timed launch"
     line.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
                  "gpu_launches": gpu_launches, "vs_baseline": None, "scaling": "weak"})
     os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -226,8 +226,9 @@ int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *ve
 
 /* ---- roofline denominators measured on the device the caller is on (MEASURED_PEAKS.json
  * has no integer peak).  Each runs a dependency-free instruction stream on every SM and reports how many
- * thread-level operations it issued; the caller times it.  kind 0: 32-bit IMAD (fma pipe); kind 1: IADD3/LOP3
- * (alu pipe); kind 2: IMAD and LOP3 interleaved 1:1 (both pipes); kind 3: shared-memory byte look-ups (LDS.U8). */
+ * thread-level operations it issued; the caller times it.  kind 0: 32-bit IMAD (fma pipe); kind 1: LOP3
+ * (alu pipe); kind 2: IMAD and LOP3 interleaved 1:1 (both pipes); kind 3: shared-memory byte look-ups (LDS.U8);
+ * kind 4: FFMA; kind 5: HFMA2; kind 6: IDP4A; kind 7: IMAD.WIDE. */
 int pb_peak_probe_dev(int kind, uint32_t iters, uint64_t *ops_out_host, uint32_t *sink_dev, void *stream);
 #ifdef __cplusplus
 }

@@ -524,8 +524,11 @@ struct __align__(16) ProveSmem {
 // Tables = ProverTables (any SRS, the reference's order of additions) or ProverPairTables (canonical on-curve SRS).
 // done_list / done_count (optional): indices of the completed proofs (status 0) are appended, one atomic per warp,
 // so that the verifier runs on a dense list; verdict (optional) gets 0xFF for every item that did not complete.
+#ifndef PB_PROVE_MINBLOCKS
+#define PB_PROVE_MINBLOCKS 1
+#endif
 template <typename Tables>
-__global__ void __launch_bounds__(BLOCK) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
+__global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
                                                       const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
                                                       uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
@@ -779,7 +782,10 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) tally_kernel(const uint8_t* __res
 
 // ------------------------------------------------------------------ roofline probes
 // Dependency-free instruction streams (16 independent chains per thread) to measure the issue-rate ceilings the
-// integer kernels are charged against.  PROBE_OPS_PER_ITER thread-level operations per loop iteration.
+// integer kernels are charged against.  PROBE_OPS_PER_ITER counted thread-level instructions per loop iteration
+// (one per chain per repetition; the SASS of every kind is checked with cuobjdump to be exactly that instruction).
+// kind 0 IMAD (32-bit)   1 LOP3 (alu pipe)   2 IMAD and LOP3 alternating   3 LDS.U8 (+ address math, counted as 1)
+// kind 4 FFMA            5 HFMA2             6 IDP4A (dp4a)                 7 IMAD.WIDE (32x32+64)
 constexpr int PROBE_OPS_PER_ITER = 64;
 __global__ void __launch_bounds__(256) peak_probe_kernel(int kind, uint32_t iters, uint32_t* __restrict__ sink) {
   __shared__ uint8_t lut[1024];
@@ -789,36 +795,79 @@ __global__ void __launch_bounds__(256) peak_probe_kernel(int kind, uint32_t iter
 #pragma unroll
   for (int k = 0; k < 16; k++) r[k] = threadIdx.x * 16u + k + blockIdx.x;
   const uint32_t m = 2654435761u + blockIdx.x, c = 40503u + threadIdx.x;
+  uint32_t x = 0;
   if (kind == 0) {
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
       for (int rep = 0; rep < 4; rep++)
 #pragma unroll
-        for (int k = 0; k < 16; k++) r[k] = r[k] * m + c;                       // IMAD
+        for (int k = 0; k < 16; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(m), "r"(c));
     }
   } else if (kind == 1) {
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
       for (int rep = 0; rep < 4; rep++)
 #pragma unroll
-        for (int k = 0; k < 16; k++) r[k] = (r[k] ^ m) + (r[(k + 1) & 15] & c);  // LOP3 + IADD3 -> counted as one op each, 2 per statement
+        for (int k = 0; k < 16; k++) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[k]) : "r"(m), "r"(c));
     }
   } else if (kind == 2) {
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
       for (int rep = 0; rep < 2; rep++)
 #pragma unroll
-        for (int k = 0; k < 16; k++) { r[k] = r[k] * m + c; r[k] ^= (r[k] >> 7); }   // IMAD + (SHF, LOP3)
+        for (int k = 0; k < 16; k++) {
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(m), "r"(c));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(k + 8) & 15]) : "r"(m), "r"(c));
+        }
     }
-  } else {
+  } else if (kind == 3) {
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
       for (int rep = 0; rep < 4; rep++)
 #pragma unroll
-        for (int k = 0; k < 16; k++) r[k] = lut[(r[k] + k * 61u) & 1023u] + (r[k] >> 3);   // LDS.U8 + address math
+        for (int k = 0; k < 16; k++) r[k] = lut[(r[k] + k * 61u) & 1023u] + (r[k] >> 3);
     }
+  } else if (kind == 4) {
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) f[k] = (float)r[k];
+    const float fm = 1.0000001f, fc = 0.5f;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k]) : "f"(fm), "f"(fc));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) x ^= __float_as_uint(f[k]);
+  } else if (kind == 5) {
+    const uint32_t hm = 0x3C003C00u, hc = 0x38003800u;     // half2(1, 1), half2(0.5, 0.5)
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(hm), "r"(hc));
+    }
+  } else if (kind == 6) {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(m), "r"(c));
+    }
+  } else {
+    unsigned long long w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = r[k];
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(m), "r"(c));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) x ^= (uint32_t)(w[k] ^ (w[k] >> 32));
   }
-  uint32_t x = 0;
 #pragma unroll
   for (int k = 0; k < 16; k++) x ^= r[k];
   if (x == 0xDEADBEEFu) sink[0] = x;

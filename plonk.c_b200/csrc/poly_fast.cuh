@@ -2,8 +2,13 @@
 //
 // The generic kernels in kernels.cuh keep polynomials in per-thread local arrays with dynamic lengths; they are
 // correct for every shape but LSU-bound.  For the fixed strides that matter, the kernels below hold every coefficient
-// in a register (all loops unrolled over the STRIDE, lengths applied as masks), and move each block's contiguous
-// slice of every byte array through shared memory with 128-bit accesses, so that HBM sees only full-line traffic.
+// in a register (all loops unrolled over the STRIDE, lengths applied as masks).  These kernels move ~26-45 bytes per
+// item, so they are only HBM-bound if the whole item costs ~150-250 issue slots; hence
+//   - INPUT records are read straight from global memory with aligned 32-bit loads + funnel shifts (a warp's records
+//     are one contiguous span, so every sector is fetched once; no shared memory, no barrier on the way in);
+//   - OUTPUT records (odd strides: 11, 7, 4 bytes) are assembled in shared memory and leave the block as 128-bit
+//     stores of its contiguous slice, so HBM sees full lines instead of one partial sector per byte;
+//   - the one-byte-per-item arrays (lengths, x, status, results) are accessed directly (already coalesced).
 // Semantics are the generic kernels' (= the reference's poly_new trimming + operation + trimming), bit for bit.
 #pragma once
 #include "kernels.cuh"
@@ -12,10 +17,39 @@ namespace pb {
 
 constexpr int PF_BLOCK = 256;
 
-template <int N>
-PB_D void load_masked(uint32_t (&r)[N], const uint8_t* row, uint32_t len) {
+// The ITEM bytes of record t of a byte array (16-byte aligned base, n records), as little-endian words w[0..].
+// Words past the end of the array are never dereferenced (index clamped), they only feed bytes that are masked off.
+template <int ITEM>
+PB_D void load_record(uint32_t (&w)[(ITEM + 3) / 4], const uint8_t* __restrict__ base, size_t t, size_t n) {
+  constexpr int NW = (ITEM + 3) / 4;
+  const size_t off = t * ITEM;
+  const size_t last = (n * ITEM - 1) >> 2;
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(base);
+  const size_t i0 = off >> 2;
+  const uint32_t sh = (uint32_t)(off & 3u) * 8u;
+  uint32_t raw[NW + 1];
 #pragma unroll
-  for (int i = 0; i < N; i++) r[i] = (uint32_t)i < len ? row[i] : 0u;
+  for (int k = 0; k <= NW; k++) { const size_t i = i0 + k; raw[k] = g[i < last ? i : last]; }
+#pragma unroll
+  for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+}
+template <int N>
+PB_D void unpack_masked(uint32_t (&r)[N], const uint32_t (&w)[(N + 3) / 4], uint32_t len) {
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = (uint32_t)i < len ? ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) : 0u;
+}
+// the block's slice of an output array with ITEM bytes per record: shared memory -> global, 128-bit stores
+template <int ITEM>
+PB_D void store_slice(uint8_t* __restrict__ g, const uint8_t* smem, size_t first, size_t n) {
+  constexpr int NV = PF_BLOCK * ITEM / 16;
+  uint8_t* dst = g + first * ITEM;
+  if (first + PF_BLOCK <= n) {
+#pragma unroll
+    for (int k = threadIdx.x; k < NV; k += PF_BLOCK) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(smem)[k];
+  } else {
+    const int cnt = (int)(n - first) * ITEM;
+    for (int k = threadIdx.x; k < cnt; k += PF_BLOCK) dst[k] = smem[k];
+  }
 }
 
 // poly_mul (poly.h:106-122) for fixed strides SA x SB -> SA+SB-1
@@ -24,33 +58,25 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_mul_fast_kernel(const uint8_t* 
                                                                  const uint8_t* __restrict__ b, const uint8_t* __restrict__ blen,
                                                                  uint8_t* __restrict__ out, uint8_t* __restrict__ olen, size_t n) {
   constexpr int SO = SA + SB - 1;
-  __shared__ __align__(16) uint8_t sa[PF_BLOCK * SA];
-  __shared__ __align__(16) uint8_t sb[PF_BLOCK * SB];
   __shared__ __align__(16) uint8_t so[PF_BLOCK * SO];
-  __shared__ __align__(16) uint8_t sla[PF_BLOCK], slb[PF_BLOCK], slo[PF_BLOCK];
   const int tid = threadIdx.x;
-  const size_t first = (size_t)blockIdx.x * PF_BLOCK;
-  stage_in<SA, PF_BLOCK>(sa, a, first, n);
-  stage_in<SB, PF_BLOCK>(sb, b, first, n);
-  stage_in<1, PF_BLOCK>(sla, alen, first, n);
-  stage_in<1, PF_BLOCK>(slb, blen, first, n);
-  __syncthreads();
-  if (first + tid < n) {
-    uint32_t ra[SA], rb[SB], ro[SO];
-    load_masked(ra, sa + tid * SA, sla[tid]);
-    load_masked(rb, sb + tid * SB, slb[tid]);
+  const size_t first = (size_t)blockIdx.x * PF_BLOCK, t = first + tid;
+  if (t < n) {
+    uint32_t wa[(SA + 3) / 4], wb[(SB + 3) / 4], ra[SA], rb[SB], ro[SO];
+    load_record<SA>(wa, a, t, n);
+    load_record<SB>(wb, b, t, n);
+    unpack_masked(ra, wa, alen[t]);
+    unpack_masked(rb, wb, blen[t]);
 #pragma unroll
     for (int k = 0; k < SO; k++) ro[k] = 0u;
     mul_acc<SA, SB>(ro, ra, rb);            // raw < min(SA,SB) * 2^8
 #pragma unroll
     for (int k = 0; k < SO; k++) { ro[k] = red17(ro[k]); so[tid * SO + k] = (uint8_t)ro[k]; }
-    // untrimmed length is la' + lb' - 1 with la', lb' the trimmed input lengths; trimming the product gives its
-    // canonical length (F17[x] has no zero divisors), and 1 for a zero product
-    slo[tid] = (uint8_t)canon_len(ro);
+    // F17[x] has no zero divisors: trimming the product gives its canonical length (1 for a zero product)
+    olen[t] = (uint8_t)canon_len(ro);
   }
   __syncthreads();
-  stage_out<SO, PF_BLOCK>(out, so, first, n);
-  stage_out<1, PF_BLOCK>(olen, slo, first, n);
+  store_slice<SO>(out, so, first, n);
 }
 
 // poly_divide (poly.h:124-177) for fixed strides: numerator SN, divisor SD, quotient SN-SD+1 columns, remainder SD-1
@@ -62,25 +88,21 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
                                                                     uint8_t* __restrict__ status, size_t n) {
   constexpr int SQ = SN - SD + 1, SR = SD - 1;
   __shared__ FieldTables ft;
-  __shared__ __align__(16) uint8_t sn[PF_BLOCK * SN];
-  __shared__ __align__(16) uint8_t sd[PF_BLOCK * SD];
   __shared__ __align__(16) uint8_t sq[PF_BLOCK * SQ];
   __shared__ __align__(16) uint8_t sr[PF_BLOCK * SR];
-  __shared__ __align__(16) uint8_t sln[PF_BLOCK], sld[PF_BLOCK], slq[PF_BLOCK], slr[PF_BLOCK], sst[PF_BLOCK];
   const int tid = threadIdx.x;
-  const size_t first = (size_t)blockIdx.x * PF_BLOCK;
+  const size_t first = (size_t)blockIdx.x * PF_BLOCK, t = first + tid;
   build_field_tables(ft);
-  stage_in<SN, PF_BLOCK>(sn, num, first, n);
-  stage_in<SD, PF_BLOCK>(sd, den, first, n);
-  stage_in<1, PF_BLOCK>(sln, nlen, first, n);
-  stage_in<1, PF_BLOCK>(sld, dlen, first, n);
   __syncthreads();
-  if (first + tid < n) {
-    uint32_t r[SN], d[SD];
-    load_masked(r, sn + tid * SN, sln[tid]);
-    load_masked(d, sd + tid * SD, sld[tid]);
-    const uint32_t nl = sln[tid] == 0 ? 0u : canon_len(r);      // poly_new trims the inputs first
-    const uint32_t dl = sld[tid] == 0 ? 0u : canon_len(d);
+  if (t < n) {
+    uint32_t wn[(SN + 3) / 4], wd[(SD + 3) / 4], r[SN], d[SD];
+    load_record<SN>(wn, num, t, n);
+    load_record<SD>(wd, den, t, n);
+    const uint32_t nlen0 = nlen[t], dlen0 = dlen[t];
+    unpack_masked(r, wn, nlen0);
+    unpack_masked(d, wd, dlen0);
+    const uint32_t nl = nlen0 == 0 ? 0u : canon_len(r);      // poly_new trims the inputs first
+    const uint32_t dl = dlen0 == 0 ? 0u : canon_len(d);
     bool zero_den = true;
 #pragma unroll
     for (int j = 0; j < SD; j++) zero_den &= d[j] == 0u;
@@ -108,7 +130,7 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
         if (k - j >= 0) r[k - j] += nf * dt[j];
     }
 #pragma unroll
-    for (int k = 0; k < SN; k++) r[k] = red17(r[k]);
+    for (int k = 0; k < SR; k++) r[k] = red17(r[k]);
     // quotient columns: q[i] = qt[i + dl - 1]
     uint32_t top = 0u;
     bool any = false;
@@ -130,39 +152,29 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
     for (int k = SR - 1; k >= 1; k--) rl = (rl == (uint32_t)(k + 1) && r[k] == 0u) ? (uint32_t)k : rl;
 #pragma unroll
     for (int k = 0; k < SR; k++) sr[tid * SR + k] = (!zero_den && (uint32_t)k < rl) ? (uint8_t)r[k] : 0;
-    slq[tid] = zero_den ? 0 : (uint8_t)ql;
-    slr[tid] = zero_den ? 0 : (uint8_t)rl;
-    sst[tid] = zero_den ? 1 : 0;                                 // "Division by zero polynomial", poly.h:125-128
+    qlen[t] = zero_den ? 0 : (uint8_t)ql;
+    rlen[t] = zero_den ? 0 : (uint8_t)rl;
+    status[t] = zero_den ? 1 : 0;                                // "Division by zero polynomial", poly.h:125-128
   }
   __syncthreads();
-  stage_out<SQ, PF_BLOCK>(quot, sq, first, n);
-  stage_out<SR, PF_BLOCK>(rem, sr, first, n);
-  stage_out<1, PF_BLOCK>(qlen, slq, first, n);
-  stage_out<1, PF_BLOCK>(rlen, slr, first, n);
-  stage_out<1, PF_BLOCK>(status, sst, first, n);
+  store_slice<SQ>(quot, sq, first, n);
+  store_slice<SR>(rem, sr, first, n);
 }
 
 // poly_eval (poly.h:265-272) for a fixed stride
 template <int SP>
 __global__ void __launch_bounds__(PF_BLOCK) poly_eval_fast_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen,
                                                                   const uint8_t* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
-  __shared__ __align__(16) uint8_t spv[PF_BLOCK * SP];
-  __shared__ __align__(16) uint8_t sl[PF_BLOCK], sx[PF_BLOCK], sy[PF_BLOCK];
-  const int tid = threadIdx.x;
-  const size_t first = (size_t)blockIdx.x * PF_BLOCK;
-  stage_in<SP, PF_BLOCK>(spv, p, first, n);
-  stage_in<1, PF_BLOCK>(sl, plen, first, n);
-  stage_in<1, PF_BLOCK>(sx, x, first, n);
-  __syncthreads();
-  if (first + tid < n) {
-    const uint32_t len = sl[tid], xv = sx[tid];
-    uint32_t y = 0u;
+  const size_t t = (size_t)blockIdx.x * PF_BLOCK + threadIdx.x;
+  if (t >= n) return;
+  uint32_t w[(SP + 3) / 4], c[SP];
+  load_record<SP>(w, p, t, n);
+  const uint32_t len = plen[t], xv = x[t];
+  unpack_masked(c, w, len);
+  uint32_t y = 0u;
 #pragma unroll
-    for (int k = SP - 1; k >= 0; k--) y = (uint32_t)k < len ? red17(y * xv + spv[tid * SP + k]) : y;   // Horner from the top
-    sy[tid] = (uint8_t)y;
-  }
-  __syncthreads();
-  stage_out<1, PF_BLOCK>(out, sy, first, n);
+  for (int k = SP - 1; k >= 0; k--) y = red17(y * xv + c[k]);    // Horner from the top; masked coefficients are 0 and y stays 0 above len
+  out[t] = (uint8_t)y;
 }
 
 }  // namespace pb

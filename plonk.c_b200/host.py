@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+LIB_PATH = os.environ.get("PB_LIB", os.path.join(_HERE, "libplonk_b200.so"))   # PB_LIB: build variants for tuning experiments
 
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)

@@ -7,7 +7,10 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 warps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi = heads[0]
+if len(heads) > 1:          # the export repeats the listing per view (SASS, then source-correlated): keep the first
+    rows = rows[:heads[1]]
 hdr = rows[hi]
 ix = {h: i for i, h in enumerate(hdr)}
 ops, samples = collections.Counter(), collections.Counter()

@@ -177,3 +177,40 @@ def test_prove_verify_fused_matches_separate_calls(host, W):
         v2 = pk.verify(p2, d[2], d[3])
         v2 = torch.where(s2 == 0, v2, torch.full_like(v2, 0xFF))
         assert torch.equal(proofs, p2) and torch.equal(status, s2) and torch.equal(verdict, v2)
+
+
+def test_invalid_copy_type_circuit(host, oracle, W):
+    """A COPY_OF.type outside {A,B,C}: the reference exits with "Invalid copy_of type" (plonk.h:155-157) for every
+    satisfied witness -> status 3 -- after the constraints assert (status 1 wins for unsatisfied witnesses)."""
+    circuit = W.PLONK_TEST_CIRCUIT.copy()
+    circuit[20 + 2] = 7                       # c_a[2].type
+    g1s, g2 = W.generator_srs(9)
+    wit, rnd, chal, u = W.make_batch(17, 0, 4000, "U17")
+    wit[::7, 8] = (wit[::7, 8] + 1) % 17      # every 7th witness violates gate 0
+    want = oracle.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal)
+    pk = host.Plonk(circuit, g1s, g2)
+    got = pk.prove(wit, rnd, chal)
+    ps.eq("invalid copy type", got, want)
+    assert set(np.unique(got[1])) == {1, 3}
+
+
+def test_abi_argument_errors(host, W):
+    g1s, g2 = W.generator_srs(9)
+    bad = W.PLONK_TEST_CIRCUIT.copy()
+    bad[24] = 0                                # a 1-based copy index of 0 underflows in the reference (plonk.h:144): rejected
+    with pytest.raises(host.PlonkB200Error) as e:
+        host.Plonk(bad, g1s, g2)
+    assert e.value.code == host.PB_ERR_ARG
+    bad = W.PLONK_TEST_CIRCUIT.copy()
+    bad[3] = 17                                # selector byte outside F17
+    with pytest.raises(host.PlonkB200Error):
+        host.Plonk(bad, g1s, g2)
+    g = g1s.copy()
+    g[0, 0] = 101                              # SRS coordinate outside F101
+    with pytest.raises(host.PlonkB200Error):
+        host.Plonk(W.PLONK_TEST_CIRCUIT, g, g2)
+    a = np.zeros((4, 70), np.uint8)            # longer than PB_POLY_MAX
+    with pytest.raises(host.PlonkB200Error):
+        host.poly_mul(a, np.full(4, 70, np.uint8), a, np.full(4, 70, np.uint8))
+    with pytest.raises(host.PlonkB200Error):
+        host.field_op(19, 0, np.zeros(16, np.uint8), np.zeros(16, np.uint8))
