@@ -139,6 +139,12 @@ int pb_poly_lagrange(const uint8_t *xs, const uint8_t *ys, size_t len, uint8_t *
 /* interpolate_at_h (plonk.h:162-195): h_pows_inv (4x4) times vals[i][4]; out[i][4] + trimmed length */
 int pb_interpolate_at_h_dev(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out, uint8_t *olen, size_t n, void *stream);
 int pb_interpolate_at_h(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out, uint8_t *olen, size_t n);
+/* BASELINE config 2 in one launch (SURVEY.md section 8(d) "config 2 unit"): per item a[6], b[6], x, vals[4] ->
+ * prod = poly_mul(a, b) [11]+len, (quot [7]+len, rem [4]+len) = poly_divide(prod, Z_H of the context), evals = poly_eval(a, x),
+ * interp [4]+len = interpolate_at_h(vals).  Byte-identical to the four separate entry points.  Device pointers only. */
+int pb_config2_items_dev(const pb_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *x, const uint8_t *vals,
+                         uint8_t *prod, uint8_t *prod_len, uint8_t *quot, uint8_t *quot_len, uint8_t *rem, uint8_t *rem_len,
+                         uint8_t *evals, uint8_t *interp, uint8_t *interp_len, size_t n, void *stream);
 /* matrix_mul (matrix.h:81-98): out[i] = a[i] (m x k) times b[i] (k x c), row-major, m,k,c <= 8 */
 int pb_matrix_mul_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n, void *stream);
 int pb_matrix_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n);

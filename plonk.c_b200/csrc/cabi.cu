@@ -423,6 +423,18 @@ int pb_interpolate_at_h(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, ui
   return PB_OK;
 }
 
+int pb_config2_items_dev(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, const uint8_t* x, const uint8_t* vals, uint8_t* prod,
+                         uint8_t* prod_len, uint8_t* quot, uint8_t* quot_len, uint8_t* rem, uint8_t* rem_len, uint8_t* evals, uint8_t* interp,
+                         uint8_t* interp_len, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && a && b && x && vals && prod && prod_len && quot && quot_len && rem && rem_len && evals && interp && interp_len);
+  ARG(aligned16(a) && aligned16(b) && aligned16(vals) && aligned16(prod) && aligned16(quot) && aligned16(rem) && aligned16(interp));
+  config2_kernel<<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(ctx->cc, a, b, x, vals, prod, prod_len, quot, quot_len, rem, rem_len, evals,
+                                                                     interp, interp_len, n);
+  LAUNCH_CHECK("config2_kernel");
+  return PB_OK;
+}
+
 int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && b && out && m >= 1 && k >= 1 && c >= 1 && m <= 8 && k <= 8 && c <= 8);

@@ -177,4 +177,62 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_eval_fast_kernel(const uint8_t*
   out[t] = (uint8_t)y;
 }
 
+// BASELINE config 2 as ONE launch.  SURVEY.md section 8(d) defines the unit as {A[6], B[6], x, vals[4]} (17 bytes in) ->
+// poly_mul(A, B), poly_divide(A*B, Z_H), poly_eval(A, x), interpolate_at_h(vals) (31 bytes out).  The four separate
+// entry points move 26 + 36 + 9 + 9 bytes per item in four launches of 20-120 us each; fused, every input byte is read
+// once, A*B never leaves registers, and the division by the context's Z_H = x^4 - 1 is seven additions.  Results are
+// byte-identical to the four separate calls (tests/test_gpu_parity.py::test_config2_fused).
+__global__ void __launch_bounds__(PF_BLOCK) config2_kernel(const __grid_constant__ CircuitConst cc, const uint8_t* __restrict__ a,
+                                                           const uint8_t* __restrict__ b, const uint8_t* __restrict__ x,
+                                                           const uint8_t* __restrict__ vals, uint8_t* __restrict__ prod,
+                                                           uint8_t* __restrict__ prod_len, uint8_t* __restrict__ quot,
+                                                           uint8_t* __restrict__ quot_len, uint8_t* __restrict__ rem,
+                                                           uint8_t* __restrict__ rem_len, uint8_t* __restrict__ evals,
+                                                           uint8_t* __restrict__ interp, uint8_t* __restrict__ interp_len, size_t n) {
+  __shared__ __align__(16) uint8_t sp[PF_BLOCK * 11];
+  __shared__ __align__(16) uint8_t sq[PF_BLOCK * 7];
+  const int tid = threadIdx.x;
+  const size_t first = (size_t)blockIdx.x * PF_BLOCK, t = first + tid;
+  if (t < n) {
+    uint32_t wa[2], wb[2], ra[6], rb[6], p[11];
+    load_record<6>(wa, a, t, n);
+    load_record<6>(wb, b, t, n);
+    unpack_masked(ra, wa, 6u);
+    unpack_masked(rb, wb, 6u);
+#pragma unroll
+    for (int k = 0; k < 11; k++) p[k] = 0u;
+    mul_acc<6, 6>(p, ra, rb);                                     // poly_mul, poly.h:106-122
+#pragma unroll
+    for (int k = 0; k < 11; k++) { p[k] = red17(p[k]); sp[tid * 11 + k] = (uint8_t)p[k]; }
+    prod_len[t] = (uint8_t)canon_len(p);
+    // poly_divide by Z_H = x^4 - 1 (poly.h:124-177): q[j] = p[j+4] + q[j+4], remainder p[k] + q[k]
+    uint32_t q[7];
+    q[6] = p[10]; q[5] = p[9]; q[4] = p[8]; q[3] = p[7];
+    q[2] = add17(p[6], q[6]); q[1] = add17(p[5], q[5]); q[0] = add17(p[4], q[4]);
+#pragma unroll
+    for (int k = 0; k < 7; k++) sq[tid * 7 + k] = (uint8_t)q[k];
+    quot_len[t] = (uint8_t)canon_len(q);
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) r[k] = add17(p[k], q[k]);
+    reinterpret_cast<uint32_t*>(rem)[t] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+    rem_len[t] = (uint8_t)canon_len(r);
+    // poly_eval(A, x), Horner from the top (poly.h:265-272)
+    const uint32_t xv = x[t];
+    uint32_t y = 0u;
+#pragma unroll
+    for (int k = 5; k >= 0; k--) y = red17(y * xv + ra[k]);
+    evals[t] = (uint8_t)y;
+    // interpolate_at_h(vals) = h_pows_inv * vals (plonk.h:162-195)
+    const uint32_t wv = reinterpret_cast<const uint32_t*>(vals)[t];
+    uint32_t v[4] = {wv & 0xFFu, (wv >> 8) & 0xFFu, (wv >> 16) & 0xFFu, wv >> 24}, f[4];
+    interpolate(cc, v, f);
+    reinterpret_cast<uint32_t*>(interp)[t] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
+    interp_len[t] = (uint8_t)canon_len(f);
+  }
+  __syncthreads();
+  store_slice<11>(prod, sp, first, n);
+  store_slice<7>(quot, sq, first, n);
+}
+
 }  // namespace pb

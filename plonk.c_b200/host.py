@@ -391,6 +391,21 @@ class Plonk:
         c.run(self._h, c.inp(vals), po, pl, C.c_size_t(n))
         return out, olen
 
+    def config2_items(self, a, b, x, vals):
+        """BASELINE config 2 in one launch (torch CUDA tensors): returns (prod, prod_len, quot, quot_len, rem, rem_len, evals,
+        interp, interp_len), byte-identical to poly_mul / poly_divide(., Z_H) / poly_eval / interpolate_at_h."""
+        import torch
+        n = _n(a)
+        dev = a.device
+        mk = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)
+        outs = (mk(n, 11), mk(n), mk(n, 7), mk(n), mk(n, 4), mk(n), mk(n), mk(n, 4), mk(n))
+        with torch.cuda.device(dev):
+            fn = lib().pb_config2_items_dev
+            fn.restype = C.c_int
+            _check(fn(self._h, *(C.c_void_p(t.data_ptr()) for t in (a, b, x, vals)), *(C.c_void_p(t.data_ptr()) for t in outs),
+                      C.c_size_t(n), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return outs
+
     def srs_eval_at_s(self, polys, plen):
         c = _Call("pb_srs_eval_at_s", polys)
         n = _n(polys)

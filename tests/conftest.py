@@ -56,5 +56,9 @@ def host():
     """The product's ctypes binding.  GPU tests call through it into libplonk_b200.so -- if the library is
     missing the test FAILS (no skip, no fallback)."""
     from plonk_c_b200 import host as h
+    if not os.path.exists(h.LIB_PATH) and "PB_LIB" not in os.environ:
+        import shutil
+        if shutil.which("nvcc"):          # the build container: cross-compile for sm_100a (no GPU needed)
+            _ensure_built().build_product()
     h.lib()
     return h

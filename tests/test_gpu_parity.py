@@ -214,3 +214,24 @@ def test_abi_argument_errors(host, W):
         host.poly_mul(a, np.full(4, 70, np.uint8), a, np.full(4, 70, np.uint8))
     with pytest.raises(host.PlonkB200Error):
         host.field_op(19, 0, np.zeros(16, np.uint8), np.zeros(16, np.uint8))
+
+
+def test_config2_fused(host, oracle, W):
+    """pb_config2_items_dev == the four separate reference functions composed by the oracle, incl. zero / short products."""
+    import torch
+    n = 50021
+    a, b, x, vals = W.make_poly_items(5, 0, n)
+    a[:500] = 0
+    b[500:900, 1:] = 0
+    a[900:1300, 3:] = 0
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
+    got = pk.config2_items(*[torch.from_numpy(v).cuda() for v in (a, b, x, vals)])
+    got = [g.cpu().numpy() for g in got]
+    six, five = np.full(n, 6, np.uint8), np.full(n, 5, np.uint8)
+    zh = np.tile(np.array([16, 0, 0, 0, 1], np.uint8), (n, 1))
+    prod, plen = oracle.poly_binop(2, a, six, b, six, 11)
+    quot, qlen, rem, rlen, st = oracle.poly_divide(prod, plen, zh, five, 7, 4)
+    ev = oracle.poly_eval(a, six, x)
+    ip, il = oracle.interpolate_at_h(vals)
+    assert not st.any()
+    ps.eq("config2 fused", tuple(got), (prod, plen, quot, qlen, rem, rlen, ev, ip, il))
