@@ -6,7 +6,10 @@
 
 namespace pb {
 
-constexpr int BLOCK = 128;         // threads per block for the heavy kernels (prove / verify / pairing)
+#ifndef PB_BLOCK
+#define PB_BLOCK 128
+#endif
+constexpr int BLOCK = PB_BLOCK;   // threads per block for the heavy kernels (prove / verify / pairing)
 constexpr int BLOCK_LIGHT = 256;   // for the byte-streaming kernels
 constexpr int POLY_MAX = 64;
 

@@ -35,7 +35,7 @@ try:
 except Exception as e:
     print(e)
 import sys, os, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from plonk_c_b200 import host, workload as W
 lib = host.lib()
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
