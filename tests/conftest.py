@@ -15,7 +15,10 @@ def pytest_configure(config):
 
 def _ensure_built():
     """CPU-side artefacts are built on demand (seconds); the CUDA library is built by __graft_entry__.build()."""
+    import shutil
     import __graft_entry__ as g
+    if not os.path.exists(g.LIB) and "PB_LIB" not in os.environ and shutil.which("nvcc"):
+        g.build_product()          # cross-compiles for sm_100a; the oracle's drop-in test binaries link against it
     if not os.path.exists(os.path.join(ROOT, "oracle", "libplonk_port.so")):
         g.build_oracle()
     return g
@@ -56,9 +59,6 @@ def host():
     """The product's ctypes binding.  GPU tests call through it into libplonk_b200.so -- if the library is
     missing the test FAILS (no skip, no fallback)."""
     from plonk_c_b200 import host as h
-    if not os.path.exists(h.LIB_PATH) and "PB_LIB" not in os.environ:
-        import shutil
-        if shutil.which("nvcc"):          # the build container: cross-compile for sm_100a (no GPU needed)
-            _ensure_built().build_product()
+    _ensure_built()
     h.lib()
     return h
