@@ -268,6 +268,44 @@ def check_protocol(impl, oracle, W, n=60000, modes=None, seed=11):
     eq("plonk_prove unsatisfied", impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal), oracle.plonk_prove_batch(C, g1s, g2, wit, rnd, chal))
 
 
+def random_circuit_batch(rng, n, identity_perm):
+    """A random circuit (all selector polynomials dense, q_O invertible) and n witnesses that satisfy it:
+    c = -(q_L a + q_R b + q_M a b + q_C) / q_O per gate.  identity_perm=True wires every cell to itself, so the grand
+    product closes and proofs complete; otherwise random copy constraints (almost every item exits with status 8)."""
+    sel = rng.integers(0, 17, (5, 4)).astype(np.int64)          # q_l q_r q_o q_m q_c
+    sel[2] = rng.integers(1, 17, 4)
+    circuit = np.zeros(44, np.uint8)
+    circuit[:20] = sel.ravel()
+    for s in range(3):
+        if identity_perm:
+            circuit[20 + 8 * s:24 + 8 * s] = s
+            circuit[24 + 8 * s:28 + 8 * s] = [1, 2, 3, 4]
+        else:
+            circuit[20 + 8 * s:24 + 8 * s] = rng.integers(0, 3, 4)
+            circuit[24 + 8 * s:28 + 8 * s] = rng.integers(1, 5, 4)
+    a = rng.integers(0, 17, (n, 4)).astype(np.int64)
+    b = rng.integers(0, 17, (n, 4)).astype(np.int64)
+    qo_inv = np.array([pow(int(q), 15, 17) for q in sel[2]], np.int64)
+    c = (-(sel[0] * a + sel[1] * b + sel[3] * a * b + sel[4]) * qo_inv) % 17
+    wit = np.concatenate([a, b, c], axis=1).astype(np.uint8)
+    return circuit, wit
+
+
+def check_random_circuits(impl, oracle, W, n=4000, circuits=12, seed=4):
+    """The circuit is data: selectors and copy constraints other than plonk-test's (dense q polynomials, q_C != 0)."""
+    rng = np.random.default_rng(seed)
+    g1s, g2 = W.generator_srs(9)
+    for k in range(circuits):
+        circuit, wit = random_circuit_batch(rng, n, identity_perm=(k % 3 != 2))
+        _, rnd, chal, u = W.make_batch(seed + k, 0, n, "U17" if k % 2 else "NZ")
+        want = oracle.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal, 8)
+        eq(f"random circuit {k} prove", impl.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal), want)
+        if k % 3 != 2:
+            assert (want[1] == 0).mean() > 0.3, "identity wiring should let proofs complete"
+        eq(f"random circuit {k} verify", impl.plonk_verify_batch(circuit, g1s, g2, want[0], chal, u),
+           oracle.plonk_verify_batch(circuit, g1s, g2, want[0], chal, u, 8))
+
+
 def check_protocol_golden(impl, W, n=2048):
     g = golden("protocol")
     C = W.PLONK_TEST_CIRCUIT

@@ -62,6 +62,16 @@ def test_header_struct_sizes(built, tmp_path):
 
 
 @pytest.mark.gpu
+def test_batch_api_from_c(built, tmp_path):
+    """include/plonk_b200.h used from plain C (the snippet of INTEGRATION.md, grown into a program)."""
+    exe = str(tmp_path / "batch_api_check")
+    r = _compile(os.path.join(ROOT, "tests", "c", "batch_api_check.c"), exe)
+    assert r.returncode == 0, r.stderr[-3000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "all checks passed" in run.stdout, run.stdout[-3000:] + run.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_dropin_check_program(built, tmp_path):
     exe = str(tmp_path / "dropin_check")
     r = _compile(os.path.join(ROOT, "tests", "c", "dropin_check.c"), exe)

@@ -235,3 +235,7 @@ def test_config2_fused(host, oracle, W):
     ip, il = oracle.interpolate_at_h(vals)
     assert not st.any()
     ps.eq("config2 fused", tuple(got), (prod, plen, quot, qlen, rem, rlen, ev, ip, il))
+
+
+def test_random_circuits(dev, oracle, W):
+    ps.check_random_circuits(dev, oracle, W)

@@ -42,3 +42,8 @@ def test_hostcheck_fast_paths(oracle, W):
     modes = [(m, f) for m, f in util.SRS_MODES.items()]
     ps.check_protocol(hcf, oracle, W, n=20000, modes=modes)
     ps.check_golden_transcript(hcf, W)
+
+
+def test_hostcheck_random_circuits(oracle, W):
+    ps.check_random_circuits(HostcheckImpl(oracle), oracle, W, n=2000, circuits=6)
+    ps.check_random_circuits(HostcheckImpl(oracle, fast=True), oracle, W, n=2000, circuits=6)
