@@ -1085,20 +1085,41 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     ctx->small_cap = cap;
   }
   cudaStream_t s0 = ctx->slots[0].stream;
-  if (mode == 1) {
-    CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, s0));
-    CU(cudaEventRecord(ctx->ev_u, s0));
-  }
+  // Chunk schedule: the pipeline's fill (first H2D + first kernels, D2H engine idle) and drain (last D2H, everything else
+  // idle) are exposed time, so the first and last chunks are small and the sizes double towards the middle, where
+  // chunks have the full size pipe_chunk() that keeps every copy above ~1 MB.
   const size_t chunk = pipe_chunk();
+  std::vector<size_t> sched;
+  {
+    const size_t small = 1u << 15;
+    const size_t ragged = n % 128;          // every chunk but the very last starts at a multiple of 128 items (16-byte aligned slices)
+    size_t head = small, left = n - ragged;
+    std::vector<size_t> tail;
+    while (left > 0) {
+      if (left <= 2 * head || head >= chunk) break;
+      sched.push_back(head);
+      tail.push_back(head);
+      left -= 2 * head;
+      head *= 2;
+    }
+    while (left > 0) { size_t m = left < chunk ? left : chunk; sched.push_back(m); left -= m; }
+    for (size_t k = tail.size(); k-- > 0;) sched.push_back(tail[k]);
+    if (ragged) sched.push_back(ragged);
+  }
   size_t done = 0;
   int slot = 0, used = 0;
-  while (done < n) {
-    size_t m = n - done < chunk ? n - done : chunk;
+  bool u_sent = false;
+  for (size_t m : sched) {
     PipeSlot& s = ctx->slots[slot];
     CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, s.stream));
     if (mode == 1) {
+      if (!u_sent) {               // the whole u array follows the first (small) chunk's inputs on the same stream
+        CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, s0));
+        CU(cudaEventRecord(ctx->ev_u, s0));
+        u_sent = true;
+      }
       if (slot != 0 && used < PIPE_SLOTS) CU(cudaStreamWaitEvent(s.stream, ctx->ev_u, 0));
       rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, ctx->d_u + done, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.stream);
     } else {
