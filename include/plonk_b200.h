@@ -103,6 +103,10 @@ int pb_ctx_srs_table(const pb_ctx *ctx, uint8_t *out);
 int pb_field_op_dev(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream);
 int pb_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
 
+/* hf_new / gf_new (hf.h:25-35, gf.h:24-34): out[i] = v[i] mod p as the C remainder with negatives folded into [0, p) */
+int pb_field_new_dev(int field, const int64_t *v, uint8_t *out, size_t n, void *stream);
+int pb_field_new(int field, const int64_t *v, uint8_t *out, size_t n);
+
 /* ---- kernel family (2): poly.h, matrix.h interpolation.  A polynomial batch is rows of `stride`
  * coefficient bytes (low degree first) plus one length byte per row; rows are passed through
  * poly_new first (trailing zeros trimmed, poly.h:20-38); 1 <= len <= stride <= PB_POLY_MAX. */

@@ -215,6 +215,30 @@ int pb_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* 
   return PB_OK;
 }
 
+int pb_field_new_dev(int field, const int64_t* v, uint8_t* out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG((field == 17 || field == 101) && v && out);
+  unsigned grid = blocks_for(n, BLOCK_LIGHT);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (field == 17) field_new_kernel<17><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(reinterpret_cast<const long long*>(v), out, n);
+  else field_new_kernel<101><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(reinterpret_cast<const long long*>(v), out, n);
+  LAUNCH_CHECK("field_new_kernel");
+  return PB_OK;
+}
+int pb_field_new(int field, const int64_t* v, uint8_t* out, size_t n) {
+  if (n == 0) return PB_OK;
+  int rc = require_device();
+  if (rc) return rc;
+  ARG(v && out);
+  DEV(dv, n * 8); DEV(dout, n);
+  H2D(dv, v, n * 8);
+  rc = pb_field_new_dev(field, dv.as<int64_t>(), dout.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(out, dout, n);
+  return PB_OK;
+}
+
 // ------------------------------------------------------------------ family (2)
 int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
                       uint8_t* out, uint8_t* olen, size_t so, size_t n, void* stream) {

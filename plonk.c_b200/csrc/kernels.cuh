@@ -77,6 +77,14 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uin
     out[i] = (uint8_t)field_apply<FIELD>(ft, op, a[i], b ? b[i] : 0u);
 }
 
+// hf_new / gf_new (hf.h:25-35, gf.h:24-34): C remainder of a signed 64-bit value, negatives folded up
+template <int FIELD>
+__global__ void __launch_bounds__(BLOCK_LIGHT) field_new_kernel(const long long* __restrict__ v, uint8_t* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (uint8_t)(FIELD == 17 ? new17(v[i]) : new101(v[i]));
+}
+
 // ------------------------------------------------------------------ family (2), generic shapes
 // Polynomials in per-thread local arrays; dynamic lengths.  (Fixed-shape fast paths: poly_fast.cuh.)
 struct LPoly { uint8_t c[2 * POLY_MAX]; int len; };

@@ -127,6 +127,17 @@ def field_op(field, op, a, b=None):
     return out
 
 
+def field_new(field, v):
+    """hf_new / gf_new over an int64 array (hf.h:25-35, gf.h:24-34)."""
+    c = _Call("pb_field_new", v)
+    n = int(np.prod(v.shape))
+    out, po = c.out(tuple(v.shape))
+    c.run(C.c_int(field), c.inp(v, np.int64), po, C.c_size_t(n))
+    return out
+
+
+def hf_new(v): return field_new(17, v)
+def gf_new(v): return field_new(101, v)
 def hf_add(a, b): return field_op(17, OP_ADD, a, b)
 def hf_sub(a, b): return field_op(17, OP_SUB, a, b)
 def hf_mul(a, b): return field_op(17, OP_MUL, a, b)

@@ -239,3 +239,15 @@ def test_config2_fused(host, oracle, W):
 
 def test_random_circuits(dev, oracle, W):
     ps.check_random_circuits(dev, oracle, W)
+
+
+def test_field_new(host, oracle):
+    """hf_new / gf_new on negatives and on +-1.7e18 (hf-test.c:231-248, gf-test.c:44-88)."""
+    import torch
+    rng = np.random.default_rng(1)
+    v = np.concatenate([rng.integers(-2**62, 2**62, 5000), np.arange(-300, 300),
+                        np.array([-(17 ** 14), 17 ** 14, -1, 0, 1, 2**63 - 1, -2**63, 1700000000000000000, -1700000000000000000])]).astype(np.int64)
+    for field, ofn in ((17, oracle.hf_new), (101, oracle.gf_new)):
+        want = np.array([ofn(int(x)) for x in v], np.uint8)
+        ps.eq(f"new{field} host path", host.field_new(field, v), want)
+        ps.eq(f"new{field} device path", host.field_new(field, torch.from_numpy(v).cuda()).cpu().numpy(), want)
