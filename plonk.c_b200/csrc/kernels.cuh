@@ -536,7 +536,7 @@ struct __align__(16) ProveSmem {
 // done_list / done_count (optional): indices of the completed proofs (status 0) are appended, one atomic per warp,
 // so that the verifier runs on a dense list; verdict (optional) gets 0xFF for every item that did not complete.
 #ifndef PB_PROVE_MINBLOCKS
-#define PB_PROVE_MINBLOCKS 1
+#define PB_PROVE_MINBLOCKS 5   // 96 registers (44 B of spills), 5 blocks of 128 threads per SM: measured best (profiles/r1/NOTES.md)
 #endif
 template <typename Tables>
 __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
