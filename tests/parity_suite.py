@@ -306,6 +306,38 @@ def check_random_circuits(impl, oracle, W, n=4000, circuits=12, seed=4):
            oracle.plonk_verify_batch(circuit, g1s, g2, want[0], chal, u, 8))
 
 
+def curve_points():
+    """All 101 finite points of y^2 = x^3 + 3 over F_101 (the group has order 102 = 2 * 3 * 17: it contains the 2-torsion
+    point (48, 0) and points of order 3, 6, 34, 51, 102 besides the order-17 subgroup the reference uses)."""
+    pts = [(x, y) for x in range(101) for y in range(101) if (y * y - x * x * x - 3) % 101 == 0]
+    assert len(pts) == 101 and (48, 0) in pts
+    return np.array([[x, y, 0] for x, y in pts], np.uint8)
+
+
+def check_whole_curve_srs(impl, oracle, W, n=6000, trials=6, seed=33):
+    """SRS points drawn from the WHOLE curve group (not only the order-17 subgroup), canonical identities mixed in.
+    Such an SRS is still "canonically encoded on-curve", so the fast paths (pair tables, joint double-and-add, re-ordered
+    additions) are taken -- their exactness argument is the group law, which must hold for 2-torsion and cofactor points too."""
+    rng = np.random.default_rng(seed)
+    pts = curve_points()
+    C = W.PLONK_TEST_CIRCUIT
+    for t in range(trials):
+        ln = int(rng.integers(9, 13))
+        g1s = pts[rng.integers(0, 101, ln)].copy()
+        g1s[rng.random(ln) < 0.15] = [0, 0, 1]
+        if t == 0:
+            g1s[:4] = [[48, 0, 0], [48, 0, 0], [0, 0, 1], [48, 0, 0]]        # 2-torsion: P + P = identity
+        g2 = np.array([36, 31, 90, 82], np.uint8)
+        wit, rnd, chal, u = W.make_batch(seed + t, 0, n, "U17")
+        want = oracle.plonk_prove_batch(C, g1s, g2, wit, rnd, chal, 8)
+        eq(f"whole-curve SRS {t} prove", impl.plonk_prove_batch(C, g1s, g2, wit, rnd, chal), want)
+        proofs = want[0].copy()
+        k = rng.integers(0, n, n // 2)                                        # replace commitments by arbitrary curve points
+        proofs[k[:, None], 3 * rng.integers(0, 9, n // 2)[:, None] + np.arange(3)] = pts[rng.integers(0, 101, n // 2)]
+        eq(f"whole-curve SRS {t} verify", impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u),
+           oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8))
+
+
 def check_protocol_golden(impl, W, n=2048):
     g = golden("protocol")
     C = W.PLONK_TEST_CIRCUIT

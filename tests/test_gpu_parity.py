@@ -251,3 +251,7 @@ def test_field_new(host, oracle):
         want = np.array([ofn(int(x)) for x in v], np.uint8)
         ps.eq(f"new{field} host path", host.field_new(field, v), want)
         ps.eq(f"new{field} device path", host.field_new(field, torch.from_numpy(v).cuda()).cpu().numpy(), want)
+
+
+def test_whole_curve_srs(dev, oracle, W):
+    ps.check_whole_curve_srs(dev, oracle, W)

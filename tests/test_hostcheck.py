@@ -47,3 +47,8 @@ def test_hostcheck_fast_paths(oracle, W):
 def test_hostcheck_random_circuits(oracle, W):
     ps.check_random_circuits(HostcheckImpl(oracle), oracle, W, n=2000, circuits=6)
     ps.check_random_circuits(HostcheckImpl(oracle, fast=True), oracle, W, n=2000, circuits=6)
+
+
+def test_hostcheck_whole_curve_srs(oracle, W):
+    ps.check_whole_curve_srs(HostcheckImpl(oracle, fast=True), oracle, W, n=3000, trials=6)
+    ps.check_whole_curve_srs(HostcheckImpl(oracle), oracle, W, n=2000, trials=2)
