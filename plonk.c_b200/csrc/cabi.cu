@@ -67,8 +67,8 @@ struct Dev {
 #define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
-constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // device scratch per slot is sized for this many items
-constexpr int PIPE_SLOTS = 4;
+constexpr size_t PIPE_CHUNK_MAX = 1u << 19;   // device scratch per slot is sized for this many items
+constexpr int PIPE_SLOTS = 6;
 // items per pipeline chunk of the host-pointer prove/verify (PB_PIPE_CHUNK overrides, for tuning; multiple of 128)
 size_t pipe_chunk() {
   static size_t v = [] {
@@ -80,8 +80,7 @@ size_t pipe_chunk() {
 }
 
 struct PipeSlot {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // inputs landed / kernels done / proofs copied out
   uint8_t *wit = nullptr, *rnd = nullptr, *chal = nullptr, *proofs = nullptr;
 };
 
@@ -112,7 +111,7 @@ struct pb_ctx {
   std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
   std::mutex pipe_mu;
   bool pipe_ready = false;
-  cudaEvent_t ev_u = nullptr;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;       // H2D engine, SMs, D2H engine
   uint8_t *d_u = nullptr, *d_status = nullptr, *d_verdict = nullptr;   // whole-batch one-byte arrays of the host-pointer pipeline
   size_t small_cap = 0;
   PipeSlot slots[PIPE_SLOTS];
@@ -147,15 +146,18 @@ int scratch_for(const pb_ctx* cctx, cudaStream_t st, size_t n, uint32_t** out) {
 
 int pipe_init(pb_ctx* c) {
   if (c->pipe_ready) return PB_OK;
+  CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   for (auto& s : c->slots) {
-    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&s.wit, PIPE_CHUNK_MAX * 12));
     CU(cudaMalloc(&s.rnd, PIPE_CHUNK_MAX * 9));
     CU(cudaMalloc(&s.chal, PIPE_CHUNK_MAX * 5));
     CU(cudaMalloc(&s.proofs, PIPE_CHUNK_MAX * 34));
-    CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
   }
-  CU(cudaEventCreateWithFlags(&c->ev_u, cudaEventDisableTiming));
   c->pipe_ready = true;
   return PB_OK;
 }
@@ -974,12 +976,11 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (c->d_verify_tables) cudaFree(c->d_verify_tables);
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
-    if (s.stream) cudaStreamDestroy(s.stream);
-    if (s.done) cudaEventDestroy(s.done);
+    for (cudaEvent_t e : {s.ev_in, s.ev_k, s.ev_out}) if (e) cudaEventDestroy(e);
     uint8_t* bufs[4] = {s.wit, s.rnd, s.chal, s.proofs};
     for (auto b : bufs) if (b) cudaFree(b);
   }
-  if (c->ev_u) cudaEventDestroy(c->ev_u);
+  for (cudaStream_t st : {c->s_in, c->s_k, c->s_out}) if (st) cudaStreamDestroy(st);
   for (uint8_t* p : {c->d_u, c->d_status, c->d_verdict}) if (p) cudaFree(p);
   delete c;
   return PB_OK;
@@ -1091,10 +1092,14 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, cons
   return rc;
 }
 
-// host-pointer versions.  Chunks of pipe_chunk() items rotate over PIPE_SLOTS streams so that the two copy engines and
-// the SMs work on different chunks at the same time.  PCIe throughput on the B200 hosts drops sharply for pieces below
-// ~1 MB (profiles/r1/pcie_probe.txt), so the one-byte-per-item arrays (u in, status and verdict out) are NOT chunked:
-// u goes up once before the first chunk, status and verdict come back once after the last one.
+// host-pointer versions: a three-stage pipeline over chunks, one stream per hardware engine -- s_in (H2D copy engine),
+// s_k (SMs), s_out (D2H copy engine) -- tied together by events, over a ring of PIPE_SLOTS buffer sets:
+//   H2D(c) waits for kernels(c - SLOTS) (input buffers free);  kernels(c) wait for H2D(c) and D2H(c - SLOTS) (proof buffer free);
+//   D2H(c) waits for kernels(c).
+// The input stage therefore never waits for the (slower) output stage, so once the inputs are up the D2H engine has the
+// PCIe link to itself.  PCIe throughput on these hosts drops sharply for pieces below ~1 MB
+// (profiles/r1/pcie_probe.txt), so the one-byte-per-item arrays (u in, status and verdict out) are not chunked: u goes
+// up with the first chunk, status and verdict come back after the last one.
 static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                     uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, int mode /*0 prove, 1 prove+verify*/) {
   pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
@@ -1108,10 +1113,8 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     CU(cudaMalloc(&ctx->d_u, cap)); CU(cudaMalloc(&ctx->d_status, cap)); CU(cudaMalloc(&ctx->d_verdict, cap));
     ctx->small_cap = cap;
   }
-  cudaStream_t s0 = ctx->slots[0].stream;
-  // Chunk schedule: the pipeline's fill (first H2D + first kernels, D2H engine idle) and drain (last D2H, everything else
-  // idle) are exposed time, so the first and last chunks are small and the sizes double towards the middle, where
-  // chunks have the full size pipe_chunk() that keeps every copy above ~1 MB.
+  // Chunk schedule: fill (first H2D + first kernels) and drain (last D2H) are exposed time, so the first and last chunks
+  // are small and the sizes double towards the middle, where chunks have the full size pipe_chunk().
   const size_t chunk = pipe_chunk();
   std::vector<size_t> sched;
   {
@@ -1130,39 +1133,61 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     for (size_t k = tail.size(); k-- > 0;) sched.push_back(tail[k]);
     if (ragged) sched.push_back(ragged);
   }
-  size_t done = 0;
-  int slot = 0, used = 0;
-  bool u_sent = false;
+  // PB_PIPE_TRACE=1: print, per chunk, when its inputs landed / its kernels finished / its proofs were copied out
+  static const bool trace = getenv("PB_PIPE_TRACE") && getenv("PB_PIPE_TRACE")[0] == '1';
+  std::vector<cudaEvent_t> tev;
+  cudaEvent_t t0 = nullptr;
+  if (trace) {
+    tev.resize(3 * sched.size());
+    for (auto& e : tev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreate(&t0));
+    CU(cudaEventRecord(t0, ctx->s_in));
+  }
+  size_t done = 0, c = 0;
   for (size_t m : sched) {
-    PipeSlot& s = ctx->slots[slot];
-    CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, s.stream));
-    CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, s.stream));
-    CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, s.stream));
-    if (mode == 1) {
-      if (!u_sent) {               // the whole u array follows the first (small) chunk's inputs on the same stream
-        CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, s0));
-        CU(cudaEventRecord(ctx->ev_u, s0));
-        u_sent = true;
-      }
-      if (slot != 0 && used < PIPE_SLOTS) CU(cudaStreamWaitEvent(s.stream, ctx->ev_u, 0));
-      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, ctx->d_u + done, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.stream);
-    } else {
-      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, ctx->d_status + done, m, s.stream);
-    }
+    PipeSlot& s = ctx->slots[c % PIPE_SLOTS];
+    const bool reuse = c >= (size_t)PIPE_SLOTS;
+    if (reuse) CU(cudaStreamWaitEvent(ctx->s_in, s.ev_k, 0));
+    CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, ctx->s_in));
+    if (mode == 1 && c == 0) CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaEventRecord(s.ev_in, ctx->s_in));
+    if (trace) CU(cudaEventRecord(tev[3 * c], ctx->s_in));
+    CU(cudaStreamWaitEvent(ctx->s_k, s.ev_in, 0));
+    if (reuse) CU(cudaStreamWaitEvent(ctx->s_k, s.ev_out, 0));
+    static const bool nokernel = getenv("PB_PIPE_NOKERNEL") && getenv("PB_PIPE_NOKERNEL")[0] == '1';   // copy-only timing experiment
+    if (nokernel)
+      rc = PB_OK;
+    else if (mode == 1)
+      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, ctx->d_u + done, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, ctx->s_k);
+    else
+      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, ctx->d_status + done, m, ctx->s_k);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaEventRecord(s.ev_k, ctx->s_k));
+    if (trace) CU(cudaEventRecord(tev[3 * c + 1], ctx->s_k));
+    CU(cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
+    CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, ctx->s_out));
+    CU(cudaEventRecord(s.ev_out, ctx->s_out));
+    if (trace) CU(cudaEventRecord(tev[3 * c + 2], ctx->s_out));
     done += m;
-    slot = (slot + 1) % PIPE_SLOTS;
-    if (used < PIPE_SLOTS) used++;
+    c++;
   }
-  // every slot's work must be finished before the two small arrays come back on slot 0's stream
-  for (int k = 1; k < used; k++) {
-    CU(cudaEventRecord(ctx->slots[k].done, ctx->slots[k].stream));
-    CU(cudaStreamWaitEvent(s0, ctx->slots[k].done, 0));
+  // s_out is ordered after the last kernels (ev_k of the last chunk), which are ordered after all earlier ones on s_k
+  CU(cudaMemcpyAsync(status, ctx->d_status, n, cudaMemcpyDeviceToHost, ctx->s_out));
+  if (mode == 1) CU(cudaMemcpyAsync(verdict, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->s_out));
+  CU(cudaStreamSynchronize(ctx->s_out));
+  CU(cudaStreamSynchronize(ctx->s_in));
+  CU(cudaStreamSynchronize(ctx->s_k));
+  if (trace) {
+    for (size_t k = 0; k < sched.size(); k++) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, t0, tev[3 * k]); cudaEventElapsedTime(&b, t0, tev[3 * k + 1]); cudaEventElapsedTime(&d, t0, tev[3 * k + 2]);
+      fprintf(stderr, "pipe chunk %2zu items %7zu  in %.3f ms  kernels %.3f ms  out %.3f ms\n", k, sched[k], a, b, d);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+    cudaEventDestroy(t0);
   }
-  CU(cudaMemcpyAsync(status, ctx->d_status, n, cudaMemcpyDeviceToHost, s0));
-  if (mode == 1) CU(cudaMemcpyAsync(verdict, ctx->d_verdict, n, cudaMemcpyDeviceToHost, s0));
-  for (int k = 0; k < used; k++) CU(cudaStreamSynchronize(ctx->slots[k].stream));
   return PB_OK;
 }
 int pb_plonk_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status, size_t n) {
