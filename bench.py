@@ -252,6 +252,16 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device. This path has no CPU fallback (use --impl reference for the CPU arm).")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NUMA: run this rank (and first-touch its pinned buffers) on the CPUs closest to its GPU; with 8 ranks on a two-socket
+    # host the end-to-end path is otherwise limited by cross-socket traffic
+    numa = "unset"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = f"nvmlDeviceSetCpuAffinity ok, {len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:
+        numa = f"not set ({type(e).__name__})"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -423,7 +433,7 @@ def run_b200(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / e2e_steps, "api": "pb_plonk_prove_verify (host pointers, pinned)"},
+                "ms_per_step": e2e_ms / e2e_steps, "api": "pb_plonk_prove_verify (host pointers, pinned)", "cpu_affinity": numa},
         "gpu_launches": 3 * args.steps,
         "roofline": roof,
         "clocks": sampler.summary(t0, t1) if sampler else None,

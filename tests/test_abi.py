@@ -27,6 +27,33 @@ def test_library_exports_every_declared_symbol(host):
     assert lib.pb_abi_version() == 1
 
 
+def dropin_declared_functions():
+    """Functions the ten drop-in headers declare (everything between their extern "C" guards)."""
+    names = {}
+    for h in ("poly", "matrix", "g1", "g2", "gt", "pairing", "srs", "constraints", "plonk"):
+        text = open(os.path.join(ROOT, "include", h + ".h")).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        m = re.search(r'extern "C" \{\s*#endif(.*?)#ifdef __cplusplus\s*\}', text, flags=re.S)
+        assert m, h
+        for fn in re.findall(r"\b([a-z][a-z0-9_]*)\s*\([^;{]*\)\s*;", m.group(1)):
+            names[fn] = h
+    return names
+
+
+def test_library_exports_every_dropin_function(host):
+    """include/{poly,matrix,g1,g2,gt,pairing,srs,constraints,plonk}.h only DECLARE the reference's functions; the shared
+    library must define every one of them (the reference defines them in its headers: src/*.h)."""
+    lib = host.lib()
+    names = dropin_declared_functions()
+    assert len(names) >= 60, len(names)
+    for must in ("poly_mul", "poly_divide", "matrix_inv", "g1_mul", "g2_add", "gtp_pow", "pairing", "srs_eval_at_s", "eval_expr",
+                 "constraints_satisfy", "plonk_new", "interpolate_at_h", "plonk_prove", "poly_print", "copy_constraints_to_roots"):
+        assert must in names, must
+    missing = [f"{n} ({h}.h)" for n, h in names.items() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert not hasattr(lib, "matrix_equal")      # the reference's tests define their own (plonk-test.c:11, matrix-test.c:4)
+
+
 def test_every_dev_entry_point_has_a_host_twin():
     names = set(declared_symbols())
     for n in names:
