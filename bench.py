@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--variant", default="U17", choices=["U17", "NZ"])
     ap.add_argument("--ref-items", type=int, default=1 << 18, help="proofs per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "poly", "g1_mul", "pairing"],
+    ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "prove_verify_fs", "poly", "g1_mul", "pairing"],
                     help="prove_verify = BASELINE config 5 (the headline, what the driver runs); poly / g1_mul / pairing = "
                          "configs 2 / 3 / 4 (single GPU, device-resident; extra lines for profiles/)")
     return ap.parse_args()
@@ -551,7 +551,7 @@ def run_config(args):
                          "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
             "cpu_baseline": {"value": cpu_rate, "unit": "smul/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
         gpu_launches = args.steps
-    else:
+    elif args.workload == "pairing":
         n = 1 << 22
         ai, bi, sc = W.make_group_items(SEED, 0, n)
         Pn = W.g1_subgroup_table()[ai]
@@ -573,7 +573,43 @@ def run_config(args):
                          "algorithmic_int_ops_per_item": int_ops, "traffic": None, "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
             "cpu_baseline": {"value": cpu_rate, "unit": "pairings/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
         gpu_launches = args.steps
-    if line["roofline"]["bound"] == "int32":
+    elif args.workload == "prove_verify_fs":
+        # the optional Fiat-Shamir mode on the headline workload: challenges drawn in the kernels (csrc/transcript.cuh)
+        n = 1 << 21
+        srs = W.generator_srs(9)
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *srs)
+        wit, rnd, _, _ = W.make_batch(SEED, 0, n, "U17")
+        Wt, Rt = T(wit), T(rnd)
+        proofs = torch.empty((n, 34), dtype=torch.uint8, device=dev)
+        status = torch.empty(n, dtype=torch.uint8, device=dev)
+        verdict = torch.empty(n, dtype=torch.uint8, device=dev)
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record(stream)            # torch creates the CUDA event lazily; the library records into it by handle
+        ms = timed(lambda: pk.prove_verify_fs_into(Wt, Rt, proofs, status, verdict))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        a.record(stream)
+        pk.prove_verify_fs_into(Wt, Rt, proofs, status, verdict, mid_event=C.c_void_p(mid.cuda_event))
+        b.record(stream)
+        torch.cuda.synchronize()
+        k_prove, k_verify = a.elapsed_time(mid), mid.elapsed_time(b)
+        m = 1 << 16
+        t0 = time.perf_counter()
+        pr, st_, ch = oracle.plonk_prove_fs_batch(W.PLONK_TEST_CIRCUIT, srs[0], srs[1], wit[:m], rnd[:m], cores)
+        oracle.plonk_verify_fs_batch(W.PLONK_TEST_CIRCUIT, srs[0], srs[1], pr[st_ == 0], cores)
+        cpu_rate = m / (time.perf_counter() - t0)
+        ok = bool((proofs[:m].cpu().numpy() == pr).all() and (status[:m].cpu().numpy() == st_).all())
+        line = {"metric": "plonk_prove_verify_fs_proofs_per_s", "unit": "proofs/s", "value": n / (ms * 1e-3), "config": {
+            "workload": "BASELINE config 5 in Fiat-Shamir mode (challenges drawn from the transcript in the kernels): 2^21 items, "
+                        "generator SRS n=9, U17 blinding"},
+            "kernel_ms": {"prove_kernel<FS>": k_prove, "verify_fast_kernel(fs)": k_verify, "both": ms},
+            "matches_oracle_on_sample": ok,
+            "roofline": {"bound": "int32", "kernel": "prove_kernel<FS>", "unit": "TIOP/s", "achieved": None, "traffic": None,
+                         "note": "same arithmetic as the explicit-challenge prover plus ~17 hash mixes; see the default workload for the roofline"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "proofs/s", "cores": cores, "kind": okind,
+                             "sample": f"first {m} items, {cores} threads; the reference is re-run once per round (<= 5 passes) to draw its challenges"}}
+        gpu_launches = 2 * (args.steps + 1)
+    if line["roofline"]["bound"] == "int32" and line["roofline"]["achieved"] is not None:
         sink = torch.zeros(4, dtype=torch.int32, device=dev)
         ops = C.c_uint64(0)
         best = 0.0

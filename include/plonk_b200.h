@@ -229,6 +229,30 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx *ctx, const uint8_t *witness, cons
                                  void *mid_event);
 int pb_plonk_prove_verify(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                           const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n);
+/* ---- Fiat-Shamir mode (optional).  The reference's prover takes its challenges from
+ * the caller (CHALLENGE, plonk.h:16-22,227) -- the entry points above keep that interface and are bit-exact with it.
+ * Here the five challenges, and the verifier's u, are drawn from a transcript hash of the circuit, the SRS and the proof
+ * elements produced so far (specification: oracle/fs_spec.inc; kernel side: csrc/transcript.cuh).  Given the challenges
+ * the transcript yields, proofs and statuses are exactly what plonk_prove returns for them. */
+/* initial transcript state for this context's circuit + SRS */
+int pb_ctx_fs_seed(const pb_ctx *ctx, uint32_t *out);
+/* witness[n][12], rnd[n][9] -> proofs[n][34], status[n]; chal_out (optional, may be NULL): [n][6] = alpha beta gamma z v u
+ * as drawn, 0xFF for a challenge the reference's execution exits before drawing */
+int pb_plonk_prove_fs_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, uint8_t *proofs, uint8_t *status,
+                          uint8_t *chal_out, size_t n, void *stream);
+int pb_plonk_prove_fs(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, uint8_t *proofs, uint8_t *status,
+                      uint8_t *chal_out, size_t n);
+/* the verifier re-derives all six challenges from the proof bytes */
+int pb_plonk_verify_fs_dev(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *verdict, uint8_t *gt, size_t n, void *stream);
+int pb_plonk_verify_fs(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *verdict, uint8_t *gt, size_t n);
+/* prove, then verify every completed proof (verdict 0xFF elsewhere); mid_event as in pb_plonk_prove_verify_ex_dev */
+int pb_plonk_prove_verify_fs_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, uint8_t *proofs, uint8_t *status,
+                                 uint8_t *verdict, size_t n, void *stream, void *mid_event);
+int pb_plonk_prove_verify_fs(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, uint8_t *proofs, uint8_t *status,
+                             uint8_t *verdict, size_t n);
+/* the six challenges of each PROOF record as a verifier derives them: chal6[n][6] */
+int pb_fs_challenges_dev(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *chal6, size_t n, void *stream);
+int pb_fs_challenges(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *chal6, size_t n);
 /* on-device tally: counts[0..15] += number of items per status byte (0..14, 15 = anything else),
  * counts[16] += verdict==1, counts[17] += a 64-bit sum of all proof bytes (checksum). counts: int64[18] device ptr */
 int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *verdict, size_t n, int64_t *counts, void *stream);

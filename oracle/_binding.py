@@ -259,6 +259,40 @@ class OracleLib:
             _p(circuit), _p(g1s), g1s.shape[0], _p(g2), _p(proofs), _p(chal), _p(u), n, _p(verdict), _p(gt), nthreads)
         return verdict, gt
 
+    # ---- Fiat-Shamir mode (spec: oracle/fs_spec.inc)
+    def plonk_prove_fs_batch(self, circuit, g1s, g2, wit, rnd, nthreads=1):
+        """-> proofs [n][34], status [n], chal [n][6] = alpha beta gamma z v u (0xFF where not drawn)"""
+        circuit, g1s, g2 = _u8(circuit), _u8(g1s), _u8(g2)
+        wit, rnd = _u8(wit), _u8(rnd)
+        n = wit.shape[0]
+        assert wit.shape == (n, 12) and rnd.shape == (n, 9) and circuit.size == 44
+        proofs = np.zeros((n, 34), np.uint8)
+        status = np.zeros(n, np.uint8)
+        chal = np.zeros((n, 6), np.uint8)
+        self._f("plonk_prove_fs_batch", [u8p, u8p, C.c_uint32, u8p, u8p, u8p, C.c_size_t, u8p, u8p, u8p, C.c_int])(
+            _p(circuit), _p(g1s), g1s.shape[0], _p(g2), _p(wit), _p(rnd), n, _p(proofs), _p(status), _p(chal), nthreads)
+        return proofs, status, chal
+
+    def fs_seed(self, circuit, g1s, g2):
+        circuit, g1s, g2 = _u8(circuit), _u8(g1s), _u8(g2)
+        return int(self._f("fs_seed", [u8p, u8p, C.c_uint32, u8p], C.c_uint32)(_p(circuit), _p(g1s), g1s.shape[0], _p(g2)))
+
+    def fs_challenges(self, circuit, g1s, g2, proofs):
+        return self.fs_derive(self.fs_seed(circuit, g1s, g2), proofs)
+
+    def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, nthreads=1, want_gt=True):
+        """the verifier's side of Fiat-Shamir mode: derive the six challenges, then the explicit-challenge verifier"""
+        d = self.fs_challenges(circuit, g1s, g2, proofs)
+        return self.plonk_verify_batch(circuit, g1s, g2, proofs, np.ascontiguousarray(d[:, :5]), np.ascontiguousarray(d[:, 5]),
+                                       nthreads, want_gt)
+
+    def fs_derive(self, seed, proofs):
+        proofs = _u8(proofs)
+        n = proofs.shape[0]
+        chal = np.zeros((n, 6), np.uint8)
+        self._f("fs_derive", [C.c_uint32, u8p, C.c_size_t, u8p])(seed, _p(proofs), n, _p(chal))
+        return chal
+
     def verifier_key(self, circuit, g1s, g2):
         circuit, g1s, g2 = _u8(circuit), _u8(g1s), _u8(g2)
         out = np.zeros((9, 3), np.uint8)

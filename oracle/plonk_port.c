@@ -21,6 +21,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <pthread.h>
+#include "fs_spec.inc"
 
 typedef uint8_t fe; /* a field element, always stored reduced */
 
@@ -432,11 +433,15 @@ static poly lin2(fe c0, fe c1) { fe t[2] = {c0, c1}; return poly_make(t, 2); }
 static void put_g1(uint8_t *o, g1 p) { o[0] = p.x; o[1] = p.y; o[2] = p.inf ? 1 : 0; }
 
 /* plonk.h:223-656.  Returns the SURVEY.md Appendix-B row of the first exit that fires (0 = done). */
+/* Fiat-Shamir mode (fs != NULL; spec: fs_spec.inc): ch is ignored, each challenge is drawn from the transcript at
+ * the point where the protocol fixes it, and fs->ch / fs->known report what was drawn before the first exit. */
+typedef struct { uint32_t st; uint8_t ch[6], known[6]; } fs_t;
 static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, const fe *wb, const fe *wc,
-                        const fe ch[5], const fe rnd[9], uint8_t proof[34]) {
+                        const fe ch[5], const fe rnd[9], uint8_t proof[34], fs_t *fs) {
   const int n = 4;
   if (!satisfies_(cs, wa, wb, wc)) return 1;                                    /* plonk.h:231 */
-  fe alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
+  fe alpha = 0, beta = 0, gamma = 0, z = 0, v = 0;
+  if (!fs) { alpha = ch[0]; beta = ch[1]; gamma = ch[2]; z = ch[3]; v = ch[4]; }
   const fe omega = 4, k1 = 2, k2 = 3;
   fe sg1[4], sg2[4], sg3[4];
   if (copy_to_roots_(pk, cs->c_type[0], cs->c_idx[0], n, sg1)) return 3;        /* plonk.h:254-256 */
@@ -456,6 +461,11 @@ static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, co
   if (srs_commit_(&pk->srs, &a, &a_s)) return 5;
   if (srs_commit_(&pk->srs, &b, &b_s)) return 5;
   if (srs_commit_(&pk->srs, &c, &c_s)) return 5;
+  if (fs) {
+    put_g1(proof, a_s); put_g1(proof + 3, b_s); put_g1(proof + 6, c_s);
+    fs->st = fs_round1(fs->st, proof, fs->ch);
+    beta = fs->ch[1]; gamma = fs->ch[2]; fs->known[1] = fs->known[2] = 1;
+  }
 
   /* round 2 (plonk.h:320-379) */
   fe acc[4];
@@ -478,6 +488,11 @@ static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, co
   poly zx = poly_add_(&t, &accx);
   g1 z_s;
   if (srs_commit_(&pk->srs, &zx, &z_s)) return 7;
+  if (fs) {
+    put_g1(proof + 9, z_s);
+    fs->st = fs_round2(fs->st, proof, fs->ch);
+    alpha = fs->ch[0]; fs->known[0] = 1;
+  }
 
   /* round 3 (plonk.h:385-524) */
   fe lv[4] = {1, 0, 0, 0};
@@ -524,6 +539,11 @@ static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, co
   if (srs_commit_(&pk->srs, &tlo, &tlo_s)) return 10;
   if (srs_commit_(&pk->srs, &tmid, &tmid_s)) return 10;
   if (srs_commit_(&pk->srs, &thi, &thi_s)) return 10;
+  if (fs) {
+    put_g1(proof + 12, tlo_s); put_g1(proof + 15, tmid_s); put_g1(proof + 18, thi_s);
+    fs->st = fs_round3(fs->st, proof, fs->ch);
+    z = fs->ch[3]; fs->known[3] = 1;
+  }
 
   /* round 4 (plonk.h:527-574) */
   fe a_z = poly_eval_(&a, z), b_z = poly_eval_(&b, z), c_z = poly_eval_(&c, z);
@@ -548,6 +568,12 @@ static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, co
   rx = poly_add_(&rx, &r3);
   rx = poly_add_(&rx, &r4);
   fe r_z = poly_eval_(&rx, z);
+  if (fs) {
+    fe sc4[7] = {a_z, b_z, c_z, s1_z, s2_z, r_z, zw_z};
+    memcpy(proof + 27, sc4, 7);
+    fs->st = fs_round4(fs->st, proof, fs->ch);
+    v = fs->ch[4]; fs->known[4] = 1;
+  }
 
   /* round 5 (plonk.h:582-621) */
   poly tm = poly_scale_(&tmid, hf_pow_(z, (uint64_t)(n + 2)));
@@ -579,6 +605,7 @@ static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, co
   for (int i = 0; i < 9; i++) put_g1(proof + 3 * i, pts[i]);
   fe sc[7] = {a_z, b_z, c_z, s1_z, s2_z, r_z, zw_z};
   memcpy(proof + 27, sc, 7);
+  if (fs) { fs->st = fs_round5(fs->st, proof, fs->ch); fs->known[5] = 1; }
   return 0;
 }
 
@@ -819,13 +846,23 @@ void port_interpolate_at_h(const uint8_t *vals, uint8_t *out, uint8_t *olen, siz
 typedef struct {
   plonk_t pk; circuit_t cs;
   const uint8_t *wit, *rnd, *chal; uint8_t *proofs, *status;
+  int fs_mode; uint32_t fs_seed; uint8_t *chal_out;
 } prove_ctx;
 static void prove_range(void *c, size_t lo, size_t hi) {
   prove_ctx *x = c;
   for (size_t i = lo; i < hi; i++) {
     const uint8_t *w = x->wit + 12 * i;
     uint8_t *o = x->proofs + 34 * i;
-    int st = plonk_prove_(&x->pk, &x->cs, w, w + 4, w + 8, x->chal + 5 * i, x->rnd + 9 * i, o);
+    int st;
+    if (x->fs_mode) {
+      fs_t fs;
+      memset(&fs, 0, sizeof fs);
+      fs.st = x->fs_seed;
+      st = plonk_prove_(&x->pk, &x->cs, w, w + 4, w + 8, NULL, x->rnd + 9 * i, o, &fs);
+      if (x->chal_out) for (int k = 0; k < 6; k++) x->chal_out[6 * i + k] = fs.known[k] ? fs.ch[k] : 0xFF;
+    } else {
+      st = plonk_prove_(&x->pk, &x->cs, w, w + 4, w + 8, x->chal + 5 * i, x->rnd + 9 * i, o, NULL);
+    }
     if (st) memset(o, 0, 34);
     x->status[i] = (uint8_t)st;
   }
@@ -838,8 +875,28 @@ void port_plonk_prove_batch(const uint8_t *circuit, const uint8_t *g1s, uint32_t
   plonk_new_(&c->pk, &s);
   circuit_from(&c->cs, circuit);
   c->wit = wit; c->rnd = rnd; c->chal = chal; c->proofs = proofs; c->status = status;
+  c->fs_mode = 0; c->fs_seed = 0; c->chal_out = NULL;
   run_ranges(prove_range, c, n, nthreads);
   free(c);
+}
+/* Fiat-Shamir mode (spec: fs_spec.inc): chal_out (optional) [n][6] = alpha beta gamma z v u, 0xFF where not drawn */
+void port_plonk_prove_fs_batch(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2b,
+                               const uint8_t *wit, const uint8_t *rnd, size_t n,
+                               uint8_t *proofs, uint8_t *status, uint8_t *chal_out, int nthreads) {
+  prove_ctx *c = malloc(sizeof *c);
+  srs_t s = srs_from(g1s, srs_len, g2b);
+  plonk_new_(&c->pk, &s);
+  circuit_from(&c->cs, circuit);
+  c->wit = wit; c->rnd = rnd; c->chal = NULL; c->proofs = proofs; c->status = status;
+  c->fs_mode = 1; c->fs_seed = fs_seed(circuit, g1s, srs_len, g2b); c->chal_out = chal_out;
+  run_ranges(prove_range, c, n, nthreads);
+  free(c);
+}
+uint32_t port_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2b) {
+  return fs_seed(circuit, g1s, srs_len, g2b);
+}
+void port_fs_derive(uint32_t seed, const uint8_t *proofs, size_t n, uint8_t *chal6) {
+  for (size_t i = 0; i < n; i++) fs_derive(seed, proofs + 34 * i, chal6 + 6 * i);
 }
 
 /* ---------------- verifier (parity unpinned: see verify_spec.inc) over the restated primitives */

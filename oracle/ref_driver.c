@@ -17,7 +17,11 @@
  *                                             malloc would run out of memory on 2^20 items.
  *                                             This makes the CPU baseline FASTER, not slower.
  *   srs_eval_at_s    -> counted wrapper       (only inside plonk.h) so that the four
- *                                             "exceeds SRS size" exits can be told apart
+ *                                             "exceeds SRS size" exits can be told apart; it
+ *                                             also records each commitment, and
+ *   poly_eval        -> logging wrapper       (only inside plonk.h) records each evaluation:
+ *                                             the Fiat-Shamir driver (fs_spec.inc) needs the
+ *                                             commitments and openings of items that exit later
  *
  * Output of this file: oracle/_ref/libref_oracle.so (git-ignored, travels to the GPU box).
  * Role: (1) pins the C restatement in oracle/plonk_port.c, (2) generates tests/golden/,
@@ -45,6 +49,9 @@ typedef struct {
   unsigned line;     /* assert line */
   const char *fmt;   /* last fprintf format string seen (classifies the exit) */
   int commits;       /* srs_eval_at_s calls completed inside plonk_prove */
+  unsigned char commit_bytes[12][3];   /* ... and what they returned (x, y, infinite), for the Fiat-Shamir driver */
+  int n_evals;                         /* poly_eval calls completed inside plonk_prove ... */
+  unsigned char eval_val[32], eval_commits[32];   /* ... their values and the commit count at the time */
   unsigned char *arena;
   size_t arena_off, arena_cap;
 } oracle_tls_t;
@@ -118,12 +125,28 @@ static void oracle_free(void *p) { (void)p; }
 #include "srs.h"
 static G1 oracle_counted_commit(const SRS *srs, const POLY *p) {
   G1 r = srs_eval_at_s(srs, p);
+  if (T.commits < 12) {
+    T.commit_bytes[T.commits][0] = r.x.value;
+    T.commit_bytes[T.commits][1] = r.y.value;
+    T.commit_bytes[T.commits][2] = r.infinite ? 1 : 0;
+  }
   T.commits++;
   return r;
 }
+static HF oracle_logged_eval(const POLY *p, HF x) {
+  HF r = poly_eval(p, x);
+  if (T.n_evals < 32) {
+    T.eval_val[T.n_evals] = r.value;
+    T.eval_commits[T.n_evals] = (unsigned char)T.commits;
+  }
+  T.n_evals++;
+  return r;
+}
 #define srs_eval_at_s(s, p) oracle_counted_commit(s, p)
+#define poly_eval(p, x) oracle_logged_eval(p, x)
 #include "plonk.h"
 #undef srs_eval_at_s
+#undef poly_eval
 #include "pairing.h"
 
 /* ------------------------------------------------------------------ helpers */
@@ -661,6 +684,129 @@ void ref_plonk_prove_batch(const uint8_t *circuit, const uint8_t *g1s, uint32_t 
 #endif
   prove_ctx c = {circuit, g1s, srs_len, g2, wit, rnd, chal, proofs, status};
   run_ranges(prove_range, &c, n, nthreads);
+}
+
+/* --------------------------- Fiat-Shamir mode (spec: fs_spec.inc).
+ * The reference takes its challenges up front, so the transcript is driven from outside: plonk_prove is
+ * run up to five times per item, each pass with the challenges known so far (zero for the rest), and the
+ * commitments / openings it produced on the way are read from the capture hooks above.  Everything a pass
+ * computes before its first not-yet-known challenge is used is what the final run computes, so the
+ * commitments and the exits of the rounds already fixed are final.  The last pass runs the unmodified
+ * prover with the complete challenge set: its PROOF bytes and exit status are the expected output. */
+#include "fs_spec.inc"
+
+typedef struct {
+  const uint8_t *circuit, *g1s; uint32_t srs_len; const uint8_t *g2;
+  const uint8_t *wit, *rnd; uint8_t *proofs, *status, *chal;
+} prove_fs_ctx;
+
+/* one trapped run of the unmodified prover (its own frame, so that nothing the caller changes between passes
+ * lives across the setjmp): returns 1 and the PROOF record in o if it completed, else 0 and the exit status */
+__attribute__((noinline)) static int fs_pass(ref_ctx_t *ctx, ASSIGNMENTS *as, HF *rnd, const uint8_t *ch6, uint8_t *o, uint8_t *status) {
+  CHALLENGE ch;
+  ch.alpha.value = ch6[0]; ch.beta.value = ch6[1]; ch.gamma.value = ch6[2]; ch.z.value = ch6[3]; ch.v.value = ch6[4];
+  T.commits = 0;
+  T.n_evals = 0;
+  volatile int completed = 0;
+  if (TRAP_BEGIN() == 0) {
+    PROOF pr = plonk_prove(&ctx->plonk, &ctx->cons, as, &ch, rnd);
+    G1 *g = &pr.a_s;
+    for (int j = 0; j < 9; j++) g1_to(o + 3 * j, g[j]);
+    HF *s = &pr.a_z;
+    for (int j = 0; j < 7; j++) o[27 + j] = s[j].value;
+    completed = 1;
+  } else {
+    *status = classify_trap();
+  }
+  TRAP_END();
+  return completed;
+}
+
+static void prove_fs_range(void *c, size_t lo, size_t hi) {
+  prove_fs_ctx *x = (prove_fs_ctx *)c;
+  size_t mark0 = arena_mark();
+  ref_ctx_t ctx;
+  ctx_build(&ctx, x->circuit, x->g1s, x->srs_len, x->g2);
+  const uint32_t seed = fs_seed(x->circuit, x->g1s, x->srs_len, x->g2);
+  size_t mark = arena_mark();
+  for (size_t i = lo; i < hi; i++) {
+    HF a[4], b[4], cc[4], rnd[9];
+    for (int j = 0; j < 4; j++) {
+      a[j].value = x->wit[12 * i + j];
+      b[j].value = x->wit[12 * i + 4 + j];
+      cc[j].value = x->wit[12 * i + 8 + j];
+    }
+    for (int j = 0; j < 9; j++) rnd[j].value = x->rnd[9 * i + j];
+    ASSIGNMENTS as; as.a = a; as.b = b; as.c = cc; as.len = 4;
+    uint8_t ch6[6] = {0, 0, 0, 0, 0, 0};
+    uint8_t known[6] = {0, 0, 0, 0, 0, 0};
+    uint8_t rec[34];            /* the transcript's view of the PROOF record, filled stage by stage */
+    uint8_t *o = x->proofs + 34 * i;
+    uint32_t st = seed;
+    int stage = 0;              /* rounds whose challenges are fixed: 0 none, 1 beta/gamma, 2 alpha, 3 z, 4 v */
+    memset(rec, 0, sizeof rec);
+    for (;;) {
+      uint8_t status = 0;
+      const int completed = fs_pass(&ctx, &as, rnd, ch6, o, &status);
+      arena_reset(mark);
+      /* how far is this pass final?  Exits of rounds <= stage+1 depend only on fixed challenges. */
+      static const uint8_t last_status_of_round[5] = {5, 7, 10, 10, 12};   /* rounds 1..5 (round 4 has no exit) */
+      if (stage == 4) {          /* complete challenge set: this is the run */
+        if (completed) {
+          fs_round5(st, o, ch6);
+          known[5] = 1;
+          x->status[i] = 0;
+        } else {
+          memset(o, 0, 34);
+          x->status[i] = status;
+        }
+        break;
+      }
+      if (!completed && status <= last_status_of_round[stage]) {   /* exits before the next challenge is drawn */
+        memset(o, 0, 34);
+        x->status[i] = status;
+        break;
+      }
+      /* advance the transcript by one round from the captured values */
+      if (stage == 0) {
+        memcpy(rec, T.commit_bytes, 9);
+        st = fs_round1(st, rec, ch6); known[1] = known[2] = 1;
+      } else if (stage == 1) {
+        memcpy(rec + 9, T.commit_bytes[3], 3);
+        st = fs_round2(st, rec, ch6); known[0] = 1;
+      } else if (stage == 2) {
+        memcpy(rec + 12, T.commit_bytes[4], 9);
+        st = fs_round3(st, rec, ch6); known[3] = 1;
+      } else {
+        /* the nine poly_eval calls after the seventh commitment: a b c s1 s2 t zw l1 r (plonk.h:527-574) */
+        uint8_t ev[9]; int k = 0;
+        for (int e = 0; e < T.n_evals && e < 32; e++) if (T.eval_commits[e] == 7 && k < 9) ev[k++] = T.eval_val[e];
+        if (k != 9) { fputs("ref_driver: fs: unexpected evaluation count\n", stderr); abort(); }
+        rec[27] = ev[0]; rec[28] = ev[1]; rec[29] = ev[2]; rec[30] = ev[3]; rec[31] = ev[4]; rec[32] = ev[8]; rec[33] = ev[6];
+        st = fs_round4(st, rec, ch6); known[4] = 1;
+      }
+      stage++;
+    }
+    if (x->chal) for (int k = 0; k < 6; k++) x->chal[6 * i + k] = known[k] ? ch6[k] : 0xFF;
+  }
+  ctx_free(&ctx);
+  arena_reset(mark0);
+}
+
+/* Fiat-Shamir plonk_prove over a batch: wit:[n][12], rnd:[n][9] -> proofs:[n][34], status:[n], and (optional)
+ * chal:[n][6] = alpha beta gamma z v u as derived, 0xFF for a challenge the reference exits before drawing. */
+void ref_plonk_prove_fs_batch(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2,
+                              const uint8_t *wit, const uint8_t *rnd, size_t n,
+                              uint8_t *proofs, uint8_t *status, uint8_t *chal, int nthreads) {
+  prove_fs_ctx c = {circuit, g1s, srs_len, g2, wit, rnd, proofs, status, chal};
+  run_ranges(prove_fs_range, &c, n, nthreads);
+}
+uint32_t ref_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2) {
+  return fs_seed(circuit, g1s, srs_len, g2);
+}
+/* the verifier's side of the transcript: all six challenges from complete PROOF records */
+void ref_fs_derive(uint32_t seed, const uint8_t *proofs, size_t n, uint8_t *chal6) {
+  for (size_t i = 0; i < n; i++) fs_derive(seed, proofs + 34 * i, chal6 + 6 * i);
 }
 
 /* --------------------------- verifier: NOT in the reference (plonk.h:656-659).  Parity unpinned.

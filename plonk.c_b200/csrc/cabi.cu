@@ -838,6 +838,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   for (int r = 0; r < 4; r++) for (int col = 0; col < 4; col++) cc.vinv[r][col] = Vinv[r * 4 + col];
   cc.srs_len = srs_len;
   cc.bad_copy = 0;
+  cc.fs_seed = fs_seed_host(circuit, srs_g1s, srs_len, srs_g2);
   // copy_constraints_to_roots (plonk.h:142-160)
   uint8_t rows[9][4];
   for (int s = 0; s < 5; s++) memcpy(rows[s], circuit + 4 * s, 4);
@@ -941,6 +942,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
     c->vkey_bytes[24] = srs_g1s[0]; c->vkey_bytes[25] = srs_g1s[1]; c->vkey_bytes[26] = srs_g1s[2] ? 1 : 0;
     c->vk.g2_one = G2{srs_g2[0], srs_g2[1]};
     c->vk.g2_s = G2{srs_g2[2], srs_g2[3]};
+    c->vk.fs_seed = c->cc.fs_seed;
     // fast-path verifier tables: only when all nine key points are canonically encoded curve points
     uint8_t on[9];
     if ((rc = pb_g1_is_on_curve(c->vkey_bytes, on, 9))) return bail(rc);
@@ -1013,14 +1015,26 @@ int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* o
 }
 
 // prove launch: pair tables when the SRS is canonical, the sequential tables otherwise
+// chal == nullptr selects the Fiat-Shamir instantiation (challenges drawn in the kernel; chal_out optional)
 static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status,
-                        size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict) {
-  if (ctx->srs_canonical && !ctx->force_exact)
-    prove_kernel<ProverPairTables><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, chal, proofs, status, n,
-                                                                           done_list, done_count, verdict);
-  else
-    prove_kernel<ProverTables><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n,
-                                                                       done_list, done_count, verdict);
+                        size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict, uint8_t* chal_out = nullptr) {
+  const bool pair = ctx->srs_canonical && !ctx->force_exact;
+  const unsigned grid = blocks_for(n, BLOCK);
+  if (chal) {
+    if (pair)
+      prove_kernel<ProverPairTables, false><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, chal, proofs, status, n,
+                                                                    done_list, done_count, verdict, nullptr);
+    else
+      prove_kernel<ProverTables, false><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n,
+                                                                done_list, done_count, verdict, nullptr);
+  } else {
+    if (pair)
+      prove_kernel<ProverPairTables, true><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, nullptr, proofs, status, n,
+                                                                   done_list, done_count, verdict, chal_out);
+    else
+      prove_kernel<ProverTables, true><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, nullptr, proofs, status, n,
+                                                               done_list, done_count, verdict, chal_out);
+  }
   LAUNCH_CHECK("prove_kernel");
   return PB_OK;
 }
@@ -1071,12 +1085,13 @@ int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const u
                               uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
   return pb_plonk_prove_verify_ex_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, nullptr);
 }
-int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
-                                 uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
-  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  ARG(u && verdict);
+// chal == u == nullptr: Fiat-Shamir mode
+static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                            uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
+  ARG(verdict);
   ARG(ctx && ctx->vk_valid);
-  ARG(witness && rnd && chal && proofs && status);
+  ARG(witness && rnd && proofs && status);
+  ARG((chal == nullptr) == (u == nullptr));
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
   ARG(n < 0xFFFFFFFFull);
   // The prover appends the indices of the completed proofs to a dense list (stream-ordered scratch), the verifier walks
@@ -1090,6 +1105,41 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, cons
   if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
   if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
   return rc;
+}
+int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                                 uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(chal && u);
+  return prove_verify_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, mid_event);
+}
+
+// ---- Fiat-Shamir mode (transcript.cuh; specification oracle/fs_spec.inc)
+int pb_ctx_fs_seed(const pb_ctx* ctx, uint32_t* out) { ARG(ctx && out); *out = ctx->cc.fs_seed; return PB_OK; }
+int pb_plonk_prove_fs_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status,
+                          uint8_t* chal_out, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && witness && rnd && proofs && status);
+  ARG(aligned16(witness) && aligned16(rnd) && aligned16(proofs) && aligned16(status));
+  return launch_prove(ctx, witness, rnd, nullptr, proofs, status, n, S(stream), nullptr, nullptr, nullptr, chal_out);
+}
+int pb_plonk_verify_fs_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* verdict, uint8_t* gt, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && proofs && verdict);
+  ARG(ctx->vk_valid);
+  ARG(aligned16(proofs) && (!gt || aligned16(gt)));
+  return launch_verify(ctx, proofs, nullptr, nullptr, nullptr, nullptr, nullptr, verdict, gt, n, S(stream));
+}
+int pb_plonk_prove_verify_fs_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status,
+                                 uint8_t* verdict, size_t n, void* stream, void* mid_event) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  return prove_verify_dev(ctx, witness, rnd, nullptr, nullptr, proofs, status, verdict, n, stream, mid_event);
+}
+int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal6, size_t n, void* stream) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && proofs && chal6);
+  fs_challenges_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc.fs_seed, proofs, chal6, n);
+  LAUNCH_CHECK("fs_challenges_kernel");
+  return PB_OK;
 }
 
 // host-pointer versions: a three-stage pipeline over chunks, one stream per hardware engine -- s_in (H2D copy engine),
@@ -1150,8 +1200,8 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     if (reuse) CU(cudaStreamWaitEvent(ctx->s_in, s.ev_k, 0));
     CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, ctx->s_in));
     CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, ctx->s_in));
-    CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, ctx->s_in));
-    if (mode == 1 && c == 0) CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, ctx->s_in));
+    if (chal) CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, ctx->s_in));   // absent in Fiat-Shamir mode
+    if (mode == 1 && c == 0 && u) CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, ctx->s_in));
     CU(cudaEventRecord(s.ev_in, ctx->s_in));
     if (trace) CU(cudaEventRecord(tev[3 * c], ctx->s_in));
     CU(cudaStreamWaitEvent(ctx->s_k, s.ev_in, 0));
@@ -1160,9 +1210,12 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     if (nokernel)
       rc = PB_OK;
     else if (mode == 1)
-      rc = pb_plonk_prove_verify_dev(ctx, s.wit, s.rnd, s.chal, ctx->d_u + done, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, ctx->s_k);
-    else
+      rc = prove_verify_dev(ctx, s.wit, s.rnd, chal ? s.chal : nullptr, u ? ctx->d_u + done : nullptr, s.proofs, ctx->d_status + done,
+                            ctx->d_verdict + done, m, ctx->s_k, nullptr);
+    else if (chal)
       rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, ctx->d_status + done, m, ctx->s_k);
+    else
+      rc = pb_plonk_prove_fs_dev(ctx, s.wit, s.rnd, s.proofs, ctx->d_status + done, nullptr, m, ctx->s_k);
     if (rc) return rc;
     CU(cudaEventRecord(s.ev_k, ctx->s_k));
     if (trace) CU(cudaEventRecord(tev[3 * c + 1], ctx->s_k));
@@ -1201,6 +1254,51 @@ int pb_plonk_prove_verify(const pb_ctx* ctx, const uint8_t* witness, const uint8
   ARG(ctx && witness && rnd && chal && u && proofs && status && verdict);
   ARG(ctx->vk_valid);
   return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, n, 1);
+}
+int pb_plonk_prove_fs(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && witness && rnd && proofs && status);
+  if (!chal_out) return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, nullptr, n, 0);
+  DeviceGuard g(ctx->device);   // with the challenge read-back: one unchunked launch
+  DEV(dw, n * 12); DEV(dr, n * 9); DEV(dp, n * 34); DEV(ds, n); DEV(dc, n * 6);
+  H2D(dw, witness, n * 12); H2D(dr, rnd, n * 9);
+  int rc = pb_plonk_prove_fs_dev(ctx, dw.as<uint8_t>(), dr.as<uint8_t>(), dp.as<uint8_t>(), ds.as<uint8_t>(), dc.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(proofs, dp, n * 34); D2H(status, ds, n); D2H(chal_out, dc, n * 6);
+  return PB_OK;
+}
+int pb_plonk_prove_verify_fs(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status,
+                             uint8_t* verdict, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && witness && rnd && proofs && status && verdict);
+  ARG(ctx->vk_valid);
+  return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, verdict, n, 1);
+}
+int pb_plonk_verify_fs(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* verdict, uint8_t* gt, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && proofs && verdict);
+  DeviceGuard g(ctx->device);
+  DEV(dp, n * 34); DEV(dv, n); DEV(dg, n * 4);
+  H2D(dp, proofs, n * 34);
+  int rc = pb_plonk_verify_fs_dev(ctx, dp.as<uint8_t>(), dv.as<uint8_t>(), gt ? dg.as<uint8_t>() : nullptr, n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(verdict, dv, n);
+  if (gt) D2H(gt, dg, n * 4);
+  return PB_OK;
+}
+int pb_fs_challenges(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal6, size_t n) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && proofs && chal6);
+  DeviceGuard g(ctx->device);
+  DEV(dp, n * 34); DEV(dc, n * 6);
+  H2D(dp, proofs, n * 34);
+  int rc = pb_fs_challenges_dev(ctx, dp.as<uint8_t>(), dc.as<uint8_t>(), n, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  D2H(chal6, dc, n * 6);
+  return PB_OK;
 }
 int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer

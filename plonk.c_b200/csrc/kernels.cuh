@@ -538,12 +538,15 @@ struct __align__(16) ProveSmem {
 #ifndef PB_PROVE_MINBLOCKS
 #define PB_PROVE_MINBLOCKS 5   // 96 registers (44 B of spills), 5 blocks of 128 threads per SM: measured best (profiles/r1/NOTES.md)
 #endif
-template <typename Tables>
+// FS = true (Fiat-Shamir mode, transcript.cuh): `chal` is not read; chal_out (optional) [n][6] receives the challenges
+// drawn before the item's first exit (alpha beta gamma z v u), 0xFF for the ones not drawn.
+template <typename Tables, bool FS = false>
 __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
                                                       const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
                                                       uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
-                                                      uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict) {
+                                                      uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
+                                                      uint8_t* __restrict__ chal_out = nullptr) {
   __shared__ ProveSmem<Tables> sm;
   const int tid = threadIdx.x;
   for (int k = tid; k < (int)(sizeof(Tables) / 4); k += BLOCK)
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
   const size_t first = (size_t)blockIdx.x * BLOCK;
   stage_in<12, BLOCK>(sm.wit, wit, first, n);
   stage_in<9, BLOCK>(sm.rnd, rnd, first, n);
-  stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  if constexpr (!FS) stage_in<5, BLOCK>(sm.chal, chal, first, n);
   __syncthreads();
   const bool live = first + tid < n;
   uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
 #pragma unroll
   for (int k = 0; k < 9; k++) r[k] = sm.rnd[tid * 9 + k];
 #pragma unroll
-  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+  for (int k = 0; k < 5; k++) ch[k] = FS ? 0u : sm.chal[tid * 5 + k];
 #pragma unroll
   for (int k = 0; k < 4; k++) bad |= wa[k] > 16u || wb[k] > 16u || wc[k] > 16u;
 #pragma unroll
@@ -577,8 +580,23 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
     for (int k = 0; k < 5; k++) ch[k] = 0;
   }
   ProofOut o;
-  prove_one(cc, sm.tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+  prove_one<FS>(cc, sm.tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
   if (bad) o.status = 254u;
+  if constexpr (FS) {
+    if (chal_out && live) {
+      // a challenge exists only if the reference's execution reaches the point where it is drawn
+      const uint32_t st = o.status;
+      const bool k1 = st == 0u || (st >= 6u && st <= 12u), k2 = st == 0u || (st >= 8u && st <= 12u);
+      const bool k3 = st == 0u || (st >= 11u && st <= 12u), k5 = st == 0u;
+      uint8_t* co = chal_out + (first + tid) * 6;
+      co[0] = k2 ? (uint8_t)o.ch[0] : 0xFF;
+      co[1] = k1 ? (uint8_t)o.ch[1] : 0xFF;
+      co[2] = k1 ? (uint8_t)o.ch[2] : 0xFF;
+      co[3] = k3 ? (uint8_t)o.ch[3] : 0xFF;
+      co[4] = k3 ? (uint8_t)o.ch[4] : 0xFF;
+      co[5] = k5 ? (uint8_t)o.ch[5] : 0xFF;
+    }
+  }
   uint8_t* po = sm.proof + tid * 34;
   const bool okp = o.status == 0u;     // a failed item's PROOF bytes are zero
 #pragma unroll
@@ -605,6 +623,22 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
   stage_out<1, BLOCK>(status, sm.status, first, n);
 }
 
+// Fiat-Shamir: the six challenges (alpha beta gamma z v u) of each PROOF record, as a verifier derives them
+__global__ void __launch_bounds__(BLOCK_LIGHT) fs_challenges_kernel(uint32_t seed, const uint8_t* __restrict__ proofs,
+                                                                    uint8_t* __restrict__ chal6, size_t n) {
+  const size_t i = (size_t)blockIdx.x * BLOCK_LIGHT + threadIdx.x;
+  if (i >= n) return;
+  uint32_t pbytes[27], op[7], ch[5], u;
+#pragma unroll
+  for (int k = 0; k < 27; k++) pbytes[k] = proofs[i * 34 + k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) op[k] = proofs[i * 34 + 27 + k];
+  fs_derive(seed, pbytes, op, ch, u);
+#pragma unroll
+  for (int k = 0; k < 5; k++) chal6[i * 6 + k] = (uint8_t)ch[k];
+  chal6[i * 6 + 5] = (uint8_t)u;
+}
+
 struct __align__(16) VerifySmem {
   __align__(16) FieldTables ft;
   __align__(16) uint8_t proof[BLOCK * 34];
@@ -620,8 +654,9 @@ __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ V
   const int tid = threadIdx.x;
   build_field_tables(sm.ft);
   const size_t first = (size_t)blockIdx.x * BLOCK;
+  const bool fs = chal == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
   stage_in<34, BLOCK>(sm.proof, proofs, first, n);
-  stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  if (!fs) stage_in<5, BLOCK>(sm.chal, chal, first, n);
   __syncthreads();
   const size_t i = first + tid;
   if (i >= n) return;
@@ -635,10 +670,16 @@ __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ V
   for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
 #pragma unroll
   for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+  uint32_t uu;
+  if (fs) {
+    fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    uu = u[i];
+  }
   VerifyOut o;
-  verify_one(key, sm.ft, pbytes, op, ch, u[i], o);
+  verify_one(key, sm.ft, pbytes, op, ch, uu, o);
   verdict[i] = (uint8_t)o.verdict;
   if (gt) reinterpret_cast<uint32_t*>(gt)[i] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
 }
@@ -668,19 +709,22 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
     reinterpret_cast<uint32_t*>(&sm.vt)[k] = reinterpret_cast<const uint32_t*>(gvt)[k];
   size_t item = first + tid;
   const bool live = item < limit;
+  const bool fs = chal == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
   if (done_list) {
     item = live ? done_list[item] : 0;
     const uint8_t* pr = proofs + item * 34;                               // gather: 34 + 5 contiguous bytes per item
-    const uint8_t* cr = chal + item * 5;
     if (live) {
 #pragma unroll
       for (int k = 0; k < 34; k++) sm.proof[tid * 34 + k] = pr[k];
+      if (!fs) {
+        const uint8_t* cr = chal + item * 5;
 #pragma unroll
-      for (int k = 0; k < 5; k++) sm.chal[tid * 5 + k] = cr[k];
+        for (int k = 0; k < 5; k++) sm.chal[tid * 5 + k] = cr[k];
+      }
     }
   } else {
     stage_in<34, BLOCK>(sm.proof, proofs, first, n);
-    stage_in<5, BLOCK>(sm.chal, chal, first, n);
+    if (!fs) stage_in<5, BLOCK>(sm.chal, chal, first, n);
   }
   __syncthreads();
   if (!live) return;
@@ -689,10 +733,16 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
   for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
 #pragma unroll
   for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+  uint32_t uu;
+  if (fs) {
+    fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    uu = u[item];
+  }
   VerifyOut o;
-  verify_one_fast(key, sm.vt, sm.ft, pbytes, op, ch, u[item], o);
+  verify_one_fast(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
   verdict[item] = (uint8_t)o.verdict;
   if (gt) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
 }

@@ -16,6 +16,7 @@
 // red17 (field.cuh).  Bounds are stated where they matter; all are far below 2^28.
 #pragma once
 #include "curve.cuh"
+#include "transcript.cuh"
 
 namespace pb {
 
@@ -32,6 +33,7 @@ struct CircuitConst {
   uint32_t l1[4];       // L1(x) = interpolate([1,0,0,0])                                 (plonk.h:390-391)
   uint32_t srs_len;     // SRS.len (srs.h:13)
   uint32_t bad_copy;    // a COPY_OF.type outside {A,B,C}: every proof exits at plonk.h:155-157
+  uint32_t fs_seed;     // Fiat-Shamir mode only: initial transcript state (transcript.cuh)
 };
 
 // Tables that are indexed per lane (so they live in shared memory, not in the constant bank).
@@ -136,9 +138,12 @@ struct ProofOut {
   G1 pts[9];        // a b c z t_lo t_mid t_hi W_z W_zw   (PROOF field order, plonk.h:24-41)
   uint32_t sc[7];   // a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z
   uint32_t status;  // SURVEY.md Appendix B row of the first exit that fires, 0 = completed
+  uint32_t ch[6];   // Fiat-Shamir mode only: alpha beta gamma z v u as drawn from the transcript
 };
 
-template <typename Tables>
+// FS = false: the reference's interface, challenges given by the caller (plonk.h:227).
+// FS = true: the five challenge arguments are ignored and drawn from the transcript (transcript.cuh).
+template <bool FS = false, typename Tables>
 PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
                     const uint32_t (&wa)[4], const uint32_t (&wb)[4], const uint32_t (&wc)[4],
                     const uint32_t (&rnd)[9], uint32_t alpha, uint32_t beta, uint32_t gamma,
@@ -170,6 +175,8 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   out.pts[0] = commit(tb, A, len_a);
   out.pts[1] = commit(tb, B, len_b);
   out.pts[2] = commit(tb, C, len_c);
+  Transcript tr{cc.fs_seed};
+  if constexpr (FS) tr.round1(out.pts[0], out.pts[1], out.pts[2], beta, gamma);
 
   // ---- round 2 (plonk.h:320-379): grand-product accumulator.  S_sigma_k evaluated at omega^(i-1)
   // is sigma_k[i-1] (S_sigma_k interpolates sigma_k over H), so no Horner evaluation is needed.
@@ -197,6 +204,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
                    rnd[8], rnd[7], rnd[6]};
   const uint32_t len_z = canon_len(Z);
   out.pts[3] = commit(tb, Z, len_z);
+  if constexpr (FS) tr.round2(out.pts[3], alpha);
 
   // ---- round 3 (plonk.h:385-511): t_numer = t1 + t2 - t3 + t4, all raw, one reduction at the end
   uint32_t tn[22];
@@ -286,6 +294,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   out.pts[4] = commit(tb, tlo, len_lo);
   out.pts[5] = commit(tb, tmid, len_mid);
   out.pts[6] = commit(tb, thi, len_hi);
+  if constexpr (FS) tr.round3(out.pts[4], out.pts[5], out.pts[6], z);
 
   // ---- round 4 (plonk.h:527-574): openings at z and the (non-standard) linearisation r(x)
   uint32_t zp[18];
@@ -320,6 +329,10 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   }
   reduce(R);
   const uint32_t r_z = dot(R, zp);
+  if constexpr (FS) {
+    const uint32_t sc[7] = {a_z, b_z, c_z, s1_z, s2_z, r_z, zw_z};
+    tr.round4(sc, v);
+  }
 
   // ---- round 5 (plonk.h:582-621): opening polynomials
   const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
@@ -351,6 +364,10 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   const uint32_t len_w = umax(len_wz, len_wzw);
   out.pts[7] = commit(tb, Wz, len_wz);
   out.pts[8] = commit(tb, Wzw, len_wzw);
+  if constexpr (FS) {
+    out.ch[0] = alpha; out.ch[1] = beta; out.ch[2] = gamma; out.ch[3] = z; out.ch[4] = v;
+    tr.round5(out.pts[7], out.pts[8], out.ch[5]);
+  }
 
   out.sc[0] = a_z; out.sc[1] = b_z; out.sc[2] = c_z; out.sc[3] = s1_z; out.sc[4] = s2_z;
   out.sc[5] = r_z; out.sc[6] = zw_z;

@@ -14,6 +14,7 @@ struct VerifyKey {
   G1 qm, ql, qr, qo, qc, s1, s2, s3;   // srs_eval_at_s of the interpolated selector / permutation polynomials
   G1 g1_one;                           // srs.g1s[0]
   G2 g2_one, g2_s;                     // srs.g2_1, srs.g2_s
+  uint32_t fs_seed;                    // Fiat-Shamir mode only: initial transcript state (transcript.cuh)
 };
 
 struct VerifyOut {

@@ -103,13 +103,14 @@ class _Call:
         self.keep.append(a)
         return a, a.ctypes.data_as(C.c_void_p)
 
-    def run(self, *args):
+    def run(self, *args, dev_tail=()):
+        """dev_tail: arguments the `_dev` entry point takes after the stream"""
         fn = getattr(lib(), self.name + ("_dev" if self.dev else ""))
         fn.restype = C.c_int
         if self.dev:
             with self.torch.cuda.device(self.device):
                 stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
-                _check(fn(*args, stream))
+                _check(fn(*args, stream, *dev_tail))
         else:
             _check(fn(*args))
 
@@ -461,6 +462,53 @@ class Plonk:
         verdict, pv = c.out((n,))
         c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), pp, ps, pv, C.c_size_t(n))
         return proofs, status, verdict
+
+    # ---- Fiat-Shamir mode (include/plonk_b200.h; specification oracle/fs_spec.inc)
+    def fs_seed(self):
+        out = C.c_uint32()
+        _check(lib().pb_ctx_fs_seed(self._h, C.byref(out)))
+        return int(out.value)
+
+    def prove_fs(self, witness, rnd, want_challenges=False):
+        """-> (proofs[n][34], status[n]) and, on request, chal[n][6] = alpha beta gamma z v u (0xFF where not drawn)."""
+        c = _Call("pb_plonk_prove_fs", witness, rnd)
+        n = _n(witness)
+        proofs, pp = c.out((n, 34))
+        status, ps = c.out((n,))
+        chal, pc = c.out((n, 6)) if want_challenges else (None, None)
+        c.run(self._h, c.inp(witness), c.inp(rnd), pp, ps, pc, C.c_size_t(n))
+        return (proofs, status, chal) if want_challenges else (proofs, status)
+
+    def verify_fs(self, proofs, want_gt=False):
+        c = _Call("pb_plonk_verify_fs", proofs)
+        n = _n(proofs)
+        verdict, pv = c.out((n,))
+        gt, pg = c.out((n, 4)) if want_gt else (None, None)
+        c.run(self._h, c.inp(proofs), pv, pg, C.c_size_t(n))
+        return (verdict, gt) if want_gt else verdict
+
+    def prove_verify_fs(self, witness, rnd):
+        c = _Call("pb_plonk_prove_verify_fs", witness, rnd)
+        n = _n(witness)
+        proofs, pp = c.out((n, 34))
+        status, ps = c.out((n,))
+        verdict, pv = c.out((n,))
+        c.run(self._h, c.inp(witness), c.inp(rnd), pp, ps, pv, C.c_size_t(n), dev_tail=(None,))
+        return proofs, status, verdict
+
+    def prove_verify_fs_into(self, witness, rnd, proofs, status, verdict, mid_event=None):
+        c = _Call("pb_plonk_prove_verify_fs", witness, rnd, proofs, status, verdict)
+        n = _n(witness)
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(proofs), c.inp(status), c.inp(verdict), C.c_size_t(n),
+              dev_tail=(mid_event,))
+
+    def fs_challenges(self, proofs):
+        """the six challenges of each PROOF record as a verifier derives them -> chal[n][6]"""
+        c = _Call("pb_fs_challenges", proofs)
+        n = _n(proofs)
+        chal, pc = c.out((n, 6))
+        c.run(self._h, c.inp(proofs), pc, C.c_size_t(n))
+        return chal
 
     def prove_verify_into(self, witness, rnd, chal, u, proofs, status, verdict):
         """Same with caller-owned buffers (numpy arrays over pinned memory, or torch CUDA tensors): no allocation

@@ -36,6 +36,21 @@ for mode, mk in list(util.SRS_MODES.items()) + [("garbage10", lambda W: util.gar
     out[mode + "_vkey"] = R.verifier_key(C, g1s, g2)
 np.savez_compressed(os.path.join(HERE, "protocol.npz"), **out)
 
+# Fiat-Shamir mode (spec oracle/fs_spec.inc): the unmodified prover driven through the transcript, seed 78
+out = {}
+for mode, mk in list(util.SRS_MODES.items()) + [("garbage10", lambda W: util.garbage_srs())]:
+    g1s, g2 = mk(W)
+    out[mode + "_seed"] = np.array([R.fs_seed(C, g1s, g2)], np.uint32)
+    for var in ("U17", "NZ"):
+        wit, rnd, _, _ = W.make_batch(78, 0, N, var)
+        wit[0], rnd[0] = W.GOLDEN_WITNESS[0], W.GOLDEN_RAND[0]
+        proofs, status, chal = R.plonk_prove_fs_batch(C, g1s, g2, wit, rnd)
+        derived = R.fs_derive(R.fs_seed(C, g1s, g2), proofs)
+        verdict, gt = R.plonk_verify_batch(C, g1s, g2, proofs, np.ascontiguousarray(derived[:, :5]), np.ascontiguousarray(derived[:, 5]))
+        k = f"{mode}_{var}"
+        out[k + "_proofs"], out[k + "_status"], out[k + "_chal"], out[k + "_verdict"], out[k + "_gt"] = proofs, status, chal, verdict, gt
+np.savez_compressed(os.path.join(HERE, "fiat_shamir.npz"), **out)
+
 # groups / pairing
 a, b = util.g1_cases(N)
 s = util.scalars_u64(N)

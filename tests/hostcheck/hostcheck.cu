@@ -19,6 +19,38 @@ static FieldTables make_ft() {
 static G1 ld(const uint8_t* p) { return G1{p[0], p[1], p[2] ? 1u : 0u}; }
 static void st(uint8_t* p, G1 g) { p[0] = (uint8_t)g.x; p[1] = (uint8_t)g.y; p[2] = (uint8_t)g.inf; }
 
+// one batch through prove_one; chal == NULL selects the Fiat-Shamir instantiation, whose chal_out (optional) follows the
+// rule of prove_kernel: a challenge exists only if the reference's execution reaches the point where it is drawn
+template <typename Tables>
+static void prove_batch(const CircuitConst& cc, const Tables& tb, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
+                        uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t wa[4], wb[4], wc[4], r[9];
+    for (int k = 0; k < 4; k++) { wa[k] = wit[12 * i + k]; wb[k] = wit[12 * i + 4 + k]; wc[k] = wit[12 * i + 8 + k]; }
+    for (int k = 0; k < 9; k++) r[k] = rnd[9 * i + k];
+    ProofOut o;
+    if (chal) {
+      const uint8_t* ch = chal + 5 * i;
+      prove_one<false>(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+    } else {
+      prove_one<true>(cc, tb, wa, wb, wc, r, 0u, 0u, 0u, 0u, 0u, o);
+      if (chal_out) {
+        const uint32_t s = o.status;
+        const bool k1 = s == 0u || (s >= 6u && s <= 12u), k2 = s == 0u || (s >= 8u && s <= 12u);
+        const bool k3 = s == 0u || (s >= 11u && s <= 12u), k5 = s == 0u;
+        const bool known[6] = {k2, k1, k1, k3, k3, k5};
+        for (int k = 0; k < 6; k++) chal_out[6 * i + k] = known[k] ? (uint8_t)o.ch[k] : 0xFF;
+      }
+    }
+    uint8_t* po = proofs + 34 * i;
+    memset(po, 0, 34);
+    if (o.status == 0) {
+      for (int j = 0; j < 9; j++) st(po + 3 * j, o.pts[j]);
+      for (int j = 0; j < 7; j++) po[27 + j] = (uint8_t)o.sc[j];
+    }
+    status[i] = (uint8_t)o.status;
+  }
+}
 extern "C" {
 
 void hc_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
@@ -63,34 +95,20 @@ void hc_pairing_f(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, 
   FieldTables ft = make_ft();
   for (size_t i = 0; i < n; i++) { GT f = miller(ft, r, ld(p + 3 * i), G2{q[2 * i], q[2 * i + 1]}); out[2 * i] = (uint8_t)f.a; out[2 * i + 1] = (uint8_t)f.b; }
 }
-// cc: CircuitConst as 86 uint32 (struct order); table: [9][17] packed
+// cc: CircuitConst as uint32 words (struct order); table: [9][17] packed.  chal NULL = Fiat-Shamir mode.
 void hc_prove(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
-              uint8_t* proofs, uint8_t* status, size_t n) {
+              uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
   CircuitConst cc;
   memcpy(&cc, cc_words, sizeof cc);
   ProverTables tb;
   tb.ft = make_ft();
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
   memcpy(tb.T, table, sizeof tb.T);
-  for (size_t i = 0; i < n; i++) {
-    uint32_t wa[4], wb[4], wc[4], r[9];
-    for (int k = 0; k < 4; k++) { wa[k] = wit[12 * i + k]; wb[k] = wit[12 * i + 4 + k]; wc[k] = wit[12 * i + 8 + k]; }
-    for (int k = 0; k < 9; k++) r[k] = rnd[9 * i + k];
-    const uint8_t* ch = chal + 5 * i;
-    ProofOut o;
-    prove_one(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
-    uint8_t* po = proofs + 34 * i;
-    memset(po, 0, 34);
-    if (o.status == 0) {
-      for (int j = 0; j < 9; j++) st(po + 3 * j, o.pts[j]);
-      for (int j = 0; j < 7; j++) po[27 + j] = (uint8_t)o.sc[j];
-    }
-    status[i] = (uint8_t)o.status;
-  }
+  prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
 }
 // fast path: pair tables built from the single-point rows exactly as pair_table_kernel does
 void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
-                    uint8_t* proofs, uint8_t* status, size_t n) {
+                    uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
   CircuitConst cc;
   memcpy(&cc, cc_words, sizeof cc);
   static ProverPairTables tb;
@@ -103,24 +121,22 @@ void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8
     const G1 r = g1_add(tb.ft, p, q);
     tb.T2[j][k % 289u] = pack_g1(r.x, r.y, r.inf);
   }
+  prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
+}
+uint32_t hc_fs_seed(const uint8_t* circuit, const uint8_t* g1s, uint32_t srs_len, const uint8_t* g2) { return fs_seed_host(circuit, g1s, srs_len, g2); }
+void hc_fs_challenges(uint32_t seed, const uint8_t* proofs, uint8_t* chal6, size_t n) {
   for (size_t i = 0; i < n; i++) {
-    uint32_t wa[4], wb[4], wc[4], r[9];
-    for (int k = 0; k < 4; k++) { wa[k] = wit[12 * i + k]; wb[k] = wit[12 * i + 4 + k]; wc[k] = wit[12 * i + 8 + k]; }
-    for (int k = 0; k < 9; k++) r[k] = rnd[9 * i + k];
-    const uint8_t* ch = chal + 5 * i;
-    ProofOut o;
-    prove_one(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
-    uint8_t* po = proofs + 34 * i;
-    memset(po, 0, 34);
-    if (o.status == 0) {
-      for (int j = 0; j < 9; j++) st(po + 3 * j, o.pts[j]);
-      for (int j = 0; j < 7; j++) po[27 + j] = (uint8_t)o.sc[j];
-    }
-    status[i] = (uint8_t)o.status;
+    uint32_t pbv[27], op[7], ch[5], u;
+    for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
+    for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
+    fs_derive(seed, pbv, op, ch, u);
+    for (int j = 0; j < 5; j++) chal6[6 * i + j] = (uint8_t)ch[j];
+    chal6[6 * i + 5] = (uint8_t)u;
   }
 }
 // fast-path verifier: tables built exactly as verify_tables_kernel does, from g1_mul rows of the nine key points
-void hc_verify_fast(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+// chal NULL = Fiat-Shamir mode (challenges and u from the proof bytes, transcript seeded with fs_seed)
+void hc_verify_fast(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   FieldTables ft = make_ft();
   VerifyKey k;
   G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
@@ -145,16 +161,18 @@ void hc_verify_fast(const uint8_t* key, const uint8_t* proofs, const uint8_t* ch
     uint32_t pbv[27], op[7], ch[5];
     for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
     for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
-    for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j];
+    uint32_t uu;
+    if (chal) { for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j]; uu = u[i]; }
+    else fs_derive(fs_seed, pbv, op, ch, uu);
     VerifyOut o;
-    verify_one_fast(k, vt, ft, pbv, op, ch, u[i], o);
+    verify_one_fast(k, vt, ft, pbv, op, ch, uu, o);
     verdict[i] = (uint8_t)o.verdict;
     if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
   }
 }
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]
-void hc_verify(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+void hc_verify(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   FieldTables ft = make_ft();
   VerifyKey k;
   G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
@@ -165,9 +183,11 @@ void hc_verify(const uint8_t* key, const uint8_t* proofs, const uint8_t* chal, c
     uint32_t pbv[27], op[7], ch[5];
     for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
     for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
-    for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j];
+    uint32_t uu;
+    if (chal) { for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j]; uu = u[i]; }
+    else fs_derive(fs_seed, pbv, op, ch, uu);
     VerifyOut o;
-    verify_one(k, ft, pbv, op, ch, u[i], o);
+    verify_one(k, ft, pbv, op, ch, uu, o);
     verdict[i] = (uint8_t)o.verdict;
     if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
   }

@@ -131,6 +131,22 @@ class GpuImpl:
     def plonk_verify_batch(self, circuit, g1s, g2, proofs, chal, u, nthreads=1, want_gt=True):
         return self._out(self.ctx(circuit, g1s, g2).verify(self._in(proofs), self._in(chal), self._in(u), want_gt=True))
 
+    # Fiat-Shamir mode
+    def plonk_prove_fs_batch(self, circuit, g1s, g2, wit, rnd, nthreads=1):
+        return self._out(self.ctx(circuit, g1s, g2).prove_fs(self._in(wit), self._in(rnd), want_challenges=True))
+
+    def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
+        return self._out(self.ctx(circuit, g1s, g2).verify_fs(self._in(proofs), want_gt=True))
+
+    def plonk_prove_verify_fs_batch(self, circuit, g1s, g2, wit, rnd):
+        return self._out(self.ctx(circuit, g1s, g2).prove_verify_fs(self._in(wit), self._in(rnd)))
+
+    def fs_seed(self, circuit, g1s, g2):
+        return self.ctx(circuit, g1s, g2).fs_seed()
+
+    def fs_challenges(self, circuit, g1s, g2, proofs):
+        return self._out(self.ctx(circuit, g1s, g2).fs_challenges(self._in(proofs)))
+
 
 def DEFAULT_CIRCUIT():
     from plonk_c_b200 import workload as W
@@ -216,7 +232,18 @@ class HostcheckImpl:
         self.lib.hc_pairing_f(C.c_uint64(r), _p(p), _p(q), _p(out), C.c_size_t(p.shape[0]))
         return out
 
-    def _cc_words(self, circuit, srs_len):
+    def fs_seed(self, circuit, g1s, g2):
+        circuit, g1s, g2 = (np.ascontiguousarray(x, np.uint8) for x in (circuit, g1s, g2))
+        self.lib.hc_fs_seed.restype = C.c_uint32
+        return int(self.lib.hc_fs_seed(_p(circuit), _p(g1s), C.c_uint32(g1s.shape[0]), _p(g2)))
+
+    def fs_challenges(self, circuit, g1s, g2, proofs):
+        proofs = np.ascontiguousarray(proofs, np.uint8)
+        out = np.zeros((proofs.shape[0], 6), np.uint8)
+        self.lib.hc_fs_challenges(C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), _p(out), C.c_size_t(proofs.shape[0]))
+        return out
+
+    def _cc_words(self, circuit, srs_len, fs_seed=0):
         o = self.o
         circuit = np.asarray(circuit, np.uint8)
         qv = circuit[:20].reshape(5, 4)
@@ -225,7 +252,7 @@ class HostcheckImpl:
         SP, _ = o.interpolate_at_h(sig)
         vinv = o.plonk_setup_dump()["h_pows_inv"]
         l1, _ = o.interpolate_at_h(np.array([[1, 0, 0, 0]], np.uint8))
-        w = np.concatenate([qv.ravel(), QP.ravel(), sig.ravel(), SP.ravel(), vinv.ravel(), l1.ravel(), [srs_len, 0]]).astype(np.uint32)
+        w = np.concatenate([qv.ravel(), QP.ravel(), sig.ravel(), SP.ravel(), vinv.ravel(), l1.ravel(), [srs_len, 0, fs_seed]]).astype(np.uint32)
         assert w.size * 4 == self.lib.hc_sizeof_cc()
         return np.ascontiguousarray(w)
 
@@ -246,13 +273,32 @@ class HostcheckImpl:
         n = wit.shape[0]
         proofs, status = np.zeros((n, 34), np.uint8), np.zeros(n, np.uint8)
         (self.lib.hc_prove_pairs if self.fast else self.lib.hc_prove)(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), _p(chal),
-                          _p(proofs), _p(status), C.c_size_t(n))
+                          _p(proofs), _p(status), None, C.c_size_t(n))
         return proofs, status
+
+    def plonk_prove_fs_batch(self, circuit, g1s, g2, wit, rnd, nthreads=1):
+        g1s = np.ascontiguousarray(g1s, np.uint8)
+        ccw, tb = self._cc_words(circuit, g1s.shape[0], self.fs_seed(circuit, g1s, g2)), self._table(g1s)
+        wit, rnd = (np.ascontiguousarray(x, np.uint8) for x in (wit, rnd))
+        n = wit.shape[0]
+        proofs, status, chal = np.zeros((n, 34), np.uint8), np.zeros(n, np.uint8), np.zeros((n, 6), np.uint8)
+        (self.lib.hc_prove_pairs if self.fast else self.lib.hc_prove)(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), None,
+                          _p(proofs), _p(status), _p(chal), C.c_size_t(n))
+        return proofs, status, chal
 
     def plonk_verify_batch(self, circuit, g1s, g2, proofs, chal, u, nthreads=1, want_gt=True):
         key = np.concatenate([self.o.verifier_key(circuit, g1s, g2).ravel(), np.asarray(g2, np.uint8)]).astype(np.uint8)
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        return verdict, gt
+
+    def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
+        key = np.concatenate([self.o.verifier_key(circuit, g1s, g2).ravel(), np.asarray(g2, np.uint8)]).astype(np.uint8)
+        proofs = np.ascontiguousarray(proofs, np.uint8)
+        n = proofs.shape[0]
+        verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
+        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), None, None,
+                                                                      _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt

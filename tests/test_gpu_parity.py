@@ -87,6 +87,30 @@ def test_protocol_golden(dev, hostpath, W):
     ps.check_protocol_golden(hostpath, W)
 
 
+def test_fiat_shamir(dev, oracle, W):
+    """Fiat-Shamir mode: the transcript-driven prover and verifier kernels against
+    oracle/fs_spec.inc, every SRS mode (fast and exact table paths)."""
+    ps.check_fiat_shamir(dev, oracle, W, n=20000)
+
+
+def test_fiat_shamir_host_path(hostpath, oracle, W):
+    ps.check_fiat_shamir(hostpath, oracle, W, n=70000, modes=[("generator9", lambda W: W.generator_srs(9)), ("identity6", lambda W: W.identity_srs(6))])
+
+
+def test_fiat_shamir_golden(dev, hostpath, W):
+    ps.check_fiat_shamir_golden(dev, W)
+    ps.check_fiat_shamir_golden(hostpath, W)
+
+
+def test_fiat_shamir_exact_path_forced(host, oracle, W):
+    import os
+    os.environ["PB_FORCE_EXACT"] = "1"
+    try:
+        ps.check_fiat_shamir(GpuImpl(host, "device"), oracle, W, n=20000, modes=[("generator9", lambda W: W.generator_srs(9))])
+    finally:
+        del os.environ["PB_FORCE_EXACT"]
+
+
 def test_setup_constants(host, oracle, W):
     """plonk_new + the witness-independent part of plonk_prove, as computed by the context's setup kernels."""
     for mk in (W.identity_srs, W.generator_srs):

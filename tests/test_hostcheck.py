@@ -44,6 +44,14 @@ def test_hostcheck_fast_paths(oracle, W):
     ps.check_golden_transcript(hcf, W)
 
 
+def test_hostcheck_fiat_shamir(oracle, W):
+    """Fiat-Shamir mode of prove_one / the verifier kernels' challenge derivation (transcript.cuh) against oracle/fs_spec.inc"""
+    import util
+    ps.check_fiat_shamir(HostcheckImpl(oracle), oracle, W, n=6000)
+    ps.check_fiat_shamir(HostcheckImpl(oracle, fast=True), oracle, W, n=6000, modes=[(m, f) for m, f in util.SRS_MODES.items()])
+    ps.check_fiat_shamir_golden(HostcheckImpl(oracle), W)
+
+
 def test_hostcheck_random_circuits(oracle, W):
     ps.check_random_circuits(HostcheckImpl(oracle), oracle, W, n=2000, circuits=6)
     ps.check_random_circuits(HostcheckImpl(oracle, fast=True), oracle, W, n=2000, circuits=6)
