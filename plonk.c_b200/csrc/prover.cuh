@@ -240,6 +240,26 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   uint32_t Zw[7];                   // z(omega x), plonk.h:466-470
 #pragma unroll
   for (int i = 0; i < 7; i++) Zw[i] = red17(Z[i] * OMEGA_POW[i]);
+  // The second opening polynomial W_zw = (z(x) - z(omega z)) / (x - z omega) (plonk.h:612-617, 621) needs only z(x) and
+  // the evaluation point.  With caller-supplied challenges it is computed and committed HERE, so that its addition
+  // chain overlaps the polynomial products of round 3; in Fiat-Shamir mode z exists only after round 3.
+  uint32_t zw_z = 0u, len_wzw = 0u;
+  bool bad_rem2 = false;
+  auto open_zw = [&]() {
+    uint32_t zq[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) zq[i] = tb.pow17[z][i];
+    zw_z = dot(Zw, zq);
+    const uint32_t zo = red17(z * 4u);
+    uint32_t Wzw[6];
+    Wzw[5] = Z[6];
+#pragma unroll
+    for (int j = 5; j >= 1; j--) Wzw[j - 1] = red17(Z[j] + zo * Wzw[j]);
+    bad_rem2 = red17(Z[0] + 17u - zw_z + zo * Wzw[0]) != 0u;
+    len_wzw = canon_len(Wzw);
+    out.pts[8] = commit(tb, Wzw, len_wzw);
+  };
+  if constexpr (!FS) open_zw();
   {  // t3 = alpha (a + beta S1 + gamma)(b + beta S2 + gamma)(c + beta S3 + gamma) z(omega x)
     uint32_t ya[6], yb[6], yc[6];
 #pragma unroll
@@ -294,7 +314,10 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   out.pts[4] = commit(tb, tlo, len_lo);
   out.pts[5] = commit(tb, tmid, len_mid);
   out.pts[6] = commit(tb, thi, len_hi);
-  if constexpr (FS) tr.round3(out.pts[4], out.pts[5], out.pts[6], z);
+  if constexpr (FS) {
+    tr.round3(out.pts[4], out.pts[5], out.pts[6], z);
+    open_zw();
+  }
 
   // ---- round 4 (plonk.h:527-574): openings at z and the (non-standard) linearisation r(x)
   uint32_t zp[18];
@@ -302,7 +325,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   for (int i = 0; i < 18; i++) zp[i] = tb.pow17[z][i];
   const uint32_t a_z = dot(A, zp), b_z = dot(B, zp), c_z = dot(C, zp);
   const uint32_t s1_z = dot(cc.SP[0], zp), s2_z = dot(cc.SP[1], zp);
-  const uint32_t t_z = dot(T, zp), zw_z = dot(Zw, zp), l1_z = dot(cc.l1, zp);
+  const uint32_t t_z = dot(T, zp), l1_z = dot(cc.l1, zp);
   const uint32_t a2 = red17(alpha * alpha);
   const uint32_t bz = red17(beta * z);
   const uint32_t e_a = red17(a_z + bz + gamma);
@@ -353,17 +376,9 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
 #pragma unroll
   for (int j = 8; j >= 1; j--) Wz[j - 1] = red17(wn[j] + z * Wz[j]);
   const bool bad_rem1 = red17(wn[0] + z * Wz[0]) != 0u;
-  // (z(x) - z_omega_z) / (x - z omega)                                                  (plonk.h:612-617)
-  const uint32_t zo = red17(z * 4u);
-  uint32_t Wzw[6];
-  Wzw[5] = Z[6];
-#pragma unroll
-  for (int j = 5; j >= 1; j--) Wzw[j - 1] = red17(Z[j] + zo * Wzw[j]);
-  const bool bad_rem2 = red17(Z[0] + 17u - zw_z + zo * Wzw[0]) != 0u;
-  const uint32_t len_wz = canon_len(Wz), len_wzw = canon_len(Wzw);
+  const uint32_t len_wz = canon_len(Wz);
   const uint32_t len_w = umax(len_wz, len_wzw);
   out.pts[7] = commit(tb, Wz, len_wz);
-  out.pts[8] = commit(tb, Wzw, len_wzw);
   if constexpr (FS) {
     out.ch[0] = alpha; out.ch[1] = beta; out.ch[2] = gamma; out.ch[3] = z; out.ch[4] = v;
     tr.round5(out.pts[7], out.pts[8], out.ch[5]);
