@@ -93,6 +93,8 @@ struct pb_ctx {
   bool vk_valid = true;               // false when a selector polynomial is longer than the SRS
   ProverTables* d_tables = nullptr;   // device: exact sequential path (any SRS)
   ProverPairTables* d_pair_tables = nullptr;   // device: fast path, only when srs_canonical
+  ProverWideTables* d_wide_tables = nullptr;   // device: widest fast path (48 MB look-up table), only when srs_canonical and not PB_WIDE_TABLES=0
+  uint16_t* d_wide_store = nullptr;            // 3 * 17^3 + 17^6 packed points behind d_wide_tables
   VerifyTables* d_verify_tables = nullptr;     // device: fast path, only when key_canonical
   bool srs_canonical = false;         // every SRS point is a canonically encoded point of E(F_101)
   bool key_canonical = false;         // same for the nine verifier-key points
@@ -909,6 +911,30 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
       if (e3 != cudaSuccess) return bail(cuda_fail(e3, "pair_table_kernel"));
       if (cudaMalloc(&c->d_pair_tables, sizeof ppt) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
       cudaMemcpy(c->d_pair_tables, &ppt, sizeof ppt, cudaMemcpyHostToDevice);
+      const char* ew = getenv("PB_WIDE_TABLES");
+      if (!(ew && ew[0] == '0')) {
+        // one-look-up commitments: T3 for SRS rows 0-2 / 3-5 / 6-8, then T6 = T3[0] (+) T3[1]  (prover.cuh)
+        const size_t n16 = 3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES;
+        uint32_t* d_single2 = nullptr;
+        if (cudaMalloc(&c->d_wide_store, n16 * sizeof(uint16_t)) != cudaSuccess || cudaMalloc(&d_single2, sizeof pt.T) != cudaSuccess ||
+            cudaMalloc(&c->d_wide_tables, sizeof(ProverWideTables)) != cudaSuccess)
+          return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+        cudaMemcpy(d_single2, pt.T, sizeof pt.T, cudaMemcpyHostToDevice);
+        uint16_t* t3 = c->d_wide_store;
+        uint16_t* t6 = c->d_wide_store + 3u * (size_t)WIDE_T3_ENTRIES;
+        wide_t3_kernel<<<58, 256>>>(d_single2, PROVER_SRS_ROWS, t3);
+        wide_t6_kernel<<<148 * 8, 256>>>(t3, t6);
+        cudaError_t e5 = cudaDeviceSynchronize();
+        cudaFree(d_single2);
+        if (e5 != cudaSuccess) return bail(cuda_fail(e5, "wide_t6_kernel"));
+        ProverWideTables wt;
+        memset(&wt, 0, sizeof wt);
+        wt.ft = pt.ft;
+        memcpy(wt.pow17, pt.pow17, sizeof wt.pow17);
+        wt.T6 = t6;
+        wt.T3 = t3 + 2u * (size_t)WIDE_T3_ENTRIES;
+        cudaMemcpy(c->d_wide_tables, &wt, sizeof wt, cudaMemcpyHostToDevice);
+      }
     }
   }
   std::vector<uint32_t> tab(rows_full * 17);
@@ -974,6 +1000,8 @@ int pb_ctx_destroy(pb_ctx* c) {
   DeviceGuard g(c->device);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_pair_tables) cudaFree(c->d_pair_tables);
+  if (c->d_wide_tables) cudaFree(c->d_wide_tables);
+  if (c->d_wide_store) cudaFree(c->d_wide_store);
   for (auto& kv : c->scratch) if (kv.second.first) cudaFree(kv.second.first);
   if (c->d_verify_tables) cudaFree(c->d_verify_tables);
   if (c->d_srs_table) cudaFree(c->d_srs_table);
@@ -1019,22 +1047,20 @@ int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* o
 static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status,
                         size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict, uint8_t* chal_out = nullptr) {
   const bool pair = ctx->srs_canonical && !ctx->force_exact;
-  const unsigned grid = blocks_for(n, BLOCK);
+  const bool wide = pair && ctx->d_wide_tables != nullptr;
+  const unsigned grid = blocks_for(n, PBLOCK);
+#define PB_LAUNCH_PROVE(TABLES, FSMODE, TB, CH, CO) \
+  prove_kernel<TABLES, FSMODE><<<grid, PBLOCK, 0, st>>>(ctx->cc, TB, witness, rnd, CH, proofs, status, n, done_list, done_count, verdict, CO)
   if (chal) {
-    if (pair)
-      prove_kernel<ProverPairTables, false><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, chal, proofs, status, n,
-                                                                    done_list, done_count, verdict, nullptr);
-    else
-      prove_kernel<ProverTables, false><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, chal, proofs, status, n,
-                                                                done_list, done_count, verdict, nullptr);
+    if (wide) PB_LAUNCH_PROVE(ProverWideTables, false, ctx->d_wide_tables, chal, nullptr);
+    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, false, ctx->d_pair_tables, chal, nullptr);
+    else PB_LAUNCH_PROVE(ProverTables, false, ctx->d_tables, chal, nullptr);
   } else {
-    if (pair)
-      prove_kernel<ProverPairTables, true><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_pair_tables, witness, rnd, nullptr, proofs, status, n,
-                                                                   done_list, done_count, verdict, chal_out);
-    else
-      prove_kernel<ProverTables, true><<<grid, BLOCK, 0, st>>>(ctx->cc, ctx->d_tables, witness, rnd, nullptr, proofs, status, n,
-                                                               done_list, done_count, verdict, chal_out);
+    if (wide) PB_LAUNCH_PROVE(ProverWideTables, true, ctx->d_wide_tables, nullptr, chal_out);
+    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, true, ctx->d_pair_tables, nullptr, chal_out);
+    else PB_LAUNCH_PROVE(ProverTables, true, ctx->d_tables, nullptr, chal_out);
   }
+#undef PB_LAUNCH_PROVE
   LAUNCH_CHECK("prove_kernel");
   return PB_OK;
 }

@@ -522,14 +522,18 @@ PB_D void stage_out(uint8_t* __restrict__ g, const uint8_t* smem, size_t first, 
   for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) dst[k] = smem[k];
 }
 
+#ifndef PB_PROVE_BLOCK
+#define PB_PROVE_BLOCK PB_BLOCK
+#endif
+constexpr int PBLOCK = PB_PROVE_BLOCK;   // threads per block of the prover (a multiple of 16: the staging copies move 16-byte pieces)
 template <typename Tables>
 struct __align__(16) ProveSmem {
   __align__(16) Tables tb;
-  __align__(16) uint8_t wit[BLOCK * 12];
-  __align__(16) uint8_t rnd[BLOCK * 9];
-  __align__(16) uint8_t chal[BLOCK * 5];
-  __align__(16) uint8_t proof[BLOCK * 34];
-  __align__(16) uint8_t status[BLOCK];
+  __align__(16) uint8_t wit[PBLOCK * 12];
+  __align__(16) uint8_t rnd[PBLOCK * 9];
+  __align__(16) uint8_t chal[PBLOCK * 5];
+  __align__(16) uint8_t proof[PBLOCK * 34];
+  __align__(16) uint8_t status[PBLOCK];
 };
 
 // Tables = ProverTables (any SRS, the reference's order of additions) or ProverPairTables (canonical on-curve SRS).
@@ -541,7 +545,7 @@ struct __align__(16) ProveSmem {
 // FS = true (Fiat-Shamir mode, transcript.cuh): `chal` is not read; chal_out (optional) [n][6] receives the challenges
 // drawn before the item's first exit (alpha beta gamma z v u), 0xFF for the ones not drawn.
 template <typename Tables, bool FS = false>
-__global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
+__global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
                                                       const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
                                                       uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
@@ -549,12 +553,12 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
                                                       uint8_t* __restrict__ chal_out = nullptr) {
   __shared__ ProveSmem<Tables> sm;
   const int tid = threadIdx.x;
-  for (int k = tid; k < (int)(sizeof(Tables) / 4); k += BLOCK)
+  for (int k = tid; k < (int)(sizeof(Tables) / 4); k += PBLOCK)
     reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
-  const size_t first = (size_t)blockIdx.x * BLOCK;
-  stage_in<12, BLOCK>(sm.wit, wit, first, n);
-  stage_in<9, BLOCK>(sm.rnd, rnd, first, n);
-  if constexpr (!FS) stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  const size_t first = (size_t)blockIdx.x * PBLOCK;
+  stage_in<12, PBLOCK>(sm.wit, wit, first, n);
+  stage_in<9, PBLOCK>(sm.rnd, rnd, first, n);
+  if constexpr (!FS) stage_in<5, PBLOCK>(sm.chal, chal, first, n);
   __syncthreads();
   const bool live = first + tid < n;
   uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
@@ -619,8 +623,8 @@ __global__ void __launch_bounds__(BLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const 
     if (live && !okp && verdict) verdict[first + tid] = 0xFF;
   }
   __syncthreads();
-  stage_out<34, BLOCK>(proofs, sm.proof, first, n);
-  stage_out<1, BLOCK>(status, sm.status, first, n);
+  stage_out<34, PBLOCK>(proofs, sm.proof, first, n);
+  stage_out<1, PBLOCK>(status, sm.status, first, n);
 }
 
 // Fiat-Shamir: the six challenges (alpha beta gamma z v u) of each PROOF record, as a verifier derives them
@@ -774,6 +778,35 @@ __global__ void pair_table_kernel(const uint32_t* __restrict__ T, uint32_t rows,
     const G1 q = 2 * j + 1 < rows ? unpack_g1(T[(2 * j + 1) * 17 + c1]) : g1_identity();
     const G1 r = g1_add(ft, p, q);
     out[k] = pack_g1(r.x, r.y, r.inf);
+  }
+}
+
+// wide tables, step 1: T3[t][c0 + 17 c1 + 289 c2] = (T[3t][c0] + T[3t+1][c1]) + T[3t+2][c2], t = 0..2, 16-bit packed
+__global__ void wide_t3_kernel(const uint32_t* __restrict__ T, uint32_t rows, uint16_t* __restrict__ out /*[3][17^3]*/) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < 3u * WIDE_T3_ENTRIES; k += gridDim.x * blockDim.x) {
+    const uint32_t t = k / WIDE_T3_ENTRIES, e = k % WIDE_T3_ENTRIES;
+    const uint32_t c[3] = {e % 17u, (e / 17u) % 17u, e / 289u};
+    G1 acc = g1_identity();
+#pragma unroll
+    for (uint32_t i = 0; i < 3; i++) {
+      const uint32_t row = 3u * t + i;
+      acc = g1_add(ft, acc, row < rows ? unpack_g1(T[row * 17u + c[i]]) : g1_identity());
+    }
+    out[k] = (uint16_t)pack_g1_16(acc);
+  }
+}
+// step 2: T6[i + 17^3 j] = T3[0][i] + T3[1][j]
+__global__ void wide_t6_kernel(const uint16_t* __restrict__ T3, uint16_t* __restrict__ T6) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < WIDE_T6_ENTRIES; k += gridDim.x * blockDim.x) {
+    const uint32_t i = k % WIDE_T3_ENTRIES, j = k / WIDE_T3_ENTRIES;
+    const G1 r = g1_add(ft, unpack_g1_16(T3[i]), unpack_g1_16(T3[WIDE_T3_ENTRIES + j]));
+    T6[k] = (uint16_t)pack_g1_16(r);
   }
 }
 

@@ -59,6 +59,31 @@ struct ProverPairTables {
   uint32_t T2[PROVER_PAIR_ROWS][289];
 };
 
+// Widest fast path (same eligibility and the same exactness argument as the pair tables): the commitment of a polynomial
+// of up to six coefficients is ONE look-up.  T6[c0 + 17 c1 + ... + 17^5 c5] = sum_{i<6} c_i * g1s[i] has 17^6 entries of
+// 16 bits (x | y << 7 | infinite << 14: coordinates are < 101) = 48 MB in global memory, built on the device at context
+// creation from the single-point rows with the reference's own g1_add.  It fits in the 126 MB L2, and every sector of it
+// is hit ~12 times per 2^21-proof launch, so the gathers are L2 hits.  T3 covers SRS rows 6..8 the same way (4913
+// entries) for the two longer polynomials z(x) (7 coefficients) and W_z (up to 9): one look-up each and ONE g1_add.
+// 2 additions per proof instead of 21.
+constexpr uint32_t WIDE_T3_ENTRIES = 17u * 17u * 17u;
+constexpr uint32_t WIDE_T6_ENTRIES = WIDE_T3_ENTRIES * WIDE_T3_ENTRIES;
+struct ProverWideTables {
+  FieldTables ft;
+  uint8_t pow17[17][20];
+  const uint16_t* T6;   // [17^6], rows 0..5
+  const uint16_t* T3;   // [17^3], rows 6..8
+};
+PB_HD uint32_t pack_g1_16(const G1& p) { return p.x | p.y << 7 | p.inf << 14; }
+PB_HD G1 unpack_g1_16(uint32_t w) { return G1{w & 0x7Fu, (w >> 7) & 0x7Fu, w >> 14}; }
+PB_HD uint32_t wide_load(const uint16_t* t, uint32_t idx) {
+#ifdef __CUDA_ARCH__
+  return __ldg(t + idx);
+#else
+  return t[idx];
+#endif
+}
+
 PB_HD G1 unpack_g1(uint32_t w) { return G1{w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 1u}; }
 PB_HD uint32_t pack_g1(uint32_t x, uint32_t y, uint32_t inf) { return x | (y << 8) | (inf << 16); }
 
@@ -130,6 +155,23 @@ PB_HD G1 commit(const ProverPairTables& tb, const uint32_t (&c)[N], uint32_t /*l
   for (int j = 1; j < (N + 1) / 2; j++) {
     const uint32_t idx = c[2 * j] * 17u + (2 * j + 1 < N ? c[2 * j + 1] : 0u);
     acc = g1_add(tb.ft, acc, unpack_g1(tb.T2[j][idx]));
+  }
+  return acc;
+}
+
+template <int N>
+PB_HD G1 commit(const ProverWideTables& tb, const uint32_t (&c)[N], uint32_t /*len: zero coefficients are no-ops here*/) {
+  static_assert(N >= 1 && N <= PROVER_SRS_ROWS, "prover polynomial shape");
+  constexpr int LO = N < 6 ? N : 6;
+  uint32_t idx = c[LO - 1];
+#pragma unroll
+  for (int i = LO - 2; i >= 0; i--) idx = idx * 17u + c[i];
+  G1 acc = unpack_g1_16(wide_load(tb.T6, idx));
+  if constexpr (N > 6) {
+    uint32_t hi = c[N - 1];
+#pragma unroll
+    for (int i = N - 2; i >= 6; i--) hi = hi * 17u + c[i];
+    acc = g1_add(tb.ft, acc, unpack_g1_16(wide_load(tb.T3, hi)));
   }
   return acc;
 }

@@ -2,6 +2,7 @@
 // (field.cuh, curve.cuh, prover.cuh, verifier.cuh) for the HOST, so that the exact code the GPU runs
 // can be diffed against the oracle in this GPU-less container.  Never linked into the product library and
 // never used as a fallback: libplonk_b200.so has no host execution path.
+#include <vector>
 #include <cstdint>
 #include <cstring>
 #include "../../plonk.c_b200/csrc/prover.cuh"
@@ -121,6 +122,39 @@ void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8
     const G1 r = g1_add(tb.ft, p, q);
     tb.T2[j][k % 289u] = pack_g1(r.x, r.y, r.inf);
   }
+  prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
+}
+// widest fast path: T3 / T6 built exactly as wide_t3_kernel / wide_t6_kernel do (cached per single-point table)
+void hc_prove_wide(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
+                   uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
+  CircuitConst cc;
+  memcpy(&cc, cc_words, sizeof cc);
+  static std::vector<uint16_t> store;
+  static uint32_t cached[PROVER_SRS_ROWS * 17];
+  static bool have = false;
+  const FieldTables ft = make_ft();
+  if (!have || memcmp(cached, table, sizeof cached) != 0) {
+    store.assign(3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES, 0);
+    for (uint32_t k = 0; k < 3u * WIDE_T3_ENTRIES; k++) {
+      const uint32_t t = k / WIDE_T3_ENTRIES, e = k % WIDE_T3_ENTRIES;
+      const uint32_t c[3] = {e % 17u, (e / 17u) % 17u, e / 289u};
+      G1 acc = g1_identity();
+      for (uint32_t i = 0; i < 3; i++) acc = g1_add(ft, acc, unpack_g1(table[(3u * t + i) * 17u + c[i]]));
+      store[k] = (uint16_t)pack_g1_16(acc);
+    }
+    uint16_t* t6 = store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
+    for (uint32_t k = 0; k < WIDE_T6_ENTRIES; k++) {
+      const G1 r = g1_add(ft, unpack_g1_16(store[k % WIDE_T3_ENTRIES]), unpack_g1_16(store[WIDE_T3_ENTRIES + k / WIDE_T3_ENTRIES]));
+      t6[k] = (uint16_t)pack_g1_16(r);
+    }
+    memcpy(cached, table, sizeof cached);
+    have = true;
+  }
+  ProverWideTables tb;
+  tb.ft = ft;
+  for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
+  tb.T6 = store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
+  tb.T3 = store.data() + 2u * (size_t)WIDE_T3_ENTRIES;
   prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
 }
 uint32_t hc_fs_seed(const uint8_t* circuit, const uint8_t* g1s, uint32_t srs_len, const uint8_t* g2) { return fs_seed_host(circuit, g1s, srs_len, g2); }

@@ -243,6 +243,10 @@ class HostcheckImpl:
         self.lib.hc_fs_challenges(C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), _p(out), C.c_size_t(proofs.shape[0]))
         return out
 
+    def _prove_fn(self):
+        # fast: False = sequential tables (any SRS); True = pair tables; "wide" = one-look-up T6 tables (prover only)
+        return {False: self.lib.hc_prove, True: self.lib.hc_prove_pairs, "wide": self.lib.hc_prove_wide}[self.fast]
+
     def _cc_words(self, circuit, srs_len, fs_seed=0):
         o = self.o
         circuit = np.asarray(circuit, np.uint8)
@@ -272,7 +276,7 @@ class HostcheckImpl:
         wit, rnd, chal = (np.ascontiguousarray(x, np.uint8) for x in (wit, rnd, chal))
         n = wit.shape[0]
         proofs, status = np.zeros((n, 34), np.uint8), np.zeros(n, np.uint8)
-        (self.lib.hc_prove_pairs if self.fast else self.lib.hc_prove)(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), _p(chal),
+        self._prove_fn()(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), _p(chal),
                           _p(proofs), _p(status), None, C.c_size_t(n))
         return proofs, status
 
@@ -282,7 +286,7 @@ class HostcheckImpl:
         wit, rnd = (np.ascontiguousarray(x, np.uint8) for x in (wit, rnd))
         n = wit.shape[0]
         proofs, status, chal = np.zeros((n, 34), np.uint8), np.zeros(n, np.uint8), np.zeros((n, 6), np.uint8)
-        (self.lib.hc_prove_pairs if self.fast else self.lib.hc_prove)(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), None,
+        self._prove_fn()(ccw.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), _p(wit), _p(rnd), None,
                           _p(proofs), _p(status), _p(chal), C.c_size_t(n))
         return proofs, status, chal
 
@@ -291,7 +295,7 @@ class HostcheckImpl:
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt
 
     def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
@@ -299,6 +303,6 @@ class HostcheckImpl:
         proofs = np.ascontiguousarray(proofs, np.uint8)
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast else self.lib.hc_verify)(_p(key), C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), None, None,
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), None, None,
                                                                       _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt

@@ -189,6 +189,21 @@ def test_protocol_exact_path_forced(host, oracle, W):
         del os.environ["PB_FORCE_EXACT"]
 
 
+def test_protocol_pair_tables_path(host, oracle, W):
+    """PB_WIDE_TABLES=0 keeps a context on the pair-table prover (5.8 KB of tables in shared memory instead of the 48 MB
+    one-look-up table): the smaller-footprint fast path must stay byte-identical too."""
+    import os
+    os.environ["PB_WIDE_TABLES"] = "0"
+    try:
+        impl = GpuImpl(host, "device")
+        modes = [("generator9", lambda W: W.generator_srs(9)), ("generator6", lambda W: W.generator_srs(6)), ("identity6", lambda W: W.identity_srs(6))]
+        ps.check_protocol(impl, oracle, W, n=30000, modes=modes)
+        ps.check_fiat_shamir(impl, oracle, W, n=10000, modes=modes[:1])
+        ps.check_golden_transcript(impl, W)
+    finally:
+        del os.environ["PB_WIDE_TABLES"]
+
+
 def test_prove_verify_fused_matches_separate_calls(host, W):
     """pb_plonk_prove_verify (prover-fed dense list) == pb_plonk_prove + pb_plonk_verify on the completed proofs."""
     import torch

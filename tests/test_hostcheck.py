@@ -44,6 +44,18 @@ def test_hostcheck_fast_paths(oracle, W):
     ps.check_golden_transcript(hcf, W)
 
 
+def test_hostcheck_wide_tables(oracle, W):
+    """One-look-up commitments (T6, 17^6 entries): same eligibility as the pair tables, byte-identical output required."""
+    import util
+    hcw = HostcheckImpl(oracle, fast="wide")
+    modes = [(m, f) for m, f in util.SRS_MODES.items()]
+    ps.check_protocol(hcw, oracle, W, n=8000, modes=modes)
+    ps.check_golden_transcript(hcw, W)
+    ps.check_fiat_shamir(hcw, oracle, W, n=4000, modes=modes[3:4])
+    ps.check_whole_curve_srs(hcw, oracle, W, n=2000, trials=3)
+    ps.check_random_circuits(hcw, oracle, W, n=1500, circuits=4)
+
+
 def test_hostcheck_fiat_shamir(oracle, W):
     """Fiat-Shamir mode of prove_one / the verifier kernels' challenge derivation (transcript.cuh) against oracle/fs_spec.inc"""
     import util
