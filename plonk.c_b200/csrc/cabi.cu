@@ -1346,7 +1346,8 @@ int pb_tally_dev(const uint8_t* proofs, const uint8_t* status, const uint8_t* ve
   if (n == 0) return PB_OK;
   unsigned grid = blocks_for(n, BLOCK_LIGHT);
   if (grid > 148u * 8u) grid = 148u * 8u;
-  tally_kernel<<<grid, BLOCK_LIGHT, 0, S(stream)>>>(proofs, status, verdict, n, reinterpret_cast<unsigned long long*>(counts));
+  const int vec = aligned16(proofs) && aligned16(status) && aligned16(verdict);   // null pointers count as aligned
+  tally_kernel<<<grid, BLOCK_LIGHT, 0, S(stream)>>>(proofs, status, verdict, n, reinterpret_cast<unsigned long long*>(counts), vec);
   LAUNCH_CHECK("tally_kernel");
   return PB_OK;
 }

@@ -849,26 +849,79 @@ __global__ void verifier_key_kernel(const uint32_t* __restrict__ Tg, uint32_t sr
 }
 
 // counts[s] += #status==s (s < 15; 15 = other), counts[16] += #verdict==1, counts[17] += sum of proof bytes
+// Per-batch counters: status histogram, accepted count, byte sum of the proofs.  HBM-bound by design:
+// 36 B per item are read once, 16 bytes per request; the counting is SIMD-in-a-word (__vcmpeq4 / __vsadu4) in registers,
+// one warp reduction and one shared-memory atomic per warp and counter, one global atomic per block and counter.
+// vec = 0: the pointers are not 16-byte aligned, everything goes through the byte loops.
 __global__ void __launch_bounds__(BLOCK_LIGHT) tally_kernel(const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ status,
-                                                            const uint8_t* __restrict__ verdict, size_t n, unsigned long long* __restrict__ counts) {
+                                                            const uint8_t* __restrict__ verdict, size_t n, unsigned long long* __restrict__ counts,
+                                                            int vec) {
   __shared__ unsigned long long sc[18];
   if (threadIdx.x < 18) sc[threadIdx.x] = 0ull;
   __syncthreads();
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t hist[16];
+#pragma unroll
+  for (int b = 0; b < 16; b++) hist[b] = 0u;
+  uint32_t accepted = 0u;
   unsigned long long sum = 0ull;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t s = status ? status[i] : 0u;
-    atomicAdd(&sc[s < 15u ? s : 15u], 1ull);
-    if (verdict && verdict[i] == 1) atomicAdd(&sc[16], 1ull);
+  const size_t nvec = vec ? n / 16 : 0;           // items covered by 16-byte pieces of status / verdict
+  for (size_t k = gtid; k < nvec; k += stride) {
+    if (status) {
+      const uint4 q = reinterpret_cast<const uint4*>(status)[k];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t low = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (uint32_t b = 0; b < 15u; b++) {
+          const uint32_t c = (uint32_t)__popc(__vcmpeq4(w[j], b * 0x01010101u)) >> 3;
+          hist[b] += c;
+          low += c;
+        }
+      }
+      hist[15] += 16u - low;                      // every status byte outside 0..14
+    }
+    if (verdict) {
+      const uint4 q = reinterpret_cast<const uint4*>(verdict)[k];
+      accepted += (uint32_t)(__popc(__vcmpeq4(q.x, 0x01010101u)) + __popc(__vcmpeq4(q.y, 0x01010101u)) +
+                             __popc(__vcmpeq4(q.z, 0x01010101u)) + __popc(__vcmpeq4(q.w, 0x01010101u))) >> 3;
+    }
+  }
+  for (size_t i = nvec * 16 + gtid; i < n; i += stride) {      // ragged tail, or everything when unaligned
+    const uint32_t s = status ? status[i] : 0u;
+    const uint32_t bin = s < 15u ? s : 15u;
+#pragma unroll
+    for (uint32_t b = 0; b < 16u; b++) hist[b] += bin == b ? 1u : 0u;
+    if (verdict && verdict[i] == 1) accepted++;
+  }
+  if (!status && vec) {                            // no status array: every item counts as status 0 (as the byte loop does)
+    for (size_t k = gtid; k < nvec; k += stride) hist[0] += 16u;
   }
   if (proofs) {
-    const size_t words = n * 34 / 4;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += stride) {
-      uint32_t w = reinterpret_cast<const uint32_t*>(proofs)[k];
-      sum += (w & 0xFFu) + ((w >> 8) & 0xFFu) + ((w >> 16) & 0xFFu) + (w >> 24);
+    const size_t bytes = n * 34;
+    const size_t nv = vec ? bytes / 16 : 0;
+    uint32_t part = 0u;
+    for (size_t k = gtid; k < nv; k += stride) {
+      const uint4 q = reinterpret_cast<const uint4*>(proofs)[k];
+      part += __vsadu4(q.x, 0u) + __vsadu4(q.y, 0u) + __vsadu4(q.z, 0u) + __vsadu4(q.w, 0u);   // <= 4080 per piece
+      if ((part >> 31) != 0u) { sum += part; part = 0u; }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) for (size_t k = words * 4; k < n * 34; k++) sum += proofs[k];
-    atomicAdd(&sc[17], sum);
+    sum += part;
+    for (size_t k = nv * 16 + gtid; k < bytes; k += stride) sum += proofs[k];
+  }
+  // warp reduction, then one shared atomic per warp and counter
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, hist[b]);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sc[b], (unsigned long long)t);
+  }
+  {
+    const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, accepted);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sc[16], (unsigned long long)t);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&sc[17], sum);
   }
   __syncthreads();
   if (threadIdx.x < 18 && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);

@@ -121,3 +121,28 @@ def test_config5_prove_verify_2p22(host, oracle, W, mode):
         rv, _ = oracle.plonk_verify_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, rp, chal[sl], u[sl], 8)
         rv = np.where(rs == 0, rv, 0xFF).astype(np.uint8)
         ps.eq(f"window {lo}", (proofs[sl].cpu().numpy(), status[sl].cpu().numpy(), verdict[sl].cpu().numpy()), (rp, rs, rv))
+
+
+def test_tally_matches_numpy(host):
+    """pb_tally_dev against plonk_c_b200.shard.tally_host: arbitrary bytes (status values beyond 14 fold into bin 15),
+    ragged sizes, pointers that are not 16-byte aligned (byte path), absent arrays, accumulation over calls."""
+    import torch
+    from plonk_c_b200 import shard
+    rng = np.random.default_rng(5)
+    for n, off in ((1, 0), (15, 0), (16, 0), (4097, 0), (100003, 0), (100003, 1), (65536, 3), (1 << 20, 0)):
+        proofs = rng.integers(0, 256, (n + 4, 34), dtype=np.uint8)
+        status = rng.integers(0, 256, n + 4, dtype=np.uint8)
+        status[rng.random(n + 4) < 0.7] = 0
+        status[rng.random(n + 4) < 0.2] = 8
+        verdict = rng.integers(0, 3, n + 4, dtype=np.uint8)
+        dp, ds, dv = (_t(x)[off:off + n] for x in (proofs, status, verdict))
+        hp, hs, hv = proofs[off:off + n], status[off:off + n], verdict[off:off + n]
+        counts = torch.zeros(18, dtype=torch.int64, device="cuda")
+        host.tally(dp, ds, dv, counts)
+        host.tally(dp, ds, dv, counts)            # accumulates
+        torch.cuda.synchronize()
+        assert counts.cpu().numpy().tolist() == (2 * shard.tally_host(hp, hs, hv)).tolist(), (n, off)
+        counts.zero_()
+        host.tally(None, ds, None, counts)
+        torch.cuda.synchronize()
+        assert counts.cpu().numpy().tolist() == shard.tally_host(None, hs, None).tolist(), (n, off, "status only")
