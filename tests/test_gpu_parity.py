@@ -204,6 +204,28 @@ def test_protocol_pair_tables_path(host, oracle, W):
         del os.environ["PB_WIDE_TABLES"]
 
 
+def test_host_pipeline_pinned_matches_pageable(host, W):
+    """Host-pointer prove+verify with pinned buffers against the same call with pageable buffers, explicit and
+    Fiat-Shamir mode, a ragged size spanning many pipeline chunks."""
+    import torch
+    n = 300007
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    wit, rnd, chal, u = W.make_batch(321, 0, n, "U17")
+    want = pk.prove_verify(wit, rnd, chal, u)                      # numpy (pageable) in and out
+    pin_in = [torch.from_numpy(x).pin_memory().numpy() for x in (wit, rnd, chal, u)]
+    pin_out = [torch.full((n, 34), 7, dtype=torch.uint8).pin_memory().numpy(), torch.full((n,), 7, dtype=torch.uint8).pin_memory().numpy(),
+               torch.full((n,), 7, dtype=torch.uint8).pin_memory().numpy()]
+    pk.prove_verify_into(*pin_in, *pin_out)
+    ps.eq("pinned outputs, explicit challenges", tuple(pin_out), want)
+    want_fs = pk.prove_verify_fs(wit, rnd)
+    for o in pin_out:
+        o[...] = 9
+    pk.prove_verify_fs_into(pin_in[0], pin_in[1], *pin_out)
+    ps.eq("pinned outputs, Fiat-Shamir", tuple(pin_out), want_fs)
+    proofs, status = pk.prove(wit, rnd, chal)
+    ps.eq("prove only", (proofs, status), want[:2])
+
+
 def test_prove_verify_fused_matches_separate_calls(host, W):
     """pb_plonk_prove_verify (prover-fed dense list) == pb_plonk_prove + pb_plonk_verify on the completed proofs."""
     import torch
