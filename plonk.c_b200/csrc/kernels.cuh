@@ -507,16 +507,34 @@ template <int ITEM, int NT>
 PB_D void stage_in(uint8_t* smem, const uint8_t* __restrict__ g, size_t first, size_t n) {
   // bytes [first*ITEM, min(first+NT, n)*ITEM) -> smem[0..]; the block base is 16-byte aligned because
   // first is a multiple of NT and NT*ITEM is a multiple of 16
-  const size_t cnt = (n - first < (size_t)NT ? n - first : (size_t)NT) * ITEM;
   const uint8_t* src = g + first * ITEM;
+  if (first + NT <= n) {   // a full block: compile-time trip count, 32-bit indices, no tail
+    constexpr int NV = NT * ITEM / 16;
+#pragma unroll
+    for (int k0 = 0; k0 < NV; k0 += NT) {
+      const int k = k0 + (int)threadIdx.x;
+      if (k0 + NT <= NV || k < NV) reinterpret_cast<uint4*>(smem)[k] = reinterpret_cast<const uint4*>(src)[k];
+    }
+    return;
+  }
+  const size_t cnt = (n - first) * ITEM;
   const size_t nv = cnt / 16;
   for (size_t k = threadIdx.x; k < nv; k += NT) reinterpret_cast<uint4*>(smem)[k] = reinterpret_cast<const uint4*>(src)[k];
   for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) smem[k] = src[k];
 }
 template <int ITEM, int NT>
 PB_D void stage_out(uint8_t* __restrict__ g, const uint8_t* smem, size_t first, size_t n) {
-  const size_t cnt = (n - first < (size_t)NT ? n - first : (size_t)NT) * ITEM;
   uint8_t* dst = g + first * ITEM;
+  if (first + NT <= n) {
+    constexpr int NV = NT * ITEM / 16;
+#pragma unroll
+    for (int k0 = 0; k0 < NV; k0 += NT) {
+      const int k = k0 + (int)threadIdx.x;
+      if (k0 + NT <= NV || k < NV) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(smem)[k];
+    }
+    return;
+  }
+  const size_t cnt = (n - first) * ITEM;
   const size_t nv = cnt / 16;
   for (size_t k = threadIdx.x; k < nv; k += NT) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(smem)[k];
   for (size_t k = nv * 16 + threadIdx.x; k < cnt; k += NT) dst[k] = smem[k];
