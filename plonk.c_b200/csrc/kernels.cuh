@@ -732,37 +732,42 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
   size_t item = first + tid;
   const bool live = item < limit;
   const bool fs = chal == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
+  uint32_t pbytes[27], op[7], ch[5];
   if (done_list) {
-    item = live ? done_list[item] : 0;
-    const uint8_t* pr = proofs + item * 34;                               // gather: 34 + 5 contiguous bytes per item
-    if (live) {
+    // dense-list mode: the items of a block are scattered, so each lane reads its own 34-byte record straight into
+    // registers (17 two-byte loads: records are 2-byte aligned) instead of staging it through shared memory
+    __syncthreads();                                                      // tables staged
+    if (!live) return;
+    item = done_list[item];
+    const uint16_t* pr = reinterpret_cast<const uint16_t*>(proofs + item * 34);
+    uint32_t b[34];
 #pragma unroll
-      for (int k = 0; k < 34; k++) sm.proof[tid * 34 + k] = pr[k];
-      if (!fs) {
-        const uint8_t* cr = chal + item * 5;
+    for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
 #pragma unroll
-        for (int k = 0; k < 5; k++) sm.chal[tid * 5 + k] = cr[k];
-      }
+    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
+    if (!fs) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
     }
   } else {
     stage_in<34, BLOCK>(sm.proof, proofs, first, n);
     if (!fs) stage_in<5, BLOCK>(sm.chal, chal, first, n);
+    __syncthreads();
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+    if (!fs) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    }
   }
-  __syncthreads();
-  if (!live) return;
-  uint32_t pbytes[27], op[7], ch[5];
-#pragma unroll
-  for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
-#pragma unroll
-  for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
   uint32_t uu;
-  if (fs) {
-    fs_derive(key.fs_seed, pbytes, op, ch, uu);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
-    uu = u[item];
-  }
+  if (fs) fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  else uu = u[item];
   VerifyOut o;
   verify_one_fast(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
   verdict[item] = (uint8_t)o.verdict;
