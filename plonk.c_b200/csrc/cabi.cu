@@ -880,7 +880,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   cudaFree(d_prow);
   cudaFree(d_g1s);
   if (e != cudaSuccess) return bail(cuda_fail(e, "srs_table_kernel"));
-  for (uint32_t i = 0; i < 101; i++) pt.ft.inv101[i] = (uint8_t)pow101(i, 99);
+  for (uint32_t i = 0; i < 256; i++) pt.ft.inv101[i] = (uint8_t)pow101(i % 101u, 99);
   for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) pt.pow17[zz][k] = (uint8_t)pow17(zz, k);
   if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));

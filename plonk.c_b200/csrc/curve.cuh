@@ -47,6 +47,35 @@ PB_HD G1 g1_add(const FieldTables& t, G1 a, G1 b) {
   return r;
 }
 
+// Leaner variants for the fast paths, where every operand is a canonically encoded point of E(F_101) (coordinates < 101,
+// infinite in {0, 1}, identity = {0, 0, 1}) -- checked before they are used (verifier.cuh step 1, context creation).
+// Same results as g1_add / g1_double on that domain; the difference is bookkeeping: the slope's denominator indexes the
+// inverse table unreduced (2y <= 200, x_b + 101 - x_a <= 201; the table repeats mod 101) and the tangent numerator
+// 3x^2 goes into the product raw (3 * 100^2 * 100 < 2^26).
+PB_HD G1 g1_double_c(const FieldTables& t, G1 a) {
+  const uint32_t m = red101(3u * a.x * a.x * inv101(t, 2u * a.y));
+  const uint32_t xr = red101(m * m + 2u * P101 - 2u * a.x);
+  const uint32_t yr = red101(m * (a.x + P101 - xr) + P101 - a.y);
+  G1 r{xr, yr, 0u};
+  if (a.inf || a.y == 0u) r = g1_identity();
+  return r;
+}
+PB_HD G1 g1_add_c(const FieldTables& t, G1 a, G1 b) {
+  const bool same_x = a.x == b.x;
+  const uint32_t sum_y = a.y + b.y;
+  const bool to_id = same_x && (sum_y == 0u || sum_y == P101 || a.y == 0u);
+  const uint32_t num = same_x ? 3u * a.x * a.x : (b.y + P101 - a.y);
+  const uint32_t den = same_x ? 2u * a.y : (b.x + P101 - a.x);
+  const uint32_t m = red101(num * inv101(t, den));
+  const uint32_t xr = red101(m * m + 2u * P101 - a.x - b.x);
+  const uint32_t yr = red101(m * (a.x + P101 - xr) + P101 - a.y);
+  G1 r{xr, yr, 0u};
+  if (to_id) r = g1_identity();
+  if (b.inf) r = a;
+  if (a.inf) r = b;
+  return r;
+}
+
 PB_HD G1 g1_neg(G1 a) {  // g1.h:85-89: the identity comes back untouched
   G1 r{a.x, neg101(a.y), 0u};
   if (a.inf) r = a;

@@ -17,7 +17,7 @@ constexpr int POLY_MAX = 64;
 // x^99 mod 101 is literally what gf_inv computes (gf.h:159-162).  ~150 thread-level pow calls per
 // block, amortised over >= 128 items of >= several hundred instructions each.
 PB_D void build_field_tables(FieldTables& ft) {
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) ft.inv101[i] = i < 101 ? (uint8_t)pow101((uint32_t)i, 99) : 0;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) ft.inv101[i] = (uint8_t)pow101((uint32_t)i % 101u, 99);
   for (int i = threadIdx.x; i < 32; i += blockDim.x) ft.inv17[i] = i < 17 ? (uint8_t)pow17((uint32_t)i, 15) : 0;
 }
 

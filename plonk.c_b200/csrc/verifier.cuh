@@ -165,29 +165,29 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
 
   // the preprocessed part of [D] + [F] - [E]: five look-ups
   G1 acc = unpack_g1(vt.P2[0][red17(red17(a_z * b_z) * v) * 17u + red17(a_z * v)]);
-  acc = g1_add(ft, acc, unpack_g1(vt.P2[1][red17(b_z * v) * 17u + red17(c_z * v)]));
-  acc = g1_add(ft, acc, unpack_g1(vt.P2[2][v * 17u + d_s3]));
-  acc = g1_add(ft, acc, unpack_g1(vt.P2[3][v5 * 17u + v6]));
-  acc = g1_add(ft, acc, unpack_g1(vt.one_neg[e]));
-  acc = g1_add(ft, acc, P[4]);                                         // [t_lo]
+  acc = g1_add_c(ft, acc, unpack_g1(vt.P2[1][red17(b_z * v) * 17u + red17(c_z * v)]));
+  acc = g1_add_c(ft, acc, unpack_g1(vt.P2[2][v * 17u + d_s3]));
+  acc = g1_add_c(ft, acc, unpack_g1(vt.P2[3][v5 * 17u + v6]));
+  acc = g1_add_c(ft, acc, unpack_g1(vt.one_neg[e]));
+  acc = g1_add_c(ft, acc, P[4]);                                         // [t_lo]
 
   // z[W_z] + u z omega [W_zw] + z^6[t_mid] + z^12[t_hi] + v^2[a] + v^3[b] + v^4[c] + d_z[z]: joint double-and-add,
   // most significant bit first, two points per 4-entry sub-table
   const G1 A0 = P[7], B0 = P[8], A1 = P[5], B1 = P[6], A2 = P[0], B2 = P[1], A3 = P[2], B3 = P[3];
   const uint32_t sa0 = z, sb0 = red17(red17(u * z) * OMEGA), sa1 = z6, sb1 = z12, sa2 = v2, sb2 = v3, sa3 = v4, sb3 = d_z;
-  const G1 S0 = g1_add(ft, A0, B0), S1 = g1_add(ft, A1, B1), S2 = g1_add(ft, A2, B2), S3 = g1_add(ft, A3, B3);
+  const G1 S0 = g1_add_c(ft, A0, B0), S1 = g1_add_c(ft, A1, B1), S2 = g1_add_c(ft, A2, B2), S3 = g1_add_c(ft, A3, B3);
   G1 s = g1_identity(), l = g1_identity();
   for (int bit = 4; bit >= 0; --bit) {
-    s = g1_double(ft, s);
-    s = g1_add(ft, s, pick4(((sa0 >> bit) & 1u) | (((sb0 >> bit) & 1u) << 1), A0, B0, S0));
-    s = g1_add(ft, s, pick4(((sa1 >> bit) & 1u) | (((sb1 >> bit) & 1u) << 1), A1, B1, S1));
-    s = g1_add(ft, s, pick4(((sa2 >> bit) & 1u) | (((sb2 >> bit) & 1u) << 1), A2, B2, S2));
-    s = g1_add(ft, s, pick4(((sa3 >> bit) & 1u) | (((sb3 >> bit) & 1u) << 1), A3, B3, S3));
-    l = g1_double(ft, l);                                              // u [W_zw] for the left-hand side
-    l = g1_add(ft, l, pick4((u >> bit) & 1u, B0, B0, B0));
+    s = g1_double_c(ft, s);
+    s = g1_add_c(ft, s, pick4(((sa0 >> bit) & 1u) | (((sb0 >> bit) & 1u) << 1), A0, B0, S0));
+    s = g1_add_c(ft, s, pick4(((sa1 >> bit) & 1u) | (((sb1 >> bit) & 1u) << 1), A1, B1, S1));
+    s = g1_add_c(ft, s, pick4(((sa2 >> bit) & 1u) | (((sb2 >> bit) & 1u) << 1), A2, B2, S2));
+    s = g1_add_c(ft, s, pick4(((sa3 >> bit) & 1u) | (((sb3 >> bit) & 1u) << 1), A3, B3, S3));
+    l = g1_double_c(ft, l);                                              // u [W_zw] for the left-hand side
+    l = g1_add_c(ft, l, pick4((u >> bit) & 1u, B0, B0, B0));
   }
-  const G1 rhs_p = g1_add(ft, acc, s);
-  const G1 lhs_p = g1_add(ft, P[7], l);
+  const G1 rhs_p = g1_add_c(ft, acc, s);
+  const G1 lhs_p = g1_add_c(ft, P[7], l);
   out.lhs = pairing17(ft, lhs_p, k.g2_s);
   out.rhs = pairing17(ft, rhs_p, k.g2_one);
   out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;

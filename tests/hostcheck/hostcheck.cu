@@ -13,7 +13,7 @@ using namespace pb;
 static FieldTables make_ft() {
   FieldTables ft;
   memset(&ft, 0, sizeof ft);
-  for (uint32_t i = 0; i < 101; i++) ft.inv101[i] = (uint8_t)pow101(i, 99);
+  for (uint32_t i = 0; i < 256; i++) ft.inv101[i] = (uint8_t)pow101(i % 101u, 99);
   for (uint32_t i = 0; i < 17; i++) ft.inv17[i] = (uint8_t)pow17(i, 15);
   return ft;
 }
