@@ -52,6 +52,14 @@ PB_D void store_slice(uint8_t* __restrict__ g, const uint8_t* smem, size_t first
   }
 }
 
+// a 6-byte record (2-byte aligned: the base is 16-byte aligned) as three 16-bit loads; a warp's 32 records are one
+// 192-byte span, so the three requests hit the same six sectors in L1
+PB_D void load_record6(uint32_t (&r)[6], const uint8_t* __restrict__ base, size_t t) {
+  const uint16_t* g = reinterpret_cast<const uint16_t*>(base) + 3 * t;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const uint32_t w = g[k]; r[2 * k] = w & 0xFFu; r[2 * k + 1] = w >> 8; }
+}
+
 // poly_mul (poly.h:106-122) for fixed strides SA x SB -> SA+SB-1
 template <int SA, int SB>
 __global__ void __launch_bounds__(PF_BLOCK) poly_mul_fast_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ alen,
@@ -194,11 +202,9 @@ __global__ void __launch_bounds__(PF_BLOCK) config2_kernel(const __grid_constant
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * PF_BLOCK, t = first + tid;
   if (t < n) {
-    uint32_t wa[2], wb[2], ra[6], rb[6], p[11];
-    load_record<6>(wa, a, t, n);
-    load_record<6>(wb, b, t, n);
-    unpack_masked(ra, wa, 6u);
-    unpack_masked(rb, wb, 6u);
+    uint32_t ra[6], rb[6], p[11];
+    load_record6(ra, a, t);
+    load_record6(rb, b, t);
 #pragma unroll
     for (int k = 0; k < 11; k++) p[k] = 0u;
     mul_acc<6, 6>(p, ra, rb);                                     // poly_mul, poly.h:106-122
