@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--variant", default="U17", choices=["U17", "NZ"])
     ap.add_argument("--ref-items", type=int, default=1 << 18, help="proofs per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "prove_verify_fs", "poly", "g1_mul", "pairing"],
+    ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "prove_verify_fs", "poly", "g1_mul", "pairing", "field"],
                     help="prove_verify = BASELINE config 5 (the headline, what the driver runs); poly / g1_mul / pairing = "
                          "configs 2 / 3 / 4 (single GPU, device-resident; extra lines for profiles/)")
     return ap.parse_args()
@@ -573,6 +573,46 @@ def run_config(args):
                          "algorithmic_int_ops_per_item": int_ops, "traffic": None, "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
             "cpu_baseline": {"value": cpu_rate, "unit": "pairings/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
         gpu_launches = args.steps
+    elif args.workload == "field":
+        # kernel family (1): hf.h / gf.h element-wise over 2^27 elements (HBM-bound: 3 B per element, 2 for unary ops), plus
+        # the tally kernel of the headline step (36 B per item read)
+        n = 1 << 27
+        rng = np.random.default_rng(SEED)
+        res, gbs = {}, {}
+        for field in (17, 101):
+            A = T(rng.integers(0, field, n, dtype=np.uint8))
+            B = T(rng.integers(1, field, n, dtype=np.uint8))
+            out = torch.empty(n, dtype=torch.uint8, device=dev)
+            for name, op, unary in (("add", host.OP_ADD, False), ("sub", host.OP_SUB, False), ("mul", host.OP_MUL, False),
+                                    ("div", host.OP_DIV, False), ("neg", host.OP_NEG, True), ("inv", host.OP_INV, True), ("pow", host.OP_POW, False)):
+                pb = None if unary else C.c_void_p(B.data_ptr())
+                ms = timed(lambda: host._check(lib.pb_field_op_dev(C.c_int(field), C.c_int(op), C.c_void_p(A.data_ptr()), pb,
+                                                                   C.c_void_p(out.data_ptr()), C.c_size_t(n), sp)))
+                key = f"{'hf' if field == 17 else 'gf'}_{name}"
+                res[key] = ms
+                gbs[key] = (2 if unary else 3) * n / (ms * 1e-3) / 1e9
+            del A, B, out
+        m = 1 << 21
+        pr = T(rng.integers(0, 101, (m, 34), dtype=np.uint8))
+        st_ = T((rng.random(m) < 0.4).astype(np.uint8) * 8)
+        vd = T(rng.integers(0, 2, m, dtype=np.uint8))
+        cnt = torch.zeros(18, dtype=torch.int64, device=dev)
+        ms = timed(lambda: host.tally(pr, st_, vd, cnt))
+        res["tally_kernel (2^21 items)"] = ms
+        gbs["tally_kernel (2^21 items)"] = 36 * m / (ms * 1e-3) / 1e9
+        a_cpu = rng.integers(0, 101, 1 << 24, dtype=np.uint8)
+        b_cpu = rng.integers(1, 101, 1 << 24, dtype=np.uint8)
+        t0 = time.perf_counter()
+        oracle.field_op(101, host.OP_MUL, a_cpu, b_cpu)
+        cpu_rate = (1 << 24) / (time.perf_counter() - t0)
+        worst = min((k for k in gbs if not k.startswith("tally")), key=lambda k: gbs[k])
+        line = {"metric": "field_ops_per_s", "unit": "elements/s", "value": n / (res["gf_mul"] * 1e-3), "config": {
+            "workload": "kernel family (1): hf.h / gf.h element-wise operations over 2^27 one-byte elements; value = gf_mul"},
+            "kernel_ms": res,
+            "roofline": {"bound": "hbm", "kernel": worst, "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peak_src,
+                         "achieved": gbs[worst], "frac": gbs[worst] / peaks["hbm_gbs"], "traffic": None, "per_kernel_gbs": gbs},
+            "cpu_baseline": {"value": cpu_rate, "unit": "elements/s", "cores": 1, "kind": okind, "sample": "gf_mul over 2^24 elements, 1 thread"}}
+        gpu_launches = 15 * args.steps
     elif args.workload == "prove_verify_fs":
         # the optional Fiat-Shamir mode on the headline workload: challenges drawn in the kernels (csrc/transcript.cuh)
         n = 1 << 21

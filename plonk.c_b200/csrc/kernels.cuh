@@ -77,6 +77,44 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uin
     out[i] = (uint8_t)field_apply<FIELD>(ft, op, a[i], b ? b[i] : 0u);
 }
 
+// hf_pow / gf_pow (hf.h:127-137, gf.h:140-151) with a one-byte exponent: the reference's square-and-multiply returns
+// (a mod p)^e with 0^0 = 1, so the result is a look-up in a per-block table tab[a][k] = a^k, k < p - 1 (Fermat:
+// a^(p-1) = 1 for a != 0), with the base-zero row handled by a select.  272 B (F17) / 10 KB (F101) of shared memory,
+// built once per block (one row per thread, p - 2 multiplications).  16 elements per thread, 128-bit accesses.
+template <int FIELD>
+__global__ void __launch_bounds__(BLOCK_LIGHT) field_pow_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ e,
+                                                                uint8_t* __restrict__ out, size_t n) {
+  constexpr uint32_t P = FIELD, ORD = FIELD - 1;
+  __shared__ uint8_t tab[P * ORD];
+  for (uint32_t row = threadIdx.x; row < P; row += blockDim.x) {
+    uint32_t v = 1u;
+    for (uint32_t k = 0; k < ORD; k++) { tab[row * ORD + k] = (uint8_t)v; v = FIELD == 17 ? mul17(v, row) : mul101(v, row); }
+  }
+  __syncthreads();
+  auto one = [&](uint32_t base, uint32_t ex) -> uint32_t {
+    const uint32_t b = FIELD == 17 ? red17(base) : red101(base);
+    const uint32_t k = FIELD == 17 ? (ex & 15u) : ex - 100u * ((ex * 41u) >> 12);     // ex mod (p - 1), ex < 256
+    const uint32_t t = tab[b * ORD + k];
+    return (b == 0u && ex != 0u) ? 0u : t;                                             // row 0 holds 0^0 = 1 only
+  };
+  const size_t nvec = n / 16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 va = reinterpret_cast<const uint4*>(a)[i], ve = reinterpret_cast<const uint4*>(e)[i];
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, we[4] = {ve.x, ve.y, ve.z, ve.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      uint32_t r = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) r |= one((wa[w] >> (8 * k)) & 0xFFu, (we[w] >> (8 * k)) & 0xFFu) << (8 * k);
+      wo[w] = r;
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+  for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint8_t)one(a[i], e[i]);
+}
+
 // hf_new / gf_new (hf.h:25-35, gf.h:24-34): C remainder of a signed 64-bit value, negatives folded up
 template <int FIELD>
 __global__ void __launch_bounds__(BLOCK_LIGHT) field_new_kernel(const long long* __restrict__ v, uint8_t* __restrict__ out, size_t n) {
@@ -925,10 +963,19 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) tally_kernel(const uint8_t* __res
     const size_t bytes = n * 34;
     const size_t nv = vec ? bytes / 16 : 0;
     uint32_t part = 0u;
-    for (size_t k = gtid; k < nv; k += stride) {
+    size_t k = gtid;
+    for (; k + 3 * stride < nv; k += 4 * stride) {          // four independent 16-byte loads in flight per lane
+      uint4 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[j] = reinterpret_cast<const uint4*>(proofs)[k + j * stride];
+#pragma unroll
+      for (int j = 0; j < 4; j++) part += __vsadu4(q[j].x, 0u) + __vsadu4(q[j].y, 0u) + __vsadu4(q[j].z, 0u) + __vsadu4(q[j].w, 0u);
+      if ((part >> 30) != 0u) { sum += part; part = 0u; }   // <= 16320 per round
+    }
+    for (; k < nv; k += stride) {
       const uint4 q = reinterpret_cast<const uint4*>(proofs)[k];
       part += __vsadu4(q.x, 0u) + __vsadu4(q.y, 0u) + __vsadu4(q.z, 0u) + __vsadu4(q.w, 0u);   // <= 4080 per piece
-      if ((part >> 31) != 0u) { sum += part; part = 0u; }
+      if ((part >> 30) != 0u) { sum += part; part = 0u; }
     }
     sum += part;
     for (size_t k = nv * 16 + gtid; k < bytes; k += stride) sum += proofs[k];

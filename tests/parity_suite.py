@@ -53,6 +53,18 @@ def check_fields_exhaustive(impl, oracle):
                 eq(f"F{p} inv vs Fermat", want, inv)
 
 
+def check_fields_pow_all_bytes(impl, oracle):
+    """hf_pow / gf_pow for EVERY base byte and EVERY exponent byte (0..255 each): exponents beyond p - 1 (the table-driven
+    kernel folds them with Fermat), 0^0 = 1, 0^e = 0, and non-canonical bases, which the reference's `%` reduces."""
+    a, e = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    a, e = np.ascontiguousarray(a.ravel()), np.ascontiguousarray(e.ravel())
+    for p in (17, 101):
+        want = oracle.field_op(p, 6, a, e)
+        eq(f"F{p} pow, all byte pairs", impl.field_op(p, 6, a, e), want)
+        ref = np.array([pow(int(x) % p, int(k), p) for x, k in zip(a[:4096], e[:4096])], np.uint8)
+        eq(f"F{p} pow vs python pow", want[:4096], ref)
+
+
 def check_fields_ragged(impl, oracle):
     """Sizes around the 16-byte vector width and the block size, including empty."""
     rng = np.random.default_rng(0)

@@ -37,6 +37,7 @@ def test_golden_transcript(dev, hostpath, W):
 
 def test_fields(dev, oracle):
     ps.check_fields_exhaustive(dev, oracle)
+    ps.check_fields_pow_all_bytes(dev, oracle)
     ps.check_fields_ragged(dev, oracle)
 
 
