@@ -923,8 +923,12 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
         // one-look-up commitments: T3 for SRS rows 0-2 / 3-5 / 6-8, then T6 = T3[0] (+) T3[1]  (prover.cuh)
         const size_t n16 = 3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES;
         uint32_t* d_single2 = nullptr;
-        if (cudaMalloc(&c->d_wide_store, n16 * sizeof(uint16_t)) != cudaSuccess || cudaMalloc(&d_single2, sizeof pt.T) != cudaSuccess ||
-            cudaMalloc(&c->d_wide_tables, sizeof(ProverWideTables)) != cudaSuccess)
+        if (cudaMalloc(&c->d_wide_store, n16 * sizeof(uint16_t)) != cudaSuccess) {
+          // no room for the 48 MB table: not an error, the context stays on the pair tables (same results)
+          cudaGetLastError();
+          c->d_wide_store = nullptr;
+        } else {
+        if (cudaMalloc(&d_single2, sizeof pt.T) != cudaSuccess || cudaMalloc(&c->d_wide_tables, sizeof(ProverWideTables)) != cudaSuccess)
           return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
         cudaMemcpy(d_single2, pt.T, sizeof pt.T, cudaMemcpyHostToDevice);
         uint16_t* t3 = c->d_wide_store;
@@ -941,6 +945,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
         wt.T6 = t6;
         wt.T3 = t3 + 2u * (size_t)WIDE_T3_ENTRIES;
         cudaMemcpy(c->d_wide_tables, &wt, sizeof wt, cudaMemcpyHostToDevice);
+        }
       }
     }
   }
