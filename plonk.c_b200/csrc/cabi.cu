@@ -1079,7 +1079,8 @@ static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t
 static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
                          const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st) {
   if (ctx->key_canonical && !ctx->force_exact && !(status && !done_list))
-    verify_fast_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n);
+    if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n);
+    else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n);
   else
     verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n);
   LAUNCH_CHECK("verify_kernel");

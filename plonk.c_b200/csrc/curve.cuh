@@ -209,18 +209,44 @@ PB_HD GT miller(const FieldTables& t, uint64_t r, G1 p, G2 q) {
 // = -(2kP) as triples, so one doubling chain P, 2P, 4P, 8P, 16P feeds all five line functions.
 // Final exponentiation: f^600 = conj(f^5) * f^95 (gt.h:32-38 splits at 101), evaluated with shared
 // squarings in the commutative ring F_101[u]/(u^2+2).
-PB_HD GT pairing17(const FieldTables& t, G1 p, G2 q) {
+// f_17,P(Q) before the final exponentiation
+PB_HD GT miller17(const FieldTables& t, G1 p, G2 q) {
   G1 p2 = g1_double(t, p), p4 = g1_double(t, p2), p8 = g1_double(t, p4), p16 = g1_double(t, p8);
   GT f = line_at(line_through(p, g1_neg(p2)), q);                    // f_2  (f_1 = 1)
   f = gt_mul(gt_sqr(f), line_at(line_through(p2, g1_neg(p4)), q));   // f_4
   f = gt_mul(gt_sqr(f), line_at(line_through(p4, g1_neg(p8)), q));   // f_8
   f = gt_mul(gt_sqr(f), line_at(line_through(p8, g1_neg(p16)), q));  // f_16
   f = gt_mul(f, line_at(line_through(p16, p), q));                   // f_17
+  return f;
+}
+// the same for a canonically encoded point of E(F_101) (fast verifier): the doubling chain without the any-input bookkeeping
+PB_HD GT miller17_c(const FieldTables& t, G1 p, G2 q) {
+  G1 p2 = g1_double_c(t, p), p4 = g1_double_c(t, p2), p8 = g1_double_c(t, p4), p16 = g1_double_c(t, p8);
+  GT f = line_at(line_through(p, g1_neg(p2)), q);
+  f = gt_mul(gt_sqr(f), line_at(line_through(p2, g1_neg(p4)), q));
+  f = gt_mul(gt_sqr(f), line_at(line_through(p4, g1_neg(p8)), q));
+  f = gt_mul(gt_sqr(f), line_at(line_through(p8, g1_neg(p16)), q));
+  f = gt_mul(f, line_at(line_through(p16, p), q));
+  return f;
+}
+PB_HD GT final_exp600(GT f) {
   GT f2 = gt_sqr(f), f4 = gt_sqr(f2), f8 = gt_sqr(f4), f16 = gt_sqr(f8), f32 = gt_sqr(f16), f64 = gt_sqr(f32);
-  (void)f32;
   GT f5 = gt_mul(f4, f);
   GT f95 = gt_mul(gt_mul(gt_mul(f64, f16), gt_mul(f8, f4)), gt_mul(f2, f));
   return gt_mul(gt_conj(f5), f95);
+}
+PB_HD GT pairing17(const FieldTables& t, G1 p, G2 q) { return final_exp600(miller17(t, p, q)); }
+
+// gtp_equal(pairing(p1, q1), pairing(p2, q2)) with ONE final exponentiation.  GT = F_101[u]/(u^2 + 2) is a field (-2 is
+// a non-residue mod 101), so for f2 != 0:  f1^600 == f2^600  <=>  (f1 / f2)^600 == 1, and 1/f2 = conj(f2) / N(f2) with
+// N(f2) in F_101^*, whose 600th power is (N^100)^6 = 1 -- hence (f1 conj(f2))^600 == 1.  A zero Miller value (the
+// reference's pairing of the identity is (0, 0)) stays zero under the power: equal iff both are zero.
+PB_HD bool pairings_equal17_c(const FieldTables& t, G1 p1, G2 q1, G1 p2, G2 q2) {
+  const GT f1 = miller17_c(t, p1, q1), f2 = miller17_c(t, p2, q2);
+  const bool z1 = (f1.a | f1.b) == 0u, z2 = (f2.a | f2.b) == 0u;
+  const GT e = final_exp600(gt_mul(f1, gt_conj(f2)));
+  const bool one = e.a == 1u && e.b == 0u;
+  return (z1 || z2) ? (z1 && z2) : one;
 }
 
 }  // namespace pb

@@ -754,6 +754,7 @@ struct __align__(16) VerifyFastSmem {
   __align__(16) uint8_t chal[BLOCK * 5];
 };
 
+template <bool WANT_GT>
 __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constant__ VerifyKey key, const VerifyTables* __restrict__ gvt,
                                                             const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                             const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
@@ -807,9 +808,9 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
   if (fs) fs_derive(key.fs_seed, pbytes, op, ch, uu);
   else uu = u[item];
   VerifyOut o;
-  verify_one_fast(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
+  verify_one_fast<WANT_GT>(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
   verdict[item] = (uint8_t)o.verdict;
-  if (gt) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+  if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
 }
 
 // status bytes -> dense list of the completed items (for pb_plonk_verify_completed_dev, where the list does not come

@@ -122,6 +122,9 @@ PB_HD G1 pick4(uint32_t sel, G1 p, G1 q, G1 pq) {   // sel: 0 -> identity, 1 -> 
   return r;
 }
 
+// WANT_GT = false: the caller does not read the two pairing values, so the check shares one final exponentiation
+// (pairings_equal17_c, curve.cuh) and out.lhs / out.rhs stay zero.
+template <bool WANT_GT = true>
 PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const FieldTables& ft, const uint32_t (&pb)[27],
                           const uint32_t (&op)[7], const uint32_t (&ch)[5], uint32_t u, VerifyOut& out) {
   out.lhs = GT{0u, 0u};
@@ -188,9 +191,13 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
   }
   const G1 rhs_p = g1_add_c(ft, acc, s);
   const G1 lhs_p = g1_add_c(ft, P[7], l);
-  out.lhs = pairing17(ft, lhs_p, k.g2_s);
-  out.rhs = pairing17(ft, rhs_p, k.g2_one);
-  out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;
+  if constexpr (WANT_GT) {
+    out.lhs = final_exp600(miller17_c(ft, lhs_p, k.g2_s));
+    out.rhs = final_exp600(miller17_c(ft, rhs_p, k.g2_one));
+    out.verdict = (out.lhs.a == out.rhs.a && out.lhs.b == out.rhs.b) ? 1u : 0u;
+  } else {
+    out.verdict = pairings_equal17_c(ft, lhs_p, k.g2_s, rhs_p, k.g2_one) ? 1u : 0u;
+  }
 }
 
 }  // namespace pb

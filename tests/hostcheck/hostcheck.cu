@@ -199,10 +199,31 @@ void hc_verify_fast(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs,
     if (chal) { for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j]; uu = u[i]; }
     else fs_derive(fs_seed, pbv, op, ch, uu);
     VerifyOut o;
-    verify_one_fast(k, vt, ft, pbv, op, ch, uu, o);
+    if (gt) verify_one_fast<true>(k, vt, ft, pbv, op, ch, uu, o);
+    else verify_one_fast<false>(k, vt, ft, pbv, op, ch, uu, o);   // verdict only: one shared final exponentiation
     verdict[i] = (uint8_t)o.verdict;
     if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
   }
+}
+// the shared-final-exponentiation identity behind pairings_equal17_c, checked on GT values directly:
+// (f1^600 == f2^600)  ==  (either zero ? both zero : (f1 conj(f2))^600 == 1), f2 over ALL of GT, f1 over every `step`-th value
+uint64_t hc_check_shared_final_exp(uint32_t step) {
+  uint64_t bad = 0;
+  for (uint32_t i = 0; i < 101u * 101u; i += step) {
+    const GT f1{i / 101u, i % 101u};
+    const GT e1 = final_exp600(f1);
+    const bool z1 = (f1.a | f1.b) == 0u;
+    for (uint32_t j = 0; j < 101u * 101u; j++) {
+      const GT f2{j / 101u, j % 101u};
+      const GT e2 = final_exp600(f2);
+      const bool want = e1.a == e2.a && e1.b == e2.b;
+      const bool z2 = (f2.a | f2.b) == 0u;
+      const GT e = final_exp600(gt_mul(f1, gt_conj(f2)));
+      const bool got = (z1 || z2) ? (z1 && z2) : (e.a == 1u && e.b == 0u);
+      bad += want != got;
+    }
+  }
+  return bad;
 }
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]

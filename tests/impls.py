@@ -131,6 +131,10 @@ class GpuImpl:
     def plonk_verify_batch(self, circuit, g1s, g2, proofs, chal, u, nthreads=1, want_gt=True):
         return self._out(self.ctx(circuit, g1s, g2).verify(self._in(proofs), self._in(chal), self._in(u), want_gt=True))
 
+    def plonk_verdict_only(self, circuit, g1s, g2, proofs, chal, u):
+        """verdicts without the two GT values (the fast verifier then shares one final exponentiation)"""
+        return self._out(self.ctx(circuit, g1s, g2).verify(self._in(proofs), self._in(chal), self._in(u), want_gt=False))
+
     # Fiat-Shamir mode
     def plonk_prove_fs_batch(self, circuit, g1s, g2, wit, rnd, nthreads=1):
         return self._out(self.ctx(circuit, g1s, g2).prove_fs(self._in(wit), self._in(rnd), want_challenges=True))
@@ -297,6 +301,14 @@ class HostcheckImpl:
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
         (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt
+
+    def plonk_verdict_only(self, circuit, g1s, g2, proofs, chal, u):
+        key = np.concatenate([self.o.verifier_key(circuit, g1s, g2).ravel(), np.asarray(g2, np.uint8)]).astype(np.uint8)
+        proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
+        n = proofs.shape[0]
+        verdict = np.zeros(n, np.uint8)
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), None, C.c_size_t(n))
+        return verdict
 
     def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
         key = np.concatenate([self.o.verifier_key(circuit, g1s, g2).ravel(), np.asarray(g2, np.uint8)]).astype(np.uint8)

@@ -271,8 +271,12 @@ def check_protocol(impl, oracle, W, n=60000, modes=None, seed=11):
                oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8))
             bad = proofs.copy()                       # one corrupted byte per proof, out-of-range values included
             bad[np.arange(n), rng.integers(0, 34, n)] = rng.integers(0, 120, n)
-            eq(f"plonk_verify corrupted {mode} {var}", impl.plonk_verify_batch(C, g1s, g2, bad, chal, u),
-               oracle.plonk_verify_batch(C, g1s, g2, bad, chal, u, 8))
+            want_bad = oracle.plonk_verify_batch(C, g1s, g2, bad, chal, u, 8)
+            eq(f"plonk_verify corrupted {mode} {var}", impl.plonk_verify_batch(C, g1s, g2, bad, chal, u), want_bad)
+            if hasattr(impl, "plonk_verdict_only"):      # verdicts without the GT values: shared final exponentiation
+                eq(f"verdict only {mode} {var}", impl.plonk_verdict_only(C, g1s, g2, proofs, chal, u),
+                   oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8)[0])
+                eq(f"verdict only corrupted {mode} {var}", impl.plonk_verdict_only(C, g1s, g2, bad, chal, u), want_bad[0])
     # a witness that violates the gates: assert(constraints_satisfy) (plonk.h:231) -> status 1
     g1s, g2 = W.generator_srs(9)
     wit, rnd, chal, u = W.make_batch(seed + 1, 0, 3000, "U17")

@@ -44,6 +44,14 @@ def test_hostcheck_fast_paths(oracle, W):
     ps.check_golden_transcript(hcf, W)
 
 
+def test_hostcheck_shared_final_exponentiation(hc):
+    """The verdict-only verifier compares two pairings with ONE final exponentiation (curve.cuh: pairings_equal17_c).
+    The identity behind it is checked here on GT values directly: every f2 in GT against every 5th f1 (21 M pairs)."""
+    import ctypes as C
+    hc.lib.hc_check_shared_final_exp.restype = C.c_uint64
+    assert hc.lib.hc_check_shared_final_exp(C.c_uint32(5)) == 0
+
+
 def test_hostcheck_wide_tables(oracle, W):
     """One-look-up commitments (T6, 17^6 entries): same eligibility as the pair tables, byte-identical output required."""
     import util
