@@ -220,13 +220,20 @@ PB_HD GT miller17(const FieldTables& t, G1 p, G2 q) {
   return f;
 }
 // the same for a canonically encoded point of E(F_101) (fast verifier): the doubling chain without the any-input bookkeeping
+// line through canonical points a, b evaluated at Q, with the differences kept unreduced (<= 201; same residues as
+// line_through + line_at): slope parts m = x_b - x_a, n = y_b - y_a, value (q.x n + m y_a - n x_a) + (-m q.y) u
+PB_HD GT line_eval_c(G1 a, G1 b, G2 q) {
+  const uint32_t m = b.x + P101 - a.x, n = b.y + P101 - a.y;
+  const uint32_t c = m * a.y + 200u * P101 - n * a.x;                 // >= 0: n x_a <= 201 * 100
+  return GT{red101(q.x * n + c), red101(q.y * (2u * P101 - m))};
+}
 PB_HD GT miller17_c(const FieldTables& t, G1 p, G2 q) {
   G1 p2 = g1_double_c(t, p), p4 = g1_double_c(t, p2), p8 = g1_double_c(t, p4), p16 = g1_double_c(t, p8);
-  GT f = line_at(line_through(p, g1_neg(p2)), q);
-  f = gt_mul(gt_sqr(f), line_at(line_through(p2, g1_neg(p4)), q));
-  f = gt_mul(gt_sqr(f), line_at(line_through(p4, g1_neg(p8)), q));
-  f = gt_mul(gt_sqr(f), line_at(line_through(p8, g1_neg(p16)), q));
-  f = gt_mul(f, line_at(line_through(p16, p), q));
+  GT f = line_eval_c(p, g1_neg(p2), q);
+  f = gt_mul(gt_sqr(f), line_eval_c(p2, g1_neg(p4), q));
+  f = gt_mul(gt_sqr(f), line_eval_c(p4, g1_neg(p8), q));
+  f = gt_mul(gt_sqr(f), line_eval_c(p8, g1_neg(p16), q));
+  f = gt_mul(f, line_eval_c(p16, p, q));
   return f;
 }
 PB_HD GT final_exp600(GT f) {

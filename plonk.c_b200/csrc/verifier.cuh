@@ -179,8 +179,14 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
   const G1 A0 = P[7], B0 = P[8], A1 = P[5], B1 = P[6], A2 = P[0], B2 = P[1], A3 = P[2], B3 = P[3];
   const uint32_t sa0 = z, sb0 = red17(red17(u * z) * OMEGA), sa1 = z6, sb1 = z12, sa2 = v2, sb2 = v3, sa3 = v4, sb3 = d_z;
   const G1 S0 = g1_add_c(ft, A0, B0), S1 = g1_add_c(ft, A1, B1), S2 = g1_add_c(ft, A2, B2), S3 = g1_add_c(ft, A3, B3);
-  G1 s = g1_identity(), l = g1_identity();
-  for (int bit = 4; bit >= 0; --bit) {
+  // top bit first, peeled: the accumulators start at the identity, whose doubling is the identity and to which an
+  // addition returns the other operand, so the first doubling and the first addition of each chain are a plain pick
+  G1 s = pick4(((sa0 >> 4) & 1u) | (((sb0 >> 4) & 1u) << 1), A0, B0, S0);
+  s = g1_add_c(ft, s, pick4(((sa1 >> 4) & 1u) | (((sb1 >> 4) & 1u) << 1), A1, B1, S1));
+  s = g1_add_c(ft, s, pick4(((sa2 >> 4) & 1u) | (((sb2 >> 4) & 1u) << 1), A2, B2, S2));
+  s = g1_add_c(ft, s, pick4(((sa3 >> 4) & 1u) | (((sb3 >> 4) & 1u) << 1), A3, B3, S3));
+  G1 l = pick4((u >> 4) & 1u, B0, B0, B0);
+  for (int bit = 3; bit >= 0; --bit) {
     s = g1_double_c(ft, s);
     s = g1_add_c(ft, s, pick4(((sa0 >> bit) & 1u) | (((sb0 >> bit) & 1u) << 1), A0, B0, S0));
     s = g1_add_c(ft, s, pick4(((sa1 >> bit) & 1u) | (((sb1 >> bit) & 1u) << 1), A1, B1, S1));
