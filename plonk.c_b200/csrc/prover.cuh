@@ -154,7 +154,7 @@ PB_HD G1 commit(const ProverPairTables& tb, const uint32_t (&c)[N], uint32_t /*l
 #pragma unroll
   for (int j = 1; j < (N + 1) / 2; j++) {
     const uint32_t idx = c[2 * j] * 17u + (2 * j + 1 < N ? c[2 * j + 1] : 0u);
-    acc = g1_add(tb.ft, acc, unpack_g1(tb.T2[j][idx]));
+    acc = g1_add_c(tb.ft, acc, unpack_g1(tb.T2[j][idx]));   // canonical table entries (the pair tables' eligibility)
   }
   return acc;
 }
@@ -171,7 +171,7 @@ PB_HD G1 commit(const ProverWideTables& tb, const uint32_t (&c)[N], uint32_t /*l
     uint32_t hi = c[N - 1];
 #pragma unroll
     for (int i = N - 2; i >= 6; i--) hi = hi * 17u + c[i];
-    acc = g1_add(tb.ft, acc, unpack_g1_16(wide_load(tb.T3, hi)));
+    acc = g1_add_c(tb.ft, acc, unpack_g1_16(wide_load(tb.T3, hi)));   // both operands are canonical table entries
   }
   return acc;
 }
