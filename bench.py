@@ -461,8 +461,17 @@ def run_config(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    # under torchrun every rank runs the same workload on its own GPU over its own item range (weak scaling, no exchange);
+    # the reported time is the max over ranks
+    rank, local_rank, world = rank_info()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        if args.workload not in ("g1_mul", "pairing"):
+            raise SystemExit("bench.py: only --workload g1_mul / pairing (and the default) run on more than one GPU")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     lib, (oracle, okind) = host.lib(), load_cpu_oracle()
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
@@ -487,7 +496,20 @@ def run_config(args):
             b.record(stream)
             torch.cuda.synchronize()
             tot += a.elapsed_time(b)
-        return tot / args.steps
+        ms = tot / args.steps
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def cpu_rate_of(fn, m):
+        """items/s of the CPU oracle on m items (rank 0 only: the other ranks would only fight for the same cores)"""
+        if rank != 0:
+            return None
+        t0 = time.perf_counter()
+        fn()
+        return m / (time.perf_counter() - t0)
 
     peaks, peak_src = measured_peaks()
     if args.workload == "poly":
@@ -534,14 +556,12 @@ def run_config(args):
     elif args.workload == "g1_mul":
         n = 1 << 24
         g1s, _ = W.generator_srs(9)
-        ai, bi, sc = W.make_group_items(SEED, 0, n)
+        ai, bi, sc = W.make_group_items(SEED, rank * n, n)
         P, S = T(g1s[ai % 10]), T(sc)
         out = torch.empty((n, 3), dtype=torch.uint8, device=dev)
         ms = timed(lambda: host._check(lib.pb_g1_mul_u8_dev(C.c_void_p(P.data_ptr()), C.c_void_p(S.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(n), sp)))
         m = 1 << 21
-        t0 = time.perf_counter()
-        oracle.g1_mul(g1s[ai[:m] % 10], sc[:m].astype(np.uint64), cores)
-        cpu_rate = m / (time.perf_counter() - t0)
+        cpu_rate = cpu_rate_of(lambda: oracle.g1_mul(g1s[ai[:m] % 10], sc[:m].astype(np.uint64), cores), m)
         int_ops = 74.5 * INT_OPS_PER_MUL + 15.6 * INT_OPS_PER_ADD
         line = {"metric": "g1_scalar_muls_per_s", "unit": "smul/s", "value": n / (ms * 1e-3), "config": {
             "workload": "BASELINE config 3: 2^24 g1_mul(P, s), P drawn from the generator SRS (n=9), s uniform on [0,17)"},
@@ -553,7 +573,7 @@ def run_config(args):
         gpu_launches = args.steps
     elif args.workload == "pairing":
         n = 1 << 22
-        ai, bi, sc = W.make_group_items(SEED, 0, n)
+        ai, bi, sc = W.make_group_items(SEED, rank * n, n)
         Pn = W.g1_subgroup_table()[ai]
         Hn = np.tile(np.array([[36, 31]], np.uint8), (n, 1))
         P = T(Pn)
@@ -562,9 +582,7 @@ def run_config(args):
         ms = timed(lambda: host._check(lib.pb_pairing_dev(C.c_void_p(P.data_ptr()), C.c_void_p(Q.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(n), sp)))
         m = 1 << 20
         Qh = Q[:m].cpu().numpy()
-        t0 = time.perf_counter()
-        oracle.pairing(Pn[:m], Qh, cores)
-        cpu_rate = m / (time.perf_counter() - t0)
+        cpu_rate = cpu_rate_of(lambda: oracle.pairing(Pn[:m], Qh, cores), m)
         int_ops = 592 * INT_OPS_PER_MUL + 143 * INT_OPS_PER_ADD
         line = {"metric": "pairings_per_s", "unit": "pairings/s", "value": n / (ms * 1e-3), "config": {
             "workload": "BASELINE config 4: 2^22 pairings e(aG, bH), a, b uniform on [1,17)"},
@@ -663,9 +681,15 @@ def run_config(args):
         line["roofline"]["peak"] = best / 1e12
         line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
     line["config"]["l2"] = "L2 flushed (256 MiB written) before every timed launch"
-    line.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
+    if world > 1:
+        line["value"] *= world      # every rank processed its own n items in the (max over ranks) time
+        line["config"]["parallelism"] = f"{world} GPUs, each its own item range of the same size, no data-path collective; time = max over ranks"
+    line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
                  "gpu_launches": gpu_launches, "vs_baseline": None, "scaling": "weak"})
-    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if rank == 0:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

@@ -13,12 +13,27 @@ constexpr int BLOCK = PB_BLOCK;   // threads per block for the heavy kernels (pr
 constexpr int BLOCK_LIGHT = 256;   // for the byte-streaming kernels
 constexpr int POLY_MAX = 64;
 
-// Every block derives its own inverse tables: x^15 mod 17 is the reference's table (hf.h:145-180),
-// x^99 mod 101 is literally what gf_inv computes (gf.h:159-162).  ~150 thread-level pow calls per
-// block, amortised over >= 128 items of >= several hundred instructions each.
+// The inverse tables: x^15 mod 17 is the reference's table (hf.h:145-180), x^99 mod 101 is literally what gf_inv computes
+// (gf.h:159-162).  They are evaluated at COMPILE time (constexpr, same square-and-multiply) into a 288-byte device constant
+// that every block copies into shared memory with 72 four-byte loads -- the light kernels (one pairing or one scalar
+// multiplication per thread) would otherwise spend ~10 % of their instructions re-deriving 288 powers per block.
+struct FieldTablesImage {
+  uint32_t w[sizeof(FieldTables) / 4];
+  constexpr FieldTablesImage() : w{} {
+    static_assert(sizeof(FieldTables) == 32 + 256, "FieldTables layout: inv17[32] then inv101[256]");
+    auto cpow = [](uint32_t base, uint32_t e, uint32_t p) {
+      uint32_t r = 1u;
+      while (e) { if (e & 1u) r = r * base % p; base = base * base % p; e >>= 1; }
+      return r;
+    };
+    for (uint32_t i = 0; i < 32; i++) w[i / 4] |= (i < 17u ? cpow(i, 15u, 17u) : 0u) << (8u * (i % 4u));
+    for (uint32_t i = 0; i < 256; i++) w[8 + i / 4] |= cpow(i % 101u, 99u, 101u) << (8u * (i % 4u));
+  }
+};
+__device__ const FieldTablesImage g_field_tables_image = FieldTablesImage();
 PB_D void build_field_tables(FieldTables& ft) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) ft.inv101[i] = (uint8_t)pow101((uint32_t)i % 101u, 99);
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) ft.inv17[i] = i < 17 ? (uint8_t)pow17((uint32_t)i, 15) : 0;
+  for (int i = threadIdx.x; i < (int)(sizeof(FieldTables) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&ft)[i] = g_field_tables_image.w[i];
 }
 
 PB_D G1 load_g1(const uint8_t* p) { return G1{p[0], p[1], p[2] != 0 ? 1u : 0u}; }
