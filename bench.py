@@ -15,6 +15,10 @@ e2e     proofs/s through the public host-pointer call pb_plonk_prove_verify: pin
         buffers out, H2D and D2H copies inside the timed region
 roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
 
+Other workloads (`--workload`, one JSON line each, L2 flushed before every timed launch; not what the driver runs):
+poly (BASELINE config 2), g1_mul (config 3) and pairing (config 4) -- the last two also under torchrun on N GPUs --,
+field (kernel family 1 and the tally kernel against HBM), prove_verify_fs (the headline batch in Fiat-Shamir mode).
+
 One JSON line on stdout (rank 0).
 """
 import argparse

@@ -67,7 +67,7 @@ PB_HD uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PB_HD uint32_t new17(int64_t v) { int64_t t = v % 17; if (t < 0) t += 17; return (uint32_t)t; }
 PB_HD uint32_t new101(int64_t v) { int64_t t = v % 101; if (t < 0) t += 101; return (uint32_t)t; }
 
-// Shared-memory look-up tables, filled once per block from the device context.
+// Shared-memory look-up tables, copied once per block from a compile-time image (kernels.cuh: build_field_tables).
 struct alignas(16) FieldTables {
   uint8_t inv17[32];    // hf_inverses, hf.h:145-180
   uint8_t inv101[256];  // (x mod 101)^99 mod 101, gf.h:159-162; entries 101..255 serve unreduced indices (curve.cuh: g1_add_c)

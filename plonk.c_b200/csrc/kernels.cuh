@@ -611,7 +611,7 @@ struct __align__(16) ProveSmem {
 // done_list / done_count (optional): indices of the completed proofs (status 0) are appended, one atomic per warp,
 // so that the verifier runs on a dense list; verdict (optional) gets 0xFF for every item that did not complete.
 #ifndef PB_PROVE_MINBLOCKS
-#define PB_PROVE_MINBLOCKS 5   // 96 registers (44 B of spills), 5 blocks of 128 threads per SM: measured best (profiles/r1/NOTES.md)
+#define PB_PROVE_MINBLOCKS 5   // 96 registers, 5 blocks of 128 threads per SM: measured best for every table variant (profiles/r1/NOTES.md)
 #endif
 // FS = true (Fiat-Shamir mode, transcript.cuh): `chal` is not read; chal_out (optional) [n][6] receives the challenges
 // drawn before the item's first exit (alpha beta gamma z v u), 0xFF for the ones not drawn.
