@@ -225,6 +225,8 @@ def test_host_pipeline_pinned_matches_pageable(host, W):
     ps.eq("pinned outputs, Fiat-Shamir", tuple(pin_out), want_fs)
     proofs, status = pk.prove(wit, rnd, chal)
     ps.eq("prove only", (proofs, status), want[:2])
+    ps.eq("prove only, Fiat-Shamir, pipelined (no challenge read-back)", pk.prove_fs(wit, rnd), want_fs[:2])
+    ps.eq("prove only, Fiat-Shamir, with challenge read-back", pk.prove_fs(wit, rnd, want_challenges=True)[:2], want_fs[:2])
 
 
 def test_prove_verify_fused_matches_separate_calls(host, W):
