@@ -376,6 +376,11 @@ def check_random_circuits(impl, oracle, W, n=4000, circuits=12, seed=4):
             assert (want[1] == 0).mean() > 0.3, "identity wiring should let proofs complete"
         eq(f"random circuit {k} verify", impl.plonk_verify_batch(circuit, g1s, g2, want[0], chal, u),
            oracle.plonk_verify_batch(circuit, g1s, g2, want[0], chal, u, 8))
+        if hasattr(impl, "plonk_prove_fs_batch") and hasattr(oracle, "plonk_prove_fs_batch") and k % 4 == 0:
+            m = min(n, 1500)                      # the circuit bytes enter the transcript seed
+            assert impl.fs_seed(circuit, g1s, g2) == oracle.fs_seed(circuit, g1s, g2)
+            eq(f"random circuit {k} prove (Fiat-Shamir)", impl.plonk_prove_fs_batch(circuit, g1s, g2, wit[:m], rnd[:m]),
+               oracle.plonk_prove_fs_batch(circuit, g1s, g2, wit[:m], rnd[:m], 8))
 
 
 def curve_points():
@@ -406,8 +411,15 @@ def check_whole_curve_srs(impl, oracle, W, n=6000, trials=6, seed=33):
         proofs = want[0].copy()
         k = rng.integers(0, n, n // 2)                                        # replace commitments by arbitrary curve points
         proofs[k[:, None], 3 * rng.integers(0, 9, n // 2)[:, None] + np.arange(3)] = pts[rng.integers(0, 101, n // 2)]
-        eq(f"whole-curve SRS {t} verify", impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u),
-           oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8))
+        want_v = oracle.plonk_verify_batch(C, g1s, g2, proofs, chal, u, 8)
+        eq(f"whole-curve SRS {t} verify", impl.plonk_verify_batch(C, g1s, g2, proofs, chal, u), want_v)
+        if hasattr(impl, "plonk_verdict_only"):
+            eq(f"whole-curve SRS {t} verdict only", impl.plonk_verdict_only(C, g1s, g2, proofs, chal, u), want_v[0])
+        if hasattr(impl, "plonk_prove_fs_batch") and hasattr(oracle, "plonk_prove_fs_batch") and t < 2:
+            eq(f"whole-curve SRS {t} prove (Fiat-Shamir)", impl.plonk_prove_fs_batch(C, g1s, g2, wit[:2000], rnd[:2000]),
+               oracle.plonk_prove_fs_batch(C, g1s, g2, wit[:2000], rnd[:2000], 8))
+            eq(f"whole-curve SRS {t} verify (Fiat-Shamir)", impl.plonk_verify_fs_batch(C, g1s, g2, proofs[:2000]),
+               oracle.plonk_verify_fs_batch(C, g1s, g2, proofs[:2000], 8))
 
 
 def check_protocol_golden(impl, W, n=2048):
