@@ -610,6 +610,9 @@ struct __align__(16) ProveSmem {
 // Tables = ProverTables (any SRS, the reference's order of additions) or ProverPairTables (canonical on-curve SRS).
 // done_list / done_count (optional): indices of the completed proofs (status 0) are appended, one atomic per warp,
 // so that the verifier runs on a dense list; verdict (optional) gets 0xFF for every item that did not complete.
+#ifndef PB_PROVE_PREFETCH
+#define PB_PROVE_PREFETCH 370   // blocks ahead (half a resident wave); measured: 0 -> 238.4 us, 370 -> 234.1, 740 -> 235.0, 1480 -> 238.8
+#endif
 #ifndef PB_PROVE_MINBLOCKS
 #define PB_PROVE_MINBLOCKS 5   // 96 registers, 5 blocks of 128 threads per SM: measured best for every table variant (profiles/r1/NOTES.md)
 #endif
@@ -627,6 +630,17 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   for (int k = tid; k < (int)(sizeof(Tables) / 4); k += PBLOCK)
     reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
   const size_t first = (size_t)blockIdx.x * PBLOCK;
+#if PB_PROVE_PREFETCH
+  {
+    // pull the inputs of the block that will take this block's slot next (~ one resident wave ahead) into L2, so that its
+    // staging loads do not wait on DRAM: 26 lines of 128 bytes, one prefetch per lane
+    const size_t pf = first + (size_t)PB_PROVE_PREFETCH * PBLOCK;
+    if (pf + PBLOCK <= n && tid < 26) {
+      const uint8_t* a = tid < 12 ? wit + pf * 12 + tid * 128 : tid < 21 ? rnd + pf * 9 + (tid - 12) * 128 : (FS ? nullptr : chal + pf * 5 + (tid - 21) * 128);
+      if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+#endif
   stage_in<12, PBLOCK>(sm.wit, wit, first, n);
   stage_in<9, PBLOCK>(sm.rnd, rnd, first, n);
   if constexpr (!FS) stage_in<5, PBLOCK>(sm.chal, chal, first, n);
