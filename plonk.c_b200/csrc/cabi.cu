@@ -890,6 +890,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   for (uint32_t i = 0; i < 256; i++) pt.ft.inv101[i] = (uint8_t)pow101(i % 101u, 99);
   for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) pt.pow17[zz][k] = (uint8_t)pow17(zz, k);
+  for (uint32_t i = 0; i < MOD17_RANGE; i++) pt.mod17[i] = (uint8_t)(i % 17u);
   if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
   cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice);
   {
@@ -908,6 +909,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
       memset(&ppt, 0, sizeof ppt);
       ppt.ft = pt.ft;
       memcpy(ppt.pow17, pt.pow17, sizeof ppt.pow17);
+      memcpy(ppt.mod17, pt.mod17, sizeof ppt.mod17);
       uint32_t *d_single = nullptr, *d_pairs = nullptr;
       if (cudaMalloc(&d_single, sizeof pt.T) != cudaSuccess || cudaMalloc(&d_pairs, sizeof ppt.T2) != cudaSuccess)
         return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
@@ -942,6 +944,7 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
         memset(&wt, 0, sizeof wt);
         wt.ft = pt.ft;
         memcpy(wt.pow17, pt.pow17, sizeof wt.pow17);
+        memcpy(wt.mod17, pt.mod17, sizeof wt.mod17);
         wt.T6 = t6;
         wt.T3 = t3 + 2u * (size_t)WIDE_T3_ENTRIES;
         cudaMemcpy(c->d_wide_tables, &wt, sizeof wt, cudaMemcpyHostToDevice);

@@ -22,6 +22,14 @@ namespace pb {
 
 constexpr int PROVER_SRS_ROWS = 9;   // the prover never touches more than nine SRS points (|W_z| <= 9)
 
+// Small-range reduction table: mod17[x] = x mod 17 for x < 2048.  About three quarters of the prover's reductions are of
+// values below 2048 (single products, sums of a few); a shared-memory look-up replaces their IMAD.HI + IMAD pair, and the
+// integer multiplier is the pipe this kernel loads most.
+constexpr uint32_t MOD17_RANGE = 2048u;
+#ifndef PB_PROVE_MODTAB
+#define PB_PROVE_MODTAB 1
+#endif
+
 // Per-circuit constants, passed to kernels BY VALUE (kernel parameters live in the constant bank,
 // so a uniform read is an instruction operand, not a load).
 struct CircuitConst {
@@ -44,6 +52,7 @@ struct ProverTables {
   // computed with the reference's own double-and-add on the device at context creation.
   // Rows >= srs_len are the identity {0,0,1}.
   uint32_t T[PROVER_SRS_ROWS][17];
+  uint8_t mod17[MOD17_RANGE];
 };
 
 // Fast-path tables, used when every SRS point is a canonically encoded point of E(F_101) (context creation checks
@@ -57,6 +66,7 @@ struct ProverPairTables {
   FieldTables ft;
   uint8_t pow17[17][20];
   uint32_t T2[PROVER_PAIR_ROWS][289];
+  uint8_t mod17[MOD17_RANGE];
 };
 
 // Widest fast path (same eligibility and the same exactness argument as the pair tables): the commitment of a polynomial
@@ -73,6 +83,7 @@ struct ProverWideTables {
   uint8_t pow17[17][20];
   const uint16_t* T6;   // [17^6], rows 0..5
   const uint16_t* T3;   // [17^3], rows 6..8
+  uint8_t mod17[MOD17_RANGE];
 };
 PB_HD uint32_t pack_g1_16(const G1& p) { return p.x | p.y << 7 | p.inf << 14; }
 PB_HD G1 unpack_g1_16(uint32_t w) { return G1{w & 0x7Fu, (w >> 7) & 0x7Fu, w >> 14}; }
@@ -129,6 +140,33 @@ PB_HD void interpolate(const CircuitConst& cc, const uint32_t (&v)[4], uint32_t 
     for (int c = 0; c < 4; c++) s += cc.vinv[r][c] * v[c];
     out[r] = red17(s);
   }
+}
+// the same with the small-range reducer (row sums are < 4 * 16 * 16 = 1024)
+template <typename Tables>
+PB_HD uint32_t red_small(const Tables& tb, uint32_t x) {
+#if PB_PROVE_MODTAB
+  return tb.mod17[x];
+#else
+  return red17(x);
+#endif
+}
+template <typename Tables>
+PB_HD void interpolate_s(const Tables& tb, const CircuitConst& cc, const uint32_t (&v)[4], uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    uint32_t s = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) s += cc.vinv[r][c] * v[c];
+    out[r] = red_small(tb, s);
+  }
+}
+template <typename Tables, int N>
+PB_HD uint32_t dot_s(const Tables& tb, const uint32_t (&a)[N], const uint32_t* zp) {
+  static_assert(N <= 7, "more than seven terms can exceed the table range");
+  uint32_t s = 0u;
+#pragma unroll
+  for (int i = 0; i < N; i++) s += a[i] * zp[i];
+  return red_small(tb, s);
 }
 // KZG commitment (srs.h:53-68) against the fixed-base table: acc = sum_{i < len} T[i][c_i], same order
 // of additions as the reference's loop, and the same NUMBER of additions: the loop must stop at the
@@ -194,6 +232,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   constexpr uint32_t K1 = 2u, K2 = 3u;                  // plonk.h:13-14
   constexpr uint32_t H[4] = {1u, 4u, 16u, 13u};         // omega^i, omega = 4 (plonk.h:12,69-71)
   constexpr uint32_t OMEGA_POW[7] = {1u, 4u, 16u, 13u, 1u, 4u, 16u};
+  auto rs = [&](uint32_t x) -> uint32_t { return red_small(tb, x); };   // x < 2048 at every use (bounds at the sites)
 
   // ---- step 1: constraints_satisfy (constraints.h:145-171), inside the assert of plonk.h:231
   bool unsat = false;
@@ -206,9 +245,9 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
 
   // ---- round 1 (plonk.h:265-301): a = f_a + (b2 + b1 x) Z_H, Z_H = x^4 - 1 (poly_z(H), plonk.h:116)
   uint32_t fa[4], fb[4], fc[4];
-  interpolate(cc, wa, fa);
-  interpolate(cc, wb, fb);
-  interpolate(cc, wc, fc);
+  interpolate_s(tb, cc, wa, fa);
+  interpolate_s(tb, cc, wb, fb);
+  interpolate_s(tb, cc, wc, fc);
   uint32_t A[6] = {sub17(fa[0], rnd[1]), sub17(fa[1], rnd[0]), fa[2], fa[3], rnd[1], rnd[0]};
   uint32_t B[6] = {sub17(fb[0], rnd[3]), sub17(fb[1], rnd[2]), fb[2], fb[3], rnd[3], rnd[2]};
   uint32_t C[6] = {sub17(fc[0], rnd[5]), sub17(fc[1], rnd[4]), fc[2], fc[3], rnd[5], rnd[4]};
@@ -227,21 +266,21 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     uint32_t w = H[i];
-    uint32_t d0 = red17(wa[i] + beta * w + gamma);
-    uint32_t d1 = red17(wb[i] + beta * (K1 * w) + gamma);
-    uint32_t d2 = red17(wc[i] + beta * (K2 * w) + gamma);
-    uint32_t n0 = red17(wa[i] + beta * cc.sig[0][i] + gamma);
-    uint32_t n1 = red17(wb[i] + beta * cc.sig[1][i] + gamma);
-    uint32_t n2 = red17(wc[i] + beta * cc.sig[2][i] + gamma);
-    uint32_t den = red17(red17(d0 * d1) * d2);
-    uint32_t num = red17(red17(n0 * n1) * n2);
-    uint32_t frac = red17(den * inv17(tb.ft, num));        // hf_div: 1/0 = 0 (hf.h:188-203)
-    acc[i + 1] = red17(acc[i] * frac);
+    uint32_t d0 = rs(wa[i] + beta * w + gamma);             // every value in this loop is < 16 + 16 * 48 + 16
+    uint32_t d1 = rs(wb[i] + beta * (K1 * w) + gamma);
+    uint32_t d2 = rs(wc[i] + beta * (K2 * w) + gamma);
+    uint32_t n0 = rs(wa[i] + beta * cc.sig[0][i] + gamma);
+    uint32_t n1 = rs(wb[i] + beta * cc.sig[1][i] + gamma);
+    uint32_t n2 = rs(wc[i] + beta * cc.sig[2][i] + gamma);
+    uint32_t den = rs(rs(d0 * d1) * d2);
+    uint32_t num = rs(rs(n0 * n1) * n2);
+    uint32_t frac = rs(den * inv17(tb.ft, num));        // hf_div: 1/0 = 0 (hf.h:188-203)
+    acc[i + 1] = rs(acc[i] * frac);
   }
   uint32_t accx[4];
-  interpolate(cc, acc, accx);
+  interpolate_s(tb, cc, acc, accx);
   // plonk.h:366-368: acc_x(omega^n) == 1, omega^4 = 1
-  const bool bad_acc = red17(accx[0] + accx[1] + accx[2] + accx[3]) != 1u;
+  const bool bad_acc = rs(accx[0] + accx[1] + accx[2] + accx[3]) != 1u;
   uint32_t Z[7] = {sub17(accx[0], rnd[8]), sub17(accx[1], rnd[7]), sub17(accx[2], rnd[6]), accx[3],
                    rnd[8], rnd[7], rnd[6]};
   const uint32_t len_z = canon_len(Z);
@@ -267,12 +306,12 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
 #pragma unroll
     for (int i = 0; i < 6; i++) { xa[i] = A[i]; xb[i] = B[i]; xc[i] = C[i]; }
     xa[0] += gamma; xa[1] += beta;
-    xb[0] += gamma; xb[1] += red17(beta * K1);
-    xc[0] += gamma; xc[1] += red17(beta * K2);
+    xb[0] += gamma; xb[1] += rs(beta * K1);
+    xc[0] += gamma; xc[1] += rs(beta * K2);
 #pragma unroll
-    for (int i = 0; i < 6; i++) xa[i] = red17(xa[i] * alpha);
-    xb[0] = red17(xb[0]); xb[1] = red17(xb[1]);
-    xc[0] = red17(xc[0]); xc[1] = red17(xc[1]);
+    for (int i = 0; i < 6; i++) xa[i] = rs(xa[i] * alpha);      // < 33 * 16
+    xb[0] = rs(xb[0]); xb[1] = rs(xb[1]);
+    xc[0] = rs(xc[0]); xc[1] = rs(xc[1]);
     uint32_t p1[11], p2[16];
     zero(p1); zero(p2);
     mul_acc<6, 6>(p1, xa, xb);      // < 6 * 2^8
@@ -281,7 +320,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   }
   uint32_t Zw[7];                   // z(omega x), plonk.h:466-470
 #pragma unroll
-  for (int i = 0; i < 7; i++) Zw[i] = red17(Z[i] * OMEGA_POW[i]);
+  for (int i = 0; i < 7; i++) Zw[i] = rs(Z[i] * OMEGA_POW[i]);
   // The second opening polynomial W_zw = (z(x) - z(omega z)) / (x - z omega) (plonk.h:612-617, 621) needs only z(x) and
   // the evaluation point.  With caller-supplied challenges it is computed and committed HERE, so that its addition
   // chain overlaps the polynomial products of round 3; in Fiat-Shamir mode z exists only after round 3.
@@ -291,13 +330,13 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
     uint32_t zq[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) zq[i] = tb.pow17[z][i];
-    zw_z = dot(Zw, zq);
-    const uint32_t zo = red17(z * 4u);
+    zw_z = dot_s(tb, Zw, zq);                                // 7 terms < 7 * 256
+    const uint32_t zo = rs(z * 4u);
     uint32_t Wzw[6];
     Wzw[5] = Z[6];
 #pragma unroll
-    for (int j = 5; j >= 1; j--) Wzw[j - 1] = red17(Z[j] + zo * Wzw[j]);
-    bad_rem2 = red17(Z[0] + 17u - zw_z + zo * Wzw[0]) != 0u;
+    for (int j = 5; j >= 1; j--) Wzw[j - 1] = rs(Z[j] + zo * Wzw[j]);
+    bad_rem2 = rs(Z[0] + 17u - zw_z + zo * Wzw[0]) != 0u;
     len_wzw = canon_len(Wzw);
     out.pts[8] = commit(tb, Wzw, len_wzw);
   };
@@ -314,9 +353,9 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
     }
     ya[0] += gamma; yb[0] += gamma; yc[0] += gamma;
 #pragma unroll
-    for (int i = 0; i < 6; i++) ya[i] = red17(red17(ya[i]) * alpha);
+    for (int i = 0; i < 6; i++) ya[i] = rs(rs(ya[i]) * alpha);    // ya < 16 + 256 + 16
 #pragma unroll
-    for (int i = 0; i < 4; i++) { yb[i] = red17(yb[i]); yc[i] = red17(yc[i]); }
+    for (int i = 0; i < 4; i++) { yb[i] = rs(yb[i]); yc[i] = rs(yc[i]); }
     uint32_t p1[11], p2[16], t3[22];
     zero(p1); zero(p2); zero(t3);
     mul_acc<6, 6>(p1, ya, yb);
@@ -327,13 +366,13 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
     for (int i = 0; i < 22; i++) tn[i] += BIG - t3[i];
   }
   {  // t4 = alpha^2 (z(x) - 1) L1(x)
-    uint32_t a2 = red17(alpha * alpha);
+    uint32_t a2 = rs(alpha * alpha);
     uint32_t zm[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) zm[i] = Z[i];
     zm[0] += 16u;
 #pragma unroll
-    for (int i = 0; i < 7; i++) zm[i] = red17(zm[i] * a2);
+    for (int i = 0; i < 7; i++) zm[i] = rs(zm[i] * a2);         // < 32 * 16
     mul_acc<7, 4>(tn, zm, cc.l1);
   }
   reduce(tn);
@@ -342,7 +381,8 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   uint32_t T[18];
 #pragma unroll
   for (int j = 17; j >= 0; j--) T[j] = tn[j + 4] + (j + 4 < 18 ? T[j + 4] : 0u);   // < 5 * 17
-  reduce(T);
+#pragma unroll
+  for (int j = 0; j < 18; j++) T[j] = rs(T[j]);
   bool bad_rem = false;                                     // plonk.h:507-510
 #pragma unroll
   for (int k = 0; k < 4; k++) bad_rem |= add17(tn[k], T[k]) != 0u;
@@ -365,19 +405,19 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   uint32_t zp[18];
 #pragma unroll
   for (int i = 0; i < 18; i++) zp[i] = tb.pow17[z][i];
-  const uint32_t a_z = dot(A, zp), b_z = dot(B, zp), c_z = dot(C, zp);
-  const uint32_t s1_z = dot(cc.SP[0], zp), s2_z = dot(cc.SP[1], zp);
-  const uint32_t t_z = dot(T, zp), l1_z = dot(cc.l1, zp);
-  const uint32_t a2 = red17(alpha * alpha);
-  const uint32_t bz = red17(beta * z);
-  const uint32_t e_a = red17(a_z + bz + gamma);
-  const uint32_t e_b = red17(b_z + K1 * bz + gamma);
-  const uint32_t e_c = red17(c_z + K2 * bz + gamma);
-  const uint32_t k2 = red17(red17(red17(e_a * e_b) * e_c) * alpha);                      // r2 scalar
-  const uint32_t f_a = red17(a_z + beta * s1_z + gamma), f_b = red17(b_z + beta * s2_z + gamma);
-  const uint32_t k3 = red17(red17(red17(f_a * f_b) * alpha) * red17(beta * zw_z));       // r3 scalar
-  const uint32_t k4 = red17(l1_z * a2);                                                   // r4 scalar
-  const uint32_t abz = red17(a_z * b_z);
+  const uint32_t a_z = dot_s(tb, A, zp), b_z = dot_s(tb, B, zp), c_z = dot_s(tb, C, zp);   // 6 terms < 6 * 256
+  const uint32_t s1_z = dot_s(tb, cc.SP[0], zp), s2_z = dot_s(tb, cc.SP[1], zp);
+  const uint32_t t_z = dot(T, zp), l1_z = dot_s(tb, cc.l1, zp);
+  const uint32_t a2 = rs(alpha * alpha);
+  const uint32_t bz = rs(beta * z);
+  const uint32_t e_a = rs(a_z + bz + gamma);
+  const uint32_t e_b = rs(b_z + K1 * bz + gamma);
+  const uint32_t e_c = rs(c_z + K2 * bz + gamma);
+  const uint32_t k2 = rs(rs(rs(e_a * e_b) * e_c) * alpha);                      // r2 scalar
+  const uint32_t f_a = rs(a_z + beta * s1_z + gamma), f_b = rs(b_z + beta * s2_z + gamma);
+  const uint32_t k3 = rs(rs(rs(f_a * f_b) * alpha) * rs(beta * zw_z));       // r3 scalar
+  const uint32_t k4 = rs(l1_z * a2);                                                   // r4 scalar
+  const uint32_t abz = rs(a_z * b_z);
   uint32_t R[10];
   zero(R);
   {
@@ -400,7 +440,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   }
 
   // ---- round 5 (plonk.h:582-621): opening polynomials
-  const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
+  const uint32_t v2 = rs(v * v), v3 = rs(v2 * v), v4 = rs(v3 * v), v5 = rs(v4 * v), v6 = rs(v5 * v);
   uint32_t wn[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) wn[i] = v * R[i];
@@ -416,8 +456,8 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   uint32_t Wz[9];
   Wz[8] = wn[9];
 #pragma unroll
-  for (int j = 8; j >= 1; j--) Wz[j - 1] = red17(wn[j] + z * Wz[j]);
-  const bool bad_rem1 = red17(wn[0] + z * Wz[0]) != 0u;
+  for (int j = 8; j >= 1; j--) Wz[j - 1] = rs(wn[j] + z * Wz[j]);
+  const bool bad_rem1 = rs(wn[0] + z * Wz[0]) != 0u;
   const uint32_t len_wz = canon_len(Wz);
   const uint32_t len_w = umax(len_wz, len_wzw);
   out.pts[7] = commit(tb, Wz, len_wz);

@@ -104,6 +104,7 @@ void hc_prove(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wi
   ProverTables tb;
   tb.ft = make_ft();
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
+  for (uint32_t i = 0; i < MOD17_RANGE; i++) tb.mod17[i] = (uint8_t)(i % 17u);
   memcpy(tb.T, table, sizeof tb.T);
   prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
 }
@@ -115,6 +116,7 @@ void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8
   static ProverPairTables tb;
   tb.ft = make_ft();
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
+  for (uint32_t i = 0; i < MOD17_RANGE; i++) tb.mod17[i] = (uint8_t)(i % 17u);
   for (uint32_t k = 0; k < PROVER_PAIR_ROWS * 289u; k++) {
     const uint32_t j = k / 289u, c0 = (k % 289u) / 17u, c1 = k % 17u;
     const G1 p = unpack_g1(table[(2 * j) * 17 + c0]);
@@ -153,6 +155,7 @@ void hc_prove_wide(const uint32_t* cc_words, const uint32_t* table, const uint8_
   ProverWideTables tb;
   tb.ft = ft;
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);
+  for (uint32_t i = 0; i < MOD17_RANGE; i++) tb.mod17[i] = (uint8_t)(i % 17u);
   tb.T6 = store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
   tb.T3 = store.data() + 2u * (size_t)WIDE_T3_ENTRIES;
   prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
