@@ -228,6 +228,54 @@ uint64_t hc_check_shared_final_exp(uint32_t step) {
   }
   return bad;
 }
+// The canonical-domain variants of the fast paths against the any-input functions, exhaustively on their domain:
+// every pair of canonically encoded points of E(F_101) (101 finite points + the identity) for g1_add_c / g1_double_c,
+// and every such point against every G2 byte pair (x, y < 101) for miller17_c.  Returns the number of mismatches.
+uint64_t hc_check_canonical_variants(const uint8_t* pts /*[np][3]*/, uint32_t np) {
+  const FieldTables ft = make_ft();
+  uint64_t bad = 0;
+  for (uint32_t i = 0; i < np; i++) {
+    const G1 a = ld(pts + 3 * i);
+    const G1 d0 = g1_double(ft, a), d1 = g1_double_c(ft, a);
+    bad += d0.x != d1.x || d0.y != d1.y || d0.inf != d1.inf;
+    for (uint32_t j = 0; j < np; j++) {
+      const G1 b = ld(pts + 3 * j);
+      const G1 r0 = g1_add(ft, a, b), r1 = g1_add_c(ft, a, b);
+      bad += r0.x != r1.x || r0.y != r1.y || r0.inf != r1.inf;
+    }
+    for (uint32_t q = 0; q < 101u * 101u; q++) {
+      const G2 Q{q / 101u, q % 101u};
+      const GT f0 = miller17(ft, a, Q), f1 = miller17_c(ft, a, Q);
+      bad += f0.a != f1.a || f0.b != f1.b;
+    }
+  }
+  return bad;
+}
+// The premise of every table path: on canonically encoded curve points the reference's g1_add IS an abelian group law
+// with one encoding per element -- commutative and associative as TRIPLES, identity {0,0,1} neutral.  All pairs, all triples.
+uint64_t hc_check_group_law(const uint8_t* pts /*[np][3]*/, uint32_t np) {
+  const FieldTables ft = make_ft();
+  auto eq = [](const G1& p, const G1& q) { return p.x == q.x && p.y == q.y && p.inf == q.inf; };
+  uint64_t bad = 0;
+  const G1 id = g1_identity();
+  for (uint32_t i = 0; i < np; i++) {
+    const G1 a = ld(pts + 3 * i);
+    bad += !eq(g1_add(ft, a, id), a) || !eq(g1_add(ft, id, a), a);
+    bad += !eq(g1_add(ft, a, g1_neg(a)), id);
+    bad += !eq(g1_add(ft, a, a), g1_double(ft, a));
+    for (uint32_t j = 0; j < np; j++) {
+      const G1 b = ld(pts + 3 * j);
+      const G1 ab = g1_add(ft, a, b);
+      bad += !eq(ab, g1_add(ft, b, a));
+      bad += !g1_is_on_curve(ab) || ab.x > 100u || ab.y > 100u || (ab.inf && (ab.x | ab.y));   // closed, canonical
+      for (uint32_t k = 0; k < np; k++) {
+        const G1 c = ld(pts + 3 * k);
+        bad += !eq(g1_add(ft, ab, c), g1_add(ft, a, g1_add(ft, b, c)));
+      }
+    }
+  }
+  return bad;
+}
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]
 void hc_verify(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {

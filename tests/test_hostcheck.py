@@ -52,6 +52,32 @@ def test_hostcheck_shared_final_exponentiation(hc):
     assert hc.lib.hc_check_shared_final_exp(C.c_uint32(5)) == 0
 
 
+def test_hostcheck_canonical_domain_variants(hc):
+    """g1_add_c / g1_double_c / miller17_c (the fast verifier's leaner group law and Miller loop) against the any-input
+    functions on their whole domain: all 102 x 102 pairs of canonical curve points, all 102 x 10201 (P, Q) pairs."""
+    import ctypes as C
+    import numpy as np
+    pts = np.concatenate([ps.curve_points(), np.array([[0, 0, 1]], np.uint8)])
+    assert pts.shape == (102, 3)
+    hc.lib.hc_check_canonical_variants.restype = C.c_uint64
+    assert hc.lib.hc_check_canonical_variants(pts.ctypes.data_as(C.c_void_p), C.c_uint32(len(pts))) == 0
+
+
+def test_hostcheck_group_law_on_canonical_points(hc, oracle):
+    """The exactness argument of the pair / wide / verifier tables and of the joint double-and-add: restricted to
+    canonically encoded points of E(F_101), g1_add (which test_hostcheck_groups pins to the reference for any input) is
+    commutative, associative, closed and has {0,0,1} as its neutral element -- as byte triples.  All 102^3 triples."""
+    import ctypes as C
+    import numpy as np
+    pts = np.concatenate([ps.curve_points(), np.array([[0, 0, 1]], np.uint8)])
+    hc.lib.hc_check_group_law.restype = C.c_uint64
+    assert hc.lib.hc_check_group_law(pts.ctypes.data_as(C.c_void_p), C.c_uint32(len(pts))) == 0
+    # and the function being exercised is the reference's, on exactly these inputs
+    a = np.repeat(pts, len(pts), axis=0)
+    b = np.tile(pts, (len(pts), 1))
+    ps.eq("g1_add on all canonical pairs", hc.g1_op(0, a, b), oracle.g1_op(0, a, b))
+
+
 def test_hostcheck_wide_tables(oracle, W):
     """One-look-up commitments (T6, 17^6 entries): same eligibility as the pair tables, byte-identical output required."""
     import util
