@@ -127,31 +127,43 @@ void hc_prove_pairs(const uint32_t* cc_words, const uint32_t* table, const uint8
   prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
 }
 // widest fast path: T3 / T6 built exactly as wide_t3_kernel / wide_t6_kernel do (cached per single-point table)
+static std::vector<uint16_t> g_wide_store;
+static void wide_build(const uint32_t* table) {
+  static uint32_t cached[PROVER_SRS_ROWS * 17];
+  static bool have = false;
+  const FieldTables ft = make_ft();
+  if (have && memcmp(cached, table, sizeof cached) == 0) return;
+  g_wide_store.assign(3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES, 0);
+  for (uint32_t k = 0; k < 3u * WIDE_T3_ENTRIES; k++) {
+    const uint32_t t = k / WIDE_T3_ENTRIES, e = k % WIDE_T3_ENTRIES;
+    const uint32_t c[3] = {e % 17u, (e / 17u) % 17u, e / 289u};
+    G1 acc = g1_identity();
+    for (uint32_t i = 0; i < 3; i++) acc = g1_add(ft, acc, unpack_g1(table[(3u * t + i) * 17u + c[i]]));
+    g_wide_store[k] = (uint16_t)pack_g1_16(acc);
+  }
+  uint16_t* t6 = g_wide_store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
+  for (uint32_t k = 0; k < WIDE_T6_ENTRIES; k++) {
+    const G1 r = g1_add(ft, unpack_g1_16(g_wide_store[k % WIDE_T3_ENTRIES]), unpack_g1_16(g_wide_store[WIDE_T3_ENTRIES + k / WIDE_T3_ENTRIES]));
+    t6[k] = (uint16_t)pack_g1_16(r);
+  }
+  memcpy(cached, table, sizeof cached);
+  have = true;
+}
+// every entry of T6 (17^6) and of the rows-6..8 T3 (17^3) unpacked to (x, y, infinite) triples, for comparison with srs_eval_at_s
+void hc_wide_tables(const uint32_t* table, uint8_t* t6_out /*[17^6][3]*/, uint8_t* t3_out /*[17^3][3]*/) {
+  wide_build(table);
+  const uint16_t* t6 = g_wide_store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
+  const uint16_t* t3 = g_wide_store.data() + 2u * (size_t)WIDE_T3_ENTRIES;
+  for (uint32_t k = 0; k < WIDE_T6_ENTRIES; k++) st(t6_out + 3 * (size_t)k, unpack_g1_16(t6[k]));
+  for (uint32_t k = 0; k < WIDE_T3_ENTRIES; k++) st(t3_out + 3 * (size_t)k, unpack_g1_16(t3[k]));
+}
 void hc_prove_wide(const uint32_t* cc_words, const uint32_t* table, const uint8_t* wit, const uint8_t* rnd, const uint8_t* chal,
                    uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
   CircuitConst cc;
   memcpy(&cc, cc_words, sizeof cc);
-  static std::vector<uint16_t> store;
-  static uint32_t cached[PROVER_SRS_ROWS * 17];
-  static bool have = false;
+  wide_build(table);
+  std::vector<uint16_t>& store = g_wide_store;
   const FieldTables ft = make_ft();
-  if (!have || memcmp(cached, table, sizeof cached) != 0) {
-    store.assign(3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES, 0);
-    for (uint32_t k = 0; k < 3u * WIDE_T3_ENTRIES; k++) {
-      const uint32_t t = k / WIDE_T3_ENTRIES, e = k % WIDE_T3_ENTRIES;
-      const uint32_t c[3] = {e % 17u, (e / 17u) % 17u, e / 289u};
-      G1 acc = g1_identity();
-      for (uint32_t i = 0; i < 3; i++) acc = g1_add(ft, acc, unpack_g1(table[(3u * t + i) * 17u + c[i]]));
-      store[k] = (uint16_t)pack_g1_16(acc);
-    }
-    uint16_t* t6 = store.data() + 3u * (size_t)WIDE_T3_ENTRIES;
-    for (uint32_t k = 0; k < WIDE_T6_ENTRIES; k++) {
-      const G1 r = g1_add(ft, unpack_g1_16(store[k % WIDE_T3_ENTRIES]), unpack_g1_16(store[WIDE_T3_ENTRIES + k / WIDE_T3_ENTRIES]));
-      t6[k] = (uint16_t)pack_g1_16(r);
-    }
-    memcpy(cached, table, sizeof cached);
-    have = true;
-  }
   ProverWideTables tb;
   tb.ft = ft;
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) tb.pow17[zz][k] = (uint8_t)pow17(zz, k);

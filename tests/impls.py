@@ -251,6 +251,14 @@ class HostcheckImpl:
         # fast: False = sequential tables (any SRS); True = pair tables; "wide" = one-look-up T6 tables (prover only)
         return {False: self.lib.hc_prove, True: self.lib.hc_prove_pairs, "wide": self.lib.hc_prove_wide}[self.fast]
 
+    def wide_tables(self, g1s):
+        """(T6 [17^6][3], T3 [17^3][3]) as the wide-table builder produces them for this SRS"""
+        tb = self._table(np.ascontiguousarray(g1s, np.uint8))
+        t6 = np.zeros((17 ** 6, 3), np.uint8)
+        t3 = np.zeros((17 ** 3, 3), np.uint8)
+        self.lib.hc_wide_tables(tb.ctypes.data_as(C.c_void_p), _p(t6), _p(t3))
+        return t6, t3
+
     def _cc_words(self, circuit, srs_len, fs_seed=0):
         o = self.o
         circuit = np.asarray(circuit, np.uint8)

@@ -78,6 +78,30 @@ def test_hostcheck_group_law_on_canonical_points(hc, oracle):
     ps.eq("g1_add on all canonical pairs", hc.g1_op(0, a, b), oracle.g1_op(0, a, b))
 
 
+def test_hostcheck_wide_table_is_srs_eval_at_s_everywhere(hc, oracle, W):
+    """EVERY entry of the one-look-up commitment table against the oracle's srs_eval_at_s: all 17^6 = 24 137 569
+    six-coefficient polynomials over SRS rows 0..5, all 17^3 over rows 6..8 (generator SRS, n = 9)."""
+    import numpy as np
+    g1s, g2 = W.generator_srs(9)
+    t6, t3 = hc.wide_tables(g1s)
+    idx = np.arange(17 ** 6, dtype=np.int64)
+    polys = np.empty((17 ** 6, 6), np.uint8)
+    for k in range(6):
+        polys[:, k] = idx % 17
+        idx //= 17
+    want, st = oracle.srs_eval_at_s(g1s, g2, polys, np.full(17 ** 6, 6, np.uint8), 8)
+    assert (st == 0).all()
+    ps.eq("T6 == srs_eval_at_s on every 6-coefficient polynomial", t6, want)
+    idx = np.arange(17 ** 3, dtype=np.int64)
+    hi = np.zeros((17 ** 3, 9), np.uint8)
+    for k in range(3):
+        hi[:, 6 + k] = idx % 17
+        idx //= 17
+    want3, st3 = oracle.srs_eval_at_s(g1s, g2, hi, np.full(17 ** 3, 9, np.uint8), 8)
+    assert (st3 == 0).all()
+    ps.eq("T3 == srs_eval_at_s on rows 6..8", t3, want3)
+
+
 def test_hostcheck_wide_tables(oracle, W):
     """One-look-up commitments (T6, 17^6 entries): same eligibility as the pair tables, byte-identical output required."""
     import util
