@@ -78,6 +78,17 @@ def test_hostcheck_group_law_on_canonical_points(hc, oracle):
     ps.eq("g1_add on all canonical pairs", hc.g1_op(0, a, b), oracle.g1_op(0, a, b))
 
 
+def test_hostcheck_pairing_on_every_canonical_input(hc, oracle):
+    """pairing17 (one doubling chain, shared squarings, f^600 = conj(f^5) f^95) against the oracle's pairing for EVERY
+    canonically encoded G1 point (101 curve points + identity) and EVERY G2 byte pair below 101: 1 040 502 pairings."""
+    import numpy as np
+    pts = np.concatenate([ps.curve_points(), np.array([[0, 0, 1]], np.uint8)])
+    q = np.stack(np.meshgrid(np.arange(101, dtype=np.uint8), np.arange(101, dtype=np.uint8), indexing="ij"), -1).reshape(-1, 2)
+    P = np.repeat(pts, len(q), axis=0)
+    Q = np.tile(q, (len(pts), 1))
+    ps.eq("pairing, all canonical (P, Q)", hc.pairing(P, Q), oracle.pairing(P, Q, 8))
+
+
 def test_hostcheck_wide_table_is_srs_eval_at_s_everywhere(hc, oracle, W):
     """EVERY entry of the one-look-up commitment table against the oracle's srs_eval_at_s: all 17^6 = 24 137 569
     six-coefficient polynomials over SRS rows 0..5, all 17^3 over rows 6..8 (generator SRS, n = 9)."""
