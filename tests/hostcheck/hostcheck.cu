@@ -288,6 +288,18 @@ uint64_t hc_check_group_law(const uint8_t* pts /*[np][3]*/, uint32_t np) {
   }
   return bad;
 }
+// Barrett reductions over their whole claimed range (field.cuh: red17 exact below 2^28, red101 below 2^26): the number of
+// x with red(x) != x % p.  Also reports, through *first_bad, the smallest x >= the claimed bound at which each formula
+// first fails (so the stated bounds can be seen to be safe, not tight guesses).
+uint64_t hc_check_barrett(uint32_t* first_bad17, uint32_t* first_bad101) {
+  uint64_t bad = 0;
+  for (uint32_t x = 0; x < (1u << 28); x++) bad += red17(x) != x % 17u;
+  for (uint32_t x = 0; x < (1u << 26); x++) bad += red101(x) != x % 101u;
+  *first_bad17 = 0; *first_bad101 = 0;
+  for (uint64_t x = 1ull << 28; x < (1ull << 32); x++) if (red17((uint32_t)x) != (uint32_t)x % 17u) { *first_bad17 = (uint32_t)x; break; }
+  for (uint64_t x = 1ull << 26; x < (1ull << 32); x++) if (red101((uint32_t)x) != (uint32_t)x % 101u) { *first_bad101 = (uint32_t)x; break; }
+  return bad;
+}
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]
 void hc_verify(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {

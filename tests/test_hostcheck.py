@@ -78,6 +78,18 @@ def test_hostcheck_group_law_on_canonical_points(hc, oracle):
     ps.eq("g1_add on all canonical pairs", hc.g1_op(0, a, b), oracle.g1_op(0, a, b))
 
 
+def test_hostcheck_barrett_reductions_over_their_whole_range(hc):
+    """red17 / red101 (multiply-high Barrett step, field.cuh) against `%` for EVERY x below the bounds the kernels rely on
+    (2^28 resp. 2^26), and where above those bounds the formulas first fail."""
+    import ctypes as C
+    b17, b101 = C.c_uint32(), C.c_uint32()
+    hc.lib.hc_check_barrett.restype = C.c_uint64
+    assert hc.lib.hc_check_barrett(C.byref(b17), C.byref(b101)) == 0
+    assert b17.value == 0 or b17.value >= 1 << 28
+    assert b101.value == 0 or b101.value >= 1 << 26
+    print("first failing x: red17", b17.value, "red101", b101.value)
+
+
 def test_hostcheck_pairing_on_every_canonical_input(hc, oracle):
     """pairing17 (one doubling chain, shared squarings, f^600 = conj(f^5) f^95) against the oracle's pairing for EVERY
     canonically encoded G1 point (101 curve points + identity) and EVERY G2 byte pair below 101: 1 040 502 pairings."""
