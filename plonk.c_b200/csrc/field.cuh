@@ -6,11 +6,15 @@
 // exact for x < 2^26.  Results are always the canonical residue, i.e. exactly what the reference's
 // `%` produces (hf.h:105-109, gf.h:115-120).  Inverses are table look-ups in shared memory: the
 // F17 table is the reference's own (hf.h:145-180, inv(0)=0); the F101 table holds x^99, which is
-// what gf_inv computes (gf.h:159-162), so inv(0)=0 there too.  Both tables are < 128 bytes, hence
-// bank-conflict free for any access pattern.
+// what gf_inv computes (gf.h:159-162), so inv(0)=0 there too (256 entries: the fast paths index it with
+// unreduced differences, curve.cuh).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#ifdef PB_CHECK_BOUNDS
+#include <cstdio>
+#include <cstdlib>
+#endif
 
 namespace pb {
 
@@ -27,6 +31,15 @@ constexpr uint32_t P101 = 101u;
 constexpr uint32_t M17 = 252645136u;  // ceil(2^32 / 17)
 constexpr uint32_t M101 = 42524429u;  // ceil(2^32 / 101)
 
+// Range checks of the reductions' inputs, compiled into the HOST build of the test library only (tests/hostcheck is built
+// with -DPB_CHECK_BOUNDS): every differential test on the CPU is then also a test of the bounds stated in the comments.
+#if defined(PB_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
+#define PB_BOUND(x, lim, what) \
+  do { if ((uint64_t)(x) >= (uint64_t)(lim)) { fprintf(stderr, "plonk_b200: bound violated: %s(%llu)\n", what, (unsigned long long)(x)); abort(); } } while (0)
+#else
+#define PB_BOUND(x, lim, what) do { } while (0)
+#endif
+
 PB_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
   return __umulhi(a, b);
@@ -36,9 +49,9 @@ PB_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
 }
 
 // canonical residue of a raw value x < 2^28
-PB_HD uint32_t red17(uint32_t x) { return x - P17 * mulhi_u32(x, M17); }
+PB_HD uint32_t red17(uint32_t x) { PB_BOUND(x, 1u << 28, "red17"); return x - P17 * mulhi_u32(x, M17); }
 // canonical residue of a raw value x < 2^26
-PB_HD uint32_t red101(uint32_t x) { return x - P101 * mulhi_u32(x, M101); }
+PB_HD uint32_t red101(uint32_t x) { PB_BOUND(x, 1u << 26, "red101"); return x - P101 * mulhi_u32(x, M101); }
 
 // inputs canonical; outputs canonical
 PB_HD uint32_t add17(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= P17 ? s - P17 : s; }
@@ -73,7 +86,7 @@ struct alignas(16) FieldTables {
   uint8_t inv101[256];  // (x mod 101)^99 mod 101, gf.h:159-162; entries 101..255 serve unreduced indices (curve.cuh: g1_add_c)
 };
 
-PB_HD uint32_t inv17(const FieldTables& t, uint32_t a) { return t.inv17[a]; }
-PB_HD uint32_t inv101(const FieldTables& t, uint32_t a) { return t.inv101[a]; }
+PB_HD uint32_t inv17(const FieldTables& t, uint32_t a) { PB_BOUND(a, 32u, "inv17 index"); return t.inv17[a]; }
+PB_HD uint32_t inv101(const FieldTables& t, uint32_t a) { PB_BOUND(a, 256u, "inv101 index"); return t.inv101[a]; }
 
 }  // namespace pb

@@ -145,6 +145,7 @@ PB_HD void interpolate(const CircuitConst& cc, const uint32_t (&v)[4], uint32_t 
 template <typename Tables>
 PB_HD uint32_t red_small(const Tables& tb, uint32_t x) {
 #if PB_PROVE_MODTAB
+  PB_BOUND(x, MOD17_RANGE, "mod17 index");
   return tb.mod17[x];
 #else
   return red17(x);

@@ -296,9 +296,19 @@ uint64_t hc_check_barrett(uint32_t* first_bad17, uint32_t* first_bad101) {
   for (uint32_t x = 0; x < (1u << 28); x++) bad += red17(x) != x % 17u;
   for (uint32_t x = 0; x < (1u << 26); x++) bad += red101(x) != x % 101u;
   *first_bad17 = 0; *first_bad101 = 0;
-  for (uint64_t x = 1ull << 28; x < (1ull << 32); x++) if (red17((uint32_t)x) != (uint32_t)x % 17u) { *first_bad17 = (uint32_t)x; break; }
-  for (uint64_t x = 1ull << 26; x < (1ull << 32); x++) if (red101((uint32_t)x) != (uint32_t)x % 101u) { *first_bad101 = (uint32_t)x; break; }
+  // beyond the claimed ranges the formulas are restated here (red17 / red101 themselves refuse such inputs in this build)
+  auto f17 = [](uint32_t x) { return x - P17 * mulhi_u32(x, M17); };
+  auto f101 = [](uint32_t x) { return x - P101 * mulhi_u32(x, M101); };
+  for (uint64_t x = 1ull << 28; x < (1ull << 32); x++) if (f17((uint32_t)x) != (uint32_t)x % 17u) { *first_bad17 = (uint32_t)x; break; }
+  for (uint64_t x = 1ull << 26; x < (1ull << 32); x++) if (f101((uint32_t)x) != (uint32_t)x % 101u) { *first_bad101 = (uint32_t)x; break; }
   return bad;
+}
+int hc_bounds_checked() {
+#ifdef PB_CHECK_BOUNDS
+  return 1;
+#else
+  return 0;
+#endif
 }
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]

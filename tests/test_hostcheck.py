@@ -78,6 +78,40 @@ def test_hostcheck_group_law_on_canonical_points(hc, oracle):
     ps.eq("g1_add on all canonical pairs", hc.g1_op(0, a, b), oracle.g1_op(0, a, b))
 
 
+def test_hostcheck_extreme_inputs_stay_within_the_reduction_bounds(oracle, W):
+    """The test library is built with -DPB_CHECK_BOUNDS: every reduction and table look-up aborts the process if its
+    input leaves the range the kernel relies on.  Inputs chosen to push the unreduced accumulators as high as they go
+    (every byte 16, or 0, or alternating; random satisfying and unsatisfying witnesses; every SRS mode and table path) --
+    the prover is straight-line, so even an unsatisfied witness runs through all five rounds."""
+    import numpy as np
+    import util
+    assert HostcheckImpl(oracle).lib.hc_bounds_checked() == 1, "tests/hostcheck must be built with -DPB_CHECK_BOUNDS"
+    C = W.PLONK_TEST_CIRCUIT
+    rng = np.random.default_rng(99)
+    n = 3000
+    wit = rng.integers(0, 17, (n, 12), dtype=np.uint8)
+    rnd = rng.integers(0, 17, (n, 9), dtype=np.uint8)
+    chal = rng.integers(0, 17, (n, 5), dtype=np.uint8)
+    for k, v in enumerate((16, 0, 1)):
+        wit[k], rnd[k], chal[k] = v, v, v
+    wit[3], rnd[3], chal[3] = 16, 0, 16
+    wit[4, ::2], rnd[4, ::2], chal[4, ::2] = 16, 16, 16
+    sat, rs, ch, _ = W.make_batch(5, 0, n, "U17")
+    rs[:, :] = 16
+    ch[:, :] = 16
+    dense = np.full(44, 16, np.uint8)                 # every selector value 16; copy constraints of the test circuit
+    dense[20:] = C[20:]
+    for fast in (False, True, "wide"):
+        impl = HostcheckImpl(oracle, fast=fast)
+        for mode in ("generator9", "identity6") if fast else ("generator9", "identity6", "generator4"):
+            g1s, g2 = util.SRS_MODES[mode](W)
+            for circuit in (C, dense):
+                ps.eq(f"extreme random {fast} {mode}", impl.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal),
+                      oracle.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal, 8))
+                ps.eq(f"extreme satisfying {fast} {mode}", impl.plonk_prove_batch(circuit, g1s, g2, sat, rs, ch),
+                      oracle.plonk_prove_batch(circuit, g1s, g2, sat, rs, ch, 8))
+
+
 def test_hostcheck_barrett_reductions_over_their_whole_range(hc):
     """red17 / red101 (multiply-high Barrett step, field.cuh) against `%` for EVERY x below the bounds the kernels rely on
     (2^28 resp. 2^26), and where above those bounds the formulas first fail."""
