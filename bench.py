@@ -11,8 +11,13 @@ plonk-test circuit with uniform blinding scalars and challenges (variant U17), g
 on-device tally of statuses / verdicts / proof checksum.
 
 value   proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
-e2e     proofs/s through the public host-pointer call pb_plonk_prove_verify: pinned host buffers in, pinned host
-        buffers out, H2D and D2H copies inside the timed region
+e2e     proofs/s through a public host-pointer call, pinned host buffers in and out, H2D and D2H copies inside the
+        timed region.  Three calls are measured, same items, same step count:
+          e2e          pb_plonk_prove_verify_packed   packed wire v2: 16 B in, 22 B per completed proof + 1 B per item out
+          e2e_compact  pb_plonk_prove_verify_compact  the reference's structs in (27 B), only the proofs that exist out
+          e2e_struct   pb_plonk_prove_verify          the reference's structs both ways (27 B in, 36 B out; round 1's e2e)
+seeded  proofs/s of pb_plonk_prove_verify_seeded_dev: inputs generated on the device from (seed, start, count), only the
+        counters come back.  Not an end-to-end number (no batch data crosses PCIe); reported beside `value`.
 roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
 
 Other workloads (`--workload`, one JSON line each, L2 flushed before every timed launch; not what the driver runs):
@@ -50,7 +55,9 @@ def parse_args():
     ap.add_argument("--items", type=int, default=1 << 21, help="proofs per rank per step")
     ap.add_argument("--srs", default="generator", choices=["generator", "identity"])
     ap.add_argument("--variant", default="U17", choices=["U17", "NZ"])
-    ap.add_argument("--ref-items", type=int, default=1 << 18, help="proofs per step of the reference arm")
+    ap.add_argument("--ref-items", type=int, default=0, help="proofs per step of the reference arm (0 = --items, the same config)")
+    ap.add_argument("--min-seconds", type=float, default=0.0,
+                    help="sustained run: raise --steps until the timed region of `value` lasts at least this long (for the clock/power record)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "prove_verify_fs", "poly", "g1_mul", "pairing", "field"],
                     help="prove_verify = BASELINE config 5 (the headline, what the driver runs); poly / g1_mul / pairing = "
@@ -120,7 +127,7 @@ def run_reference(args):
     srs = (W.generator_srs if args.srs == "generator" else W.identity_srs)(9)
     lib, kind = load_cpu_oracle()
     cores = os.cpu_count() or 1
-    n = args.ref_items
+    n = args.ref_items or args.items
     wit, rnd, chal, u = W.make_batch(SEED, 0, n, args.variant)
     for _ in range(args.warmup):
         cpu_prove_verify(lib, W, srs, wit, rnd, chal, u, cores)
@@ -129,13 +136,15 @@ def run_reference(args):
         t += cpu_prove_verify(lib, W, srs, wit, rnd, chal, u, cores)
     value = n * args.steps / t
     cfg = workload_config(args, world)
-    cfg["items_per_step_reference_arm"] = n
+    if n != args.items:
+        cfg["items_per_step_reference_arm"] = n
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{n} items per step (bounded sample of the same stream), {cores} host threads"},
+                         "sample": f"{n} items per step = one GPU's share of the same stream (rank 0's items), {cores} host threads, "
+                                   f"prove + verify of the completed proofs ({'oracle/_ref: unmodified reference headers, gcc -O2, per-thread bump arena' if kind == 'reference' else 'oracle/plonk_port.c restatement'})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,6 +241,12 @@ def algorithmic_ops(args, W, srs):
             "convention": "1 field mul = 3 INT32 ops, 1 add/sub = 2, 1 F17 inverse look-up = 1; per attempted item"}
 
 
+def rank_stats(values):
+    """min / median / max of a per-rank list and the rank that holds the max (the straggler decides a max-over-ranks number)"""
+    v = [float(x) for x in values]
+    return {"min": min(v), "median": float(np.median(v)), "max": max(v), "rank_of_max": int(np.argmax(v)), "ranks": len(v)}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -315,6 +330,17 @@ def run_b200(args):
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
+    if args.min_seconds > 0:          # sustained run: size the step count from a short timed probe (all ranks agree on it)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for k in range(8):
+            step(k)
+        b.record(stream)
+        torch.cuda.synchronize()
+        want = torch.tensor([int(np.ceil(args.min_seconds * 1e3 / (a.elapsed_time(b) / 8)))], dtype=torch.int64, device=dev)
+        if dist is not None:
+            dist.all_reduce(want, op=dist.ReduceOp.MAX)
+        args.steps = max(args.steps, int(want.item()))
     counts.zero_()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     for e3 in evs:
@@ -340,39 +366,104 @@ def run_b200(args):
     if sampler:
         time.sleep(0.15)
         sampler.stop()
+    per_rank = shard.gather_scalar(elapsed_ms / args.steps, dev)        # every rank's own ms per step (device time)
     gcounts, elapsed_ms = shard.reduce_counters(counts, elapsed_ms)
     value = total * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- e2e: the public host-pointer call, pinned host buffers, copies inside the timed region
+    def timed_steps(fn, steps):
+        """max over ranks of the device time of `steps` calls of fn(k), barrier + synchronize on both sides"""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        a.record(stream)
+        for k in range(steps):
+            fn(k)
+        b.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        return shard.reduce_max(a.elapsed_time(b), dev)
+
+    # ---- the same step on the shared-memory SRS path (pair tables, PB_WIDE_TABLES=0): BASELINE's "SRS held in shared memory"
+    os.environ["PB_WIDE_TABLES"] = "0"
+    try:
+        pk_pair = host.Plonk(W.PLONK_TEST_CIRCUIT, srs[0], srs[1], device=local_rank)
+    finally:
+        del os.environ["PB_WIDE_TABLES"]
+
+    def step_pair(k):
+        (wit, rnd, chal, u), (proofs, status, verdict) = sets[k % NBUF]
+        host._check(lib.pb_plonk_prove_verify_ex_dev(pk_pair._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict),
+                                                     C.c_size_t(n), sp, None))
+        host._check(lib.pb_tally_dev(P(proofs), P(status), P(verdict), C.c_size_t(n), P(counts), sp))
+    for k in range(3):
+        step_pair(k)
+    pair_steps = min(args.steps, 20)
+    pair_ms = timed_steps(step_pair, pair_steps)
+    pk_pair.close()
+
+    # ---- seeded mode: inputs generated on the device, only the counters come back (not an e2e number)
+    ws = pk.seeded_workspace(n, dev)
+    scounts = torch.zeros(shard.N_COUNTERS, dtype=torch.int64, device=dev)
+    for k in range(3):
+        pk.prove_verify_seeded_dev(SEED, start, n, args.variant, ws, scounts)
+    scounts.zero_()
+    seeded_steps = min(args.steps, 20)
+    seeded_ms = timed_steps(lambda k: pk.prove_verify_seeded_dev(SEED + k % NBUF, start, n, args.variant, ws, scounts), seeded_steps)
+    del ws
+
+    # ---- e2e: public host-pointer calls, pinned host buffers, copies inside the timed region (wall clock around the
+    # synchronous calls, barrier + synchronize on both sides, max over ranks)
+    from plonk_c_b200 import wire
     pin = [torch.from_numpy(x).pin_memory() for x in host_in]
+    pin_packed = torch.from_numpy(wire.pack_inputs(*host_in)).pin_memory()
     hout = [torch.empty((n, 34), dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
             torch.empty(n, dtype=torch.uint8).pin_memory()]
+    hpacked = [torch.empty((n, 22), dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()]
     np_in = [t.numpy() for t in pin]
     np_out = [t.numpy() for t in hout]
-    e2e_steps = args.steps
-    for _ in range(max(1, min(args.warmup, 3))):
-        pk.prove_verify_into(*np_in, *np_out)
-    barrier()
-    torch.cuda.synchronize()
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
-        pk.prove_verify_into(*np_in, *np_out)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - te) * 1e3
-    barrier()
-    if dist is not None:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = total * e2e_steps / (e2e_ms * 1e-3)
-    h2d = n * (12 + 9 + 5 + 1)
-    d2h = n * (34 + 1 + 1)
-    # the device path and the host path must agree on what they computed
-    ok = (torch.equal(hout[1], sets[0][1][1].cpu()) and torch.equal(hout[0], sets[0][1][0].cpu())
-          and torch.equal(hout[2], sets[0][1][2].cpu()))
-    if not ok:
-        raise SystemExit("bench.py: host-pointer path and device path disagree")
+    np_packed_in, np_packed_out = pin_packed.numpy(), [t.numpy() for t in hpacked]
+    e2e_steps = min(args.steps, 20)
+    done_box = [0]
 
+    def e2e_time(fn):
+        for _ in range(max(1, min(args.warmup, 3))):
+            fn()
+        barrier()
+        torch.cuda.synchronize()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - te) * 1e3
+        barrier()
+        each = shard.gather_scalar(ms / e2e_steps, dev)
+        return shard.reduce_max(ms, dev), each
+
+    def run_packed():
+        done_box[0] = pk.prove_verify_packed_into(np_packed_in, *np_packed_out)
+    packed_ms, packed_each = e2e_time(run_packed)
+    n_done = done_box[0]
+    # the device path and the packed host path must agree on what they computed
+    ref_p, ref_s, ref_v = (t.cpu().numpy() for t in sets[0][1])
+    if not (n_done == int((ref_s == 0).sum()) and np.array_equal(np_packed_out[0][:n_done], wire.pack_proofs(ref_p[ref_s == 0]))
+            and np.array_equal(np_packed_out[1], wire.make_sv(ref_s, ref_v))):
+        raise SystemExit("bench.py: packed host-pointer path and device path disagree")
+
+    def run_compact():
+        done_box[0] = pk.prove_verify_compact_into(*np_in, *np_out)
+    compact_ms, compact_each = e2e_time(run_compact)
+    if not (done_box[0] == n_done and np.array_equal(np_out[0][:n_done], ref_p[ref_s == 0]) and np.array_equal(np_out[1], ref_s)
+            and np.array_equal(np_out[2], ref_v)):
+        raise SystemExit("bench.py: compact host-pointer path and device path disagree")
+    struct_ms, struct_each = e2e_time(lambda: pk.prove_verify_into(*np_in, *np_out))
+    if not (np.array_equal(np_out[0], ref_p) and np.array_equal(np_out[1], ref_s) and np.array_equal(np_out[2], ref_v)):
+        raise SystemExit("bench.py: host-pointer path and device path disagree")
+    done_all = shard.reduce_sum(n_done, dev)        # completed proofs per step over all ranks (data-dependent D2H size)
+
+    def e2e_entry(ms, each, api, h2d, d2h, note):
+        return {"value": total * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms / e2e_steps, "steps": e2e_steps, "api": api, "bytes_per_item": (h2d + d2h) / n,
+                "per_rank_ms_per_step": rank_stats(each), "cpu_affinity": numa, "note": note}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -395,49 +486,67 @@ def run_b200(args):
         probe[name] = best / 1e12
     alg = algorithmic_ops(args, W, srs)
     dominant = "verify_kernel" if verify_ms >= prove_ms else "prove_kernel"
-    dom_ms = max(verify_ms, prove_ms)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dominant)
+    other = "prove_kernel" if dominant == "verify_kernel" else "verify_kernel"
+    kms = {"prove_kernel": prove_ms, "verify_kernel": verify_ms}
+    try:        # executed-instruction counts of the same kernels on the same batch, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "ncu_headline.json")) as f:
+            ncu = json.load(f)
     except Exception:
-        pass
+        ncu = {}
     roof = {"bound": "int32", "kernel": dominant, "unit": "TIOP/s", "peak": probe["imad"],
             "peak_source": "measured live: dependency-free 32-bit IMAD stream on all SMs (pb_peak_probe_dev kind 0)",
-            "traffic": traffic, "probes_tiops": probe,
-            "kernel_ms": {"prove_kernel": prove_ms, "verify_kernel": verify_ms},
-            "kernel_share_of_step": {"prove_kernel": prove_ms * args.steps / elapsed_ms, "verify_kernel": verify_ms * args.steps / elapsed_ms}}
-    if alg:
-        per_item = alg["verify_int_ops_per_item"] if dominant == "verify_kernel" else alg["prove_int_ops_per_item"]
-        roof["achieved"] = per_item * n / (dom_ms * 1e-3) / 1e12
-        roof["frac"] = roof["achieved"] / roof["peak"]
+            "probes_tiops": probe, "kernel_ms": kms,
+            "kernel_share_of_step": {k: v * args.steps / elapsed_ms for k, v in kms.items()}}
+
+    def executed(kernel):
+        """TIOP/s of IMAD-pipe thread-instructions the kernel EXECUTES: per-item count from the ncu source page (thread
+        instructions of every IMAD* opcode / items of that launch) x this run's items / this run's kernel time."""
+        per_item = (ncu.get(kernel) or {}).get("imad_thread_inst_per_item")
+        return None if per_item is None else per_item * n / (kms[kernel] * 1e-3) / 1e12
+    roof["achieved"] = executed(dominant)
+    roof["frac"] = None if roof["achieved"] is None else roof["achieved"] / roof["peak"]
+    oth = executed(other)
+    roof["other_kernel_frac"] = {other: None if oth is None else oth / roof["peak"]}
+    roof["issue_slot_utilization"] = {k: (ncu.get(k) or {}).get("issue_slot_utilization") for k in kms}
+    roof["traffic"] = (ncu.get(dominant) or {}).get("dram_bytes_per_launch_warm") or (ncu.get(dominant) or {}).get("dram_bytes_per_launch")
+    roof["ncu"] = ncu or None
+    if alg:     # SURVEY 8(d)'s convention: the REFERENCE's operation count over this kernel's time -- a speed-up, not an efficiency
+        roof["algorithmic_speedup"] = {
+            "prove_kernel": alg["prove_int_ops_per_item"] * n / (prove_ms * 1e-3) / 1e12 / roof["peak"],
+            "verify_kernel": alg["verify_int_ops_per_item"] * n / (verify_ms * 1e-3) / 1e12 / roof["peak"],
+            "meaning": "INT32 ops of the reference's algorithm (mul = 3, add/sub = 2) per second / IMAD peak; above 1 because the kernels "
+                       "replace most of those operations (fixed-base tables, look-up inversions, joint double-and-add)"}
         roof["algorithmic"] = alg
-        roof["other_kernel_frac"] = {
-            ("prove_kernel" if dominant == "verify_kernel" else "verify_kernel"):
-                (alg["prove_int_ops_per_item"] if dominant == "verify_kernel" else alg["verify_int_ops_per_item"]) * n
-                / (min(verify_ms, prove_ms) * 1e-3) / 1e12 / roof["peak"]}
-    else:
-        roof["achieved"], roof["frac"] = None, None
-    try:        # hardware-side view of the same kernels, from the committed ncu capture (not measurable without a profiler)
-        with open(os.path.join(ROOT, "profiles", "ncu_headline.json")) as f:
-            roof["ncu"] = json.load(f)
-    except Exception:
-        roof["ncu"] = None
-    roof["note"] = ("achieved/frac follow SURVEY 8(d): algorithmic INT32 ops of the REFERENCE's algorithm per launch / kernel time. The kernels need far "
-                    "fewer operations than the reference (fixed-base tables instead of per-term double-and-add with Fermat inversions, joint "
-                    "double-and-add), so frac > 1 is speed-up over the reference's operation count, not hardware efficiency; the hardware view is "
-                    "roofline.ncu (issue-slot and IMAD-pipe utilisation).")
+    roof["note"] = ("achieved = IMAD-pipe thread-instructions the dominant kernel executes per second (count per item from the committed "
+                    "ncu source page, profiles/ncu_headline.json; time and peak measured in this run); frac = achieved / the live "
+                    "dependency-free IMAD probe.  issue_slot_utilization is ncu's smsp__issue_active of the same capture.")
     bytes_item = {"prove_kernel": 26 + 35, "verify_kernel": 34 + 5 + 1 + 1 + 1}
     roof["hbm"] = {"peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
-                   "achieved": {k: bytes_item[k] * n / (ms * 1e-3) / 1e9 for k, ms in (("prove_kernel", prove_ms), ("verify_kernel", verify_ms))},
+                   "achieved": {k: bytes_item[k] * n / (ms * 1e-3) / 1e9 for k, ms in kms.items()},
                    "algorithmic_bytes_per_item": bytes_item}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / e2e_steps, "api": "pb_plonk_prove_verify (host pointers, pinned)", "cpu_affinity": numa},
+        "per_rank_ms_per_step": rank_stats(per_rank),
+        "e2e": e2e_entry(packed_ms, packed_each, "pb_plonk_prove_verify_packed (host pointers, pinned; packed wire v2, csrc/wire.cuh)",
+                         n * 16, n + n_done * 22,
+                         "16 B in; out: 22 B per completed proof (dense, item order) + 1 status/verdict byte per item; same information as "
+                         "the struct arrays (pb_wire_* / wire.py convert); d2h bytes are rank 0's (data-dependent)"),
+        "e2e_compact": e2e_entry(compact_ms, compact_each, "pb_plonk_prove_verify_compact (host pointers, pinned; the reference's structs)",
+                                 n * 27, 2 * n + n_done * 34,
+                                 "struct inputs (27 B); out: status + verdict per item and the PROOF structs of the completed items only"),
+        "e2e_struct": e2e_entry(struct_ms, struct_each, "pb_plonk_prove_verify (host pointers, pinned; the reference's structs)",
+                                n * 27, n * 36, "round 1's e2e: every item's 34-byte PROOF record travels, zero-filled where the reference exits"),
+        "seeded": {"value": total * seeded_steps / (seeded_ms * 1e-3), "unit": UNIT, "ms_per_step": seeded_ms / seeded_steps, "steps": seeded_steps,
+                   "api": "pb_plonk_prove_verify_seeded_dev (seed, start, count) -> 18 counters",
+                   "note": "inputs generated on the device (splitmix64 stream of workload.py), proved, verified, tallied; no batch data "
+                           "crosses PCIe, so this is NOT an end-to-end number"},
+        "value_pair_tables": {"value": total * pair_steps / (pair_ms * 1e-3), "unit": UNIT, "ms_per_step": pair_ms / pair_steps, "steps": pair_steps,
+                              "note": "same step with PB_WIDE_TABLES=0: the SRS fixed-base pair tables (5.8 KB) live in shared memory "
+                                      "(BASELINE north star (3)); the headline keeps a 48 MB one-look-up table in L2 instead"},
+        "completed_proofs_per_step": done_all,
         "gpu_launches": 3 * args.steps,
         "roofline": roof,
         "clocks": sampler.summary(t0, t1) if sampler else None,
@@ -445,7 +554,7 @@ def run_b200(args):
                     "verified_accept": int(gcounts[16]), "proof_byte_checksum": int(gcounts[17]),
                     "note": "items attempted = global_items_per_step x steps; the reference exits on ~39% of random inputs (SURVEY.md App. B)"},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args, W, srs)
         except Exception as e:  # the baseline is reported, never required for the GPU number

@@ -229,6 +229,54 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx *ctx, const uint8_t *witness, cons
                                  void *mid_event);
 int pb_plonk_prove_verify(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                           const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, size_t n);
+/* ---- outputs that cost less PCIe than the reference's structs.  End to end the path is bound by the host link, not by
+ * the kernels: 27 B in + 36 B out per proof with the struct arrays above.
+ *
+ * Compact output: same struct inputs; D2H carries only the proofs that exist.  proofs_dense (capacity n x 34 bytes)
+ * receives the PROOF structs of the completed items (status 0) in item order, *n_done their number; status[n] and
+ * verdict[n] as in pb_plonk_prove_verify.  pb_wire_scatter_proofs rebuilds the [n][34] array of the struct API (the
+ * records of items on which the reference exits are zero by definition, plonk_b200.h header note). */
+int pb_plonk_prove_verify_compact(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                                  const uint8_t *u, uint8_t *proofs_dense, size_t *n_done, uint8_t *status,
+                                  uint8_t *verdict, size_t n);
+/* the dense list on the device: proofs[n][34] + status[n] -> proofs_dense (16-byte aligned, capacity n x 34),
+ * *n_done_dev; offs_scratch: (n / 128 + 4) uint32 of device scratch */
+int pb_gather_completed_dev(const uint8_t *proofs, const uint8_t *status, uint8_t *proofs_dense, uint32_t *n_done_dev,
+                            uint32_t *offs_scratch, size_t n, void *stream);
+
+/* Packed wire v2 (layout: csrc/wire.cuh; Python twin: plonk.c_b200/wire.py).  Input record 16 bytes = four little-endian
+ * u32, each seven base-17 digits (least significant first) of the 27 values a[4] b[4] c[4] | rand[9] | alpha beta gamma z v
+ * | u, one spare digit 0.  Output: 22 bytes per COMPLETED proof, dense, item order (nine u16 points x | y << 7 |
+ * infinite << 14, one u32 with the seven openings as base-17 digits), and one sv byte per item (low nibble: prove status,
+ * 15 = PB_PROVE_BAD_INPUT; high nibble: verdict, 15 = not verified).  16 B in, ~14 B out per item instead of 27 / 36. */
+#define PB_PACKED_IN_BYTES 16
+#define PB_PACKED_PROOF_BYTES 22
+int pb_plonk_prove_verify_packed(const pb_ctx *ctx, const uint8_t *packed_in, uint8_t *packed_proofs /* capacity n x 22 */,
+                                 size_t *n_done, uint8_t *sv, size_t n);
+size_t pb_packed_workspace_bytes(size_t n);
+int pb_plonk_prove_verify_packed_dev(const pb_ctx *ctx, const uint8_t *packed_in, uint8_t *packed_proofs,
+                                     uint32_t *n_done_dev, uint8_t *sv, void *workspace, size_t n, void *stream);
+/* format conversion on the host (plain C loops, no arithmetic of the path) */
+int pb_wire_pack_inputs(const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal, const uint8_t *u, uint8_t *packed, size_t n);
+int pb_wire_unpack_inputs(const uint8_t *packed, uint8_t *witness, uint8_t *rnd, uint8_t *chal, uint8_t *u,
+                          uint8_t *valid /* optional */, size_t n);
+int pb_wire_pack_proofs(const uint8_t *proofs, uint8_t *packed, size_t n);
+int pb_wire_unpack_proofs(const uint8_t *packed, uint8_t *proofs, size_t n);
+int pb_wire_scatter_proofs(const uint8_t *proofs_dense, const uint8_t *status, uint8_t *proofs, size_t n);
+int pb_wire_split_sv(const uint8_t *sv, uint8_t *status /* optional */, uint8_t *verdict /* optional */, size_t n);
+
+/* Seeded mode (SURVEY.md sections 7.4 / 8(e)): items [start, start + count) of the synthetic stream `seed` are generated
+ * on the device (draw j of item i = splitmix64(seed + 16 i + j): witness row, nine blinding scalars, five challenges, u;
+ * variant 0 = "U17", 1 = "NZ"; plonk.c_b200/workload.py make_batch is the host twin), proved, verified and tallied there;
+ * only counts[18] (pb_tally_dev layout) come back.  No batch data crosses PCIe. */
+int pb_plonk_prove_verify_seeded(const pb_ctx *ctx, uint64_t seed, uint64_t start, size_t count, int variant, int64_t counts[18]);
+size_t pb_seeded_workspace_bytes(size_t n);
+int pb_plonk_prove_verify_seeded_dev(const pb_ctx *ctx, uint64_t seed, uint64_t start, size_t n, int variant, void *workspace,
+                                     int64_t *counts_dev, void *stream);
+/* the generator alone: struct arrays (witness rnd chal u, all or none) and / or packed records (may be NULL) */
+int pb_synth_batch_dev(const pb_ctx *ctx, uint64_t seed, uint64_t start, size_t n, int variant, uint8_t *witness,
+                       uint8_t *rnd, uint8_t *chal, uint8_t *u, uint8_t *packed, void *stream);
+
 /* ---- Fiat-Shamir mode (optional).  The reference's prover takes its challenges from
  * the caller (CHALLENGE, plonk.h:16-22,227) -- the entry points above keep that interface and are bit-exact with it.
  * Here the five challenges, and the verifier's u, are drawn from a transcript hash of the circuit, the SRS and the proof

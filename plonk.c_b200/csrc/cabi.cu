@@ -67,8 +67,9 @@ struct Dev {
 #define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
-constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // device scratch per slot is sized for this many items
+constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // largest chunk of the host-pointer pipelines
 constexpr int PIPE_SLOTS = 6;
+constexpr int PIPE_LOOKAHEAD = 3;             // compact / packed modes: chunks enqueued ahead of the one whose count the host waits for
 // items per pipeline chunk of the host-pointer prove/verify (PB_PIPE_CHUNK overrides, for tuning; multiple of 128)
 size_t pipe_chunk() {
   static size_t v = [] {
@@ -79,10 +80,15 @@ size_t pipe_chunk() {
   return v;
 }
 
+// one buffer set of the host-pointer pipelines, sized for `cap` items (a multiple of 128, grown on demand)
 struct PipeSlot {
-  cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // inputs landed / kernels done / proofs copied out
-  uint8_t *wit = nullptr, *rnd = nullptr, *chal = nullptr, *proofs = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // inputs landed / kernels done / outputs copied out
+  uint8_t* in = nullptr;       // [cap * 26]: witness | rnd | chal (struct inputs), or the packed records [cap * 16]
+  uint8_t* proofs = nullptr;   // [cap * 34]: PROOF structs at item positions
+  uint8_t* dense = nullptr;    // [cap * 34 + 16]: completed proofs only (compact / packed outputs)
+  uint32_t* offs = nullptr;    // [cap / 128 + 4]: group offsets of the dense list; the last word is the chunk's count
 };
+enum PipeMode { PIPE_PROVE = 0, PIPE_STRUCT = 1, PIPE_COMPACT = 2, PIPE_PACKED = 3 };
 
 }  // namespace
 
@@ -112,11 +118,16 @@ struct pb_ctx {
   std::mutex scratch_mu;
   std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
   std::mutex pipe_mu;
-  bool pipe_ready = false;
+  bool pipe_ready = false;            // streams and events exist
   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;       // H2D engine, SMs, D2H engine
-  uint8_t *d_u = nullptr, *d_status = nullptr, *d_verdict = nullptr;   // whole-batch one-byte arrays of the host-pointer pipeline
+  uint8_t *d_u = nullptr, *d_status = nullptr, *d_verdict = nullptr, *d_sv = nullptr;   // whole-batch one-byte arrays of the host-pointer pipelines
   size_t small_cap = 0;
+  size_t slot_cap = 0;                // items each slot's buffers hold
   PipeSlot slots[PIPE_SLOTS];
+  uint32_t* h_count = nullptr;        // pinned, [PIPE_SLOTS]: completed proofs of the chunk in each slot
+  uint8_t* d_wtab = nullptr;          // seeded mode: the 289-row witness table of the synthetic stream
+  uint8_t* d_seed_ws = nullptr;       // seeded mode: workspace (packed inputs, proofs, status, verdict, counters)
+  size_t seed_ws_items = 0;
 };
 
 namespace {
@@ -146,21 +157,38 @@ int scratch_for(const pb_ctx* cctx, cudaStream_t st, size_t n, uint32_t** out) {
   return PB_OK;
 }
 
-int pipe_init(pb_ctx* c) {
-  if (c->pipe_ready) return PB_OK;
-  CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-  for (auto& s : c->slots) {
-    CU(cudaMalloc(&s.wit, PIPE_CHUNK_MAX * 12));
-    CU(cudaMalloc(&s.rnd, PIPE_CHUNK_MAX * 9));
-    CU(cudaMalloc(&s.chal, PIPE_CHUNK_MAX * 5));
-    CU(cudaMalloc(&s.proofs, PIPE_CHUNK_MAX * 34));
-    CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+// streams, events and the pinned count mirror (once); slot buffers for chunks of up to `cap` items (grown on demand, so a
+// batch of one -- the drop-in plonk_prove -- does not allocate buffers for a million).  A failure part-way leaves
+// everything allocated so far owned by the context: the next call resumes, pb_ctx_destroy frees.
+int pipe_init(pb_ctx* c, size_t cap) {
+  if (!c->pipe_ready) {
+    if (!c->s_in) CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_k) CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+    if (!c->s_out) CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (auto& s : c->slots) {
+      if (!s.ev_in) CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+      if (!s.ev_k) CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+      if (!s.ev_out) CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    if (!c->h_count) CU(cudaHostAlloc(reinterpret_cast<void**>(&c->h_count), PIPE_SLOTS * sizeof(uint32_t), cudaHostAllocDefault));
+    c->pipe_ready = true;
   }
-  c->pipe_ready = true;
+  cap = (cap + 4095) & ~(size_t)4095;
+  if (c->slot_cap >= cap) return PB_OK;
+  CU(cudaStreamSynchronize(c->s_in)); CU(cudaStreamSynchronize(c->s_k)); CU(cudaStreamSynchronize(c->s_out));
+  c->slot_cap = 0;
+  for (auto& s : c->slots) {
+    for (void** p : {reinterpret_cast<void**>(&s.in), reinterpret_cast<void**>(&s.proofs), reinterpret_cast<void**>(&s.dense),
+                     reinterpret_cast<void**>(&s.offs)}) {
+      if (*p) CU(cudaFree(*p));
+      *p = nullptr;
+    }
+    CU(cudaMalloc(&s.in, cap * 26));
+    CU(cudaMalloc(&s.proofs, cap * 34));
+    CU(cudaMalloc(&s.dense, cap * 34 + 16));
+    CU(cudaMalloc(reinterpret_cast<void**>(&s.offs), (cap / 128 + 4) * sizeof(uint32_t)));
+  }
+  c->slot_cap = cap;
   return PB_OK;
 }
 
@@ -169,7 +197,7 @@ int pipe_init(pb_ctx* c) {
 extern "C" {
 
 const char* pb_last_error(void) { return g_err.c_str(); }
-int pb_abi_version(void) { return 1; }
+int pb_abi_version(void) { return 2; }
 int pb_device_count(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -1022,11 +1050,12 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
     for (cudaEvent_t e : {s.ev_in, s.ev_k, s.ev_out}) if (e) cudaEventDestroy(e);
-    uint8_t* bufs[4] = {s.wit, s.rnd, s.chal, s.proofs};
+    void* bufs[4] = {s.in, s.proofs, s.dense, s.offs};
     for (auto b : bufs) if (b) cudaFree(b);
   }
   for (cudaStream_t st : {c->s_in, c->s_k, c->s_out}) if (st) cudaStreamDestroy(st);
-  for (uint8_t* p : {c->d_u, c->d_status, c->d_verdict}) if (p) cudaFree(p);
+  for (uint8_t* p : {c->d_u, c->d_status, c->d_verdict, c->d_sv, c->d_wtab, c->d_seed_ws}) if (p) cudaFree(p);
+  if (c->h_count) cudaFreeHost(c->h_count);
   delete c;
   return PB_OK;
 }
@@ -1058,34 +1087,42 @@ int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* o
 }
 
 // prove launch: pair tables when the SRS is canonical, the sequential tables otherwise
-// chal == nullptr selects the Fiat-Shamir instantiation (challenges drawn in the kernel; chal_out optional)
+// chal == nullptr selects the Fiat-Shamir instantiation (challenges drawn in the kernel; chal_out optional);
+// packed != nullptr selects the packed-input instantiation (wire.cuh): witness / rnd / chal are not read
 static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status,
-                        size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict, uint8_t* chal_out = nullptr) {
+                        size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict, uint8_t* chal_out = nullptr,
+                        const uint8_t* packed = nullptr) {
   const bool pair = ctx->srs_canonical && !ctx->force_exact;
   const bool wide = pair && ctx->d_wide_tables != nullptr;
   const unsigned grid = blocks_for(n, PBLOCK);
-#define PB_LAUNCH_PROVE(TABLES, FSMODE, TB, CH, CO) \
-  prove_kernel<TABLES, FSMODE><<<grid, PBLOCK, 0, st>>>(ctx->cc, TB, witness, rnd, CH, proofs, status, n, done_list, done_count, verdict, CO)
-  if (chal) {
-    if (wide) PB_LAUNCH_PROVE(ProverWideTables, false, ctx->d_wide_tables, chal, nullptr);
-    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, false, ctx->d_pair_tables, chal, nullptr);
-    else PB_LAUNCH_PROVE(ProverTables, false, ctx->d_tables, chal, nullptr);
+#define PB_LAUNCH_PROVE(TABLES, FSMODE, PK, TB, W, CH, CO) \
+  prove_kernel<TABLES, FSMODE, PK><<<grid, PBLOCK, 0, st>>>(ctx->cc, TB, W, rnd, CH, proofs, status, n, done_list, done_count, verdict, CO)
+  if (packed) {
+    if (wide) PB_LAUNCH_PROVE(ProverWideTables, false, true, ctx->d_wide_tables, packed, nullptr, nullptr);
+    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, false, true, ctx->d_pair_tables, packed, nullptr, nullptr);
+    else PB_LAUNCH_PROVE(ProverTables, false, true, ctx->d_tables, packed, nullptr, nullptr);
+  } else if (chal) {
+    if (wide) PB_LAUNCH_PROVE(ProverWideTables, false, false, ctx->d_wide_tables, witness, chal, nullptr);
+    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, false, false, ctx->d_pair_tables, witness, chal, nullptr);
+    else PB_LAUNCH_PROVE(ProverTables, false, false, ctx->d_tables, witness, chal, nullptr);
   } else {
-    if (wide) PB_LAUNCH_PROVE(ProverWideTables, true, ctx->d_wide_tables, nullptr, chal_out);
-    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, true, ctx->d_pair_tables, nullptr, chal_out);
-    else PB_LAUNCH_PROVE(ProverTables, true, ctx->d_tables, nullptr, chal_out);
+    if (wide) PB_LAUNCH_PROVE(ProverWideTables, true, false, ctx->d_wide_tables, witness, nullptr, chal_out);
+    else if (pair) PB_LAUNCH_PROVE(ProverPairTables, true, false, ctx->d_pair_tables, witness, nullptr, chal_out);
+    else PB_LAUNCH_PROVE(ProverTables, true, false, ctx->d_tables, witness, nullptr, chal_out);
   }
 #undef PB_LAUNCH_PROVE
   LAUNCH_CHECK("prove_kernel");
   return PB_OK;
 }
 static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
-                         const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st) {
+                         const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st,
+                         const uint8_t* packed = nullptr) {
+  const uint32_t* pk = reinterpret_cast<const uint32_t*>(packed);
   if (ctx->key_canonical && !ctx->force_exact && !(status && !done_list))
-    if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n);
-    else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n);
+    if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n, pk);
+    else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk);
   else
-    verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n);
+    verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n, pk);
   LAUNCH_CHECK("verify_kernel");
   return PB_OK;
 }
@@ -1127,14 +1164,15 @@ int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const u
                               uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream) {
   return pb_plonk_prove_verify_ex_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, nullptr);
 }
-// chal == u == nullptr: Fiat-Shamir mode
+// chal == u == nullptr: Fiat-Shamir mode; packed != nullptr: packed input records instead of witness / rnd / chal / u
 static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
-                            uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
+                            uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event,
+                            const uint8_t* packed = nullptr) {
   ARG(verdict);
   ARG(ctx && ctx->vk_valid);
-  ARG(witness && rnd && proofs && status);
+  ARG((packed || (witness && rnd)) && proofs && status);
   ARG((chal == nullptr) == (u == nullptr));
-  ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
+  ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status) && aligned16(packed));
   ARG(n < 0xFFFFFFFFull);
   // The prover appends the indices of the completed proofs to a dense list (stream-ordered scratch), the verifier walks
   // that list: no lane idles on the ~40% of random inputs on which the reference exits.
@@ -1143,9 +1181,9 @@ static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uin
   int rc = scratch_for(ctx, st, n, &scratch);
   if (rc) return rc;
   CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
-  rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict);
+  rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict, nullptr, packed);
   if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
-  if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st);
+  if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st, packed);
   return rc;
 }
 int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
@@ -1184,30 +1222,52 @@ int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal
   return PB_OK;
 }
 
+// dense list of the completed proofs of a chunk (stream-ordered): offs[0 .. groups) and the count in offs[cap / 128 + 3]
+static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t m, uint32_t* offs, uint32_t* count,
+                         uint8_t* dense, uint8_t* sv, bool pack, cudaStream_t st) {
+  done_offsets_kernel<<<1, 1024, 0, st>>>(status, m, offs, count);
+  LAUNCH_CHECK("done_offsets_kernel");
+  if (pack) gather_done_kernel<true><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
+  else gather_done_kernel<false><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
+  LAUNCH_CHECK("gather_done_kernel");
+  return PB_OK;
+}
+
 // host-pointer versions: a three-stage pipeline over chunks, one stream per hardware engine -- s_in (H2D copy engine),
 // s_k (SMs), s_out (D2H copy engine) -- tied together by events, over a ring of PIPE_SLOTS buffer sets:
-//   H2D(c) waits for kernels(c - SLOTS) (input buffers free);  kernels(c) wait for H2D(c) and D2H(c - SLOTS) (proof buffer free);
+//   H2D(c) waits for kernels(c - SLOTS) (input buffers free);  kernels(c) wait for H2D(c) and D2H(c - SLOTS) (output buffers free);
 //   D2H(c) waits for kernels(c).
 // The input stage therefore never waits for the (slower) output stage, so once the inputs are up the D2H engine has the
 // PCIe link to itself.  PCIe throughput on these hosts drops sharply for pieces below ~1 MB
-// (profiles/r1/pcie_probe.txt), so the one-byte-per-item arrays (u in, status and verdict out) are not chunked: u goes
+// (profiles/r1/pcie_probe.txt), so the one-byte-per-item arrays (u in; status, verdict or sv out) are not chunked: u goes
 // up with the first chunk, status and verdict come back after the last one.
+//
+// Modes (PipeMode): PROVE / STRUCT move the reference's structs both ways (27 B in, 34 + 2 B out per item).
+// COMPACT: struct inputs; only the proofs that exist come back -- the completed ones, dense, in item order (the zero
+// records of items on which the reference exits do not travel).  PACKED: packed wire v2 both ways (wire.cuh: 16 B in,
+// 22 B per completed proof + 1 B per item out).  In the last two the size of a chunk's D2H copy is known only when its
+// kernels have run: the host waits for chunk c - PIPE_LOOKAHEAD's kernels (the GPU has the chunks in between queued),
+// reads the count from pinned memory and issues that chunk's copy.
 static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
-                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, int mode /*0 prove, 1 prove+verify*/) {
+                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, int mode, size_t* n_done = nullptr) {
   pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
   DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(PB_ERR_CUDA, "plonk_b200: cudaSetDevice failed");
   std::lock_guard<std::mutex> lock(ctx->pipe_mu);
-  int rc = pipe_init(ctx);
+  const size_t chunk = pipe_chunk();
+  int rc = pipe_init(ctx, n < chunk ? n : chunk);
   if (rc) return rc;
   if (ctx->small_cap < n) {
-    for (uint8_t** p : {&ctx->d_u, &ctx->d_status, &ctx->d_verdict}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
+    for (uint8_t** p : {&ctx->d_u, &ctx->d_status, &ctx->d_verdict, &ctx->d_sv}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
+    ctx->small_cap = 0;
     size_t cap = (n + 255) & ~(size_t)255;
-    CU(cudaMalloc(&ctx->d_u, cap)); CU(cudaMalloc(&ctx->d_status, cap)); CU(cudaMalloc(&ctx->d_verdict, cap));
+    CU(cudaMalloc(&ctx->d_u, cap)); CU(cudaMalloc(&ctx->d_status, cap)); CU(cudaMalloc(&ctx->d_verdict, cap)); CU(cudaMalloc(&ctx->d_sv, cap));
     ctx->small_cap = cap;
   }
+  const bool packed = mode == PIPE_PACKED, dense = mode == PIPE_COMPACT || mode == PIPE_PACKED;
+  const size_t rec = packed ? PACKED_PROOF_BYTES : 34;
   // Chunk schedule: fill (first H2D + first kernels) and drain (last D2H) are exposed time, so the first and last chunks
   // are small and the sizes double towards the middle, where chunks have the full size pipe_chunk().
-  const size_t chunk = pipe_chunk();
   std::vector<size_t> sched;
   {
     const size_t small = 1u << 15;
@@ -1235,45 +1295,79 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     CU(cudaEventCreate(&t0));
     CU(cudaEventRecord(t0, ctx->s_in));
   }
+  size_t total_done = 0;
+  // compact / packed modes: the chunk's kernels have run -> its count is in pinned memory -> issue its D2H copy
+  auto finish = [&](size_t c) -> int {
+    PipeSlot& s = ctx->slots[c % PIPE_SLOTS];
+    CU(cudaEventSynchronize(s.ev_k));
+    const size_t cnt = ctx->h_count[c % PIPE_SLOTS];
+    if (cnt > sched[c]) return fail(PB_ERR_CUDA, "plonk_b200: dense-list count exceeds the chunk");
+    if (cnt) CU(cudaMemcpyAsync(proofs + total_done * rec, s.dense, cnt * rec, cudaMemcpyDeviceToHost, ctx->s_out));
+    CU(cudaEventRecord(s.ev_out, ctx->s_out));
+    if (trace) CU(cudaEventRecord(tev[3 * c + 2], ctx->s_out));
+    total_done += cnt;
+    return PB_OK;
+  };
   size_t done = 0, c = 0;
   for (size_t m : sched) {
+    if (dense && c >= (size_t)PIPE_LOOKAHEAD && (rc = finish(c - PIPE_LOOKAHEAD))) return rc;
     PipeSlot& s = ctx->slots[c % PIPE_SLOTS];
     const bool reuse = c >= (size_t)PIPE_SLOTS;
+    uint8_t *d_wit = s.in, *d_rnd = s.in + ctx->slot_cap * 12, *d_chal = s.in + ctx->slot_cap * 21;
     if (reuse) CU(cudaStreamWaitEvent(ctx->s_in, s.ev_k, 0));
-    CU(cudaMemcpyAsync(s.wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, ctx->s_in));
-    CU(cudaMemcpyAsync(s.rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, ctx->s_in));
-    if (chal) CU(cudaMemcpyAsync(s.chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, ctx->s_in));   // absent in Fiat-Shamir mode
-    if (mode == 1 && c == 0 && u) CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, ctx->s_in));
+    if (packed) {
+      CU(cudaMemcpyAsync(s.in, witness + done * PACKED_IN_BYTES, m * PACKED_IN_BYTES, cudaMemcpyHostToDevice, ctx->s_in));
+    } else {
+      CU(cudaMemcpyAsync(d_wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, ctx->s_in));
+      CU(cudaMemcpyAsync(d_rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, ctx->s_in));
+      if (chal) CU(cudaMemcpyAsync(d_chal, chal + done * 5, m * 5, cudaMemcpyHostToDevice, ctx->s_in));   // absent in Fiat-Shamir mode
+      if (mode != PIPE_PROVE && c == 0 && u) CU(cudaMemcpyAsync(ctx->d_u, u, n, cudaMemcpyHostToDevice, ctx->s_in));
+    }
     CU(cudaEventRecord(s.ev_in, ctx->s_in));
     if (trace) CU(cudaEventRecord(tev[3 * c], ctx->s_in));
     CU(cudaStreamWaitEvent(ctx->s_k, s.ev_in, 0));
     if (reuse) CU(cudaStreamWaitEvent(ctx->s_k, s.ev_out, 0));
-    static const bool nokernel = getenv("PB_PIPE_NOKERNEL") && getenv("PB_PIPE_NOKERNEL")[0] == '1';   // copy-only timing experiment
-    if (nokernel)
-      rc = PB_OK;
-    else if (mode == 1)
-      rc = prove_verify_dev(ctx, s.wit, s.rnd, chal ? s.chal : nullptr, u ? ctx->d_u + done : nullptr, s.proofs, ctx->d_status + done,
+    if (packed)
+      rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, ctx->s_k, nullptr, s.in);
+    else if (mode != PIPE_PROVE)
+      rc = prove_verify_dev(ctx, d_wit, d_rnd, chal ? d_chal : nullptr, u ? ctx->d_u + done : nullptr, s.proofs, ctx->d_status + done,
                             ctx->d_verdict + done, m, ctx->s_k, nullptr);
     else if (chal)
-      rc = pb_plonk_prove_dev(ctx, s.wit, s.rnd, s.chal, s.proofs, ctx->d_status + done, m, ctx->s_k);
+      rc = pb_plonk_prove_dev(ctx, d_wit, d_rnd, d_chal, s.proofs, ctx->d_status + done, m, ctx->s_k);
     else
-      rc = pb_plonk_prove_fs_dev(ctx, s.wit, s.rnd, s.proofs, ctx->d_status + done, nullptr, m, ctx->s_k);
+      rc = pb_plonk_prove_fs_dev(ctx, d_wit, d_rnd, s.proofs, ctx->d_status + done, nullptr, m, ctx->s_k);
     if (rc) return rc;
+    if (dense) {
+      uint32_t* cnt = s.offs + ctx->slot_cap / 128 + 3;
+      if ((rc = launch_gather(s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.offs, cnt, s.dense, ctx->d_sv + done, packed, ctx->s_k))) return rc;
+      CU(cudaMemcpyAsync(ctx->h_count + c % PIPE_SLOTS, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_k));
+    }
     CU(cudaEventRecord(s.ev_k, ctx->s_k));
     if (trace) CU(cudaEventRecord(tev[3 * c + 1], ctx->s_k));
-    CU(cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
-    CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, ctx->s_out));
-    CU(cudaEventRecord(s.ev_out, ctx->s_out));
-    if (trace) CU(cudaEventRecord(tev[3 * c + 2], ctx->s_out));
+    if (!dense) {
+      CU(cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
+      CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, ctx->s_out));
+      CU(cudaEventRecord(s.ev_out, ctx->s_out));
+      if (trace) CU(cudaEventRecord(tev[3 * c + 2], ctx->s_out));
+    }
     done += m;
     c++;
   }
+  if (dense)
+    for (size_t k = c > (size_t)PIPE_LOOKAHEAD ? c - PIPE_LOOKAHEAD : 0; k < c; k++)
+      if ((rc = finish(k))) return rc;
   // s_out is ordered after the last kernels (ev_k of the last chunk), which are ordered after all earlier ones on s_k
-  CU(cudaMemcpyAsync(status, ctx->d_status, n, cudaMemcpyDeviceToHost, ctx->s_out));
-  if (mode == 1) CU(cudaMemcpyAsync(verdict, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->s_out));
+  if (!dense && c) CU(cudaStreamWaitEvent(ctx->s_out, ctx->slots[(c - 1) % PIPE_SLOTS].ev_k, 0));
+  if (packed) {
+    CU(cudaMemcpyAsync(status /* = sv */, ctx->d_sv, n, cudaMemcpyDeviceToHost, ctx->s_out));
+  } else {
+    CU(cudaMemcpyAsync(status, ctx->d_status, n, cudaMemcpyDeviceToHost, ctx->s_out));
+    if (mode != PIPE_PROVE) CU(cudaMemcpyAsync(verdict, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->s_out));
+  }
   CU(cudaStreamSynchronize(ctx->s_out));
   CU(cudaStreamSynchronize(ctx->s_in));
   CU(cudaStreamSynchronize(ctx->s_k));
+  if (n_done) *n_done = total_done;
   if (trace) {
     for (size_t k = 0; k < sched.size(); k++) {
       float a = 0, b = 0, d = 0;
@@ -1288,19 +1382,224 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
 int pb_plonk_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
-  return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, n, 0);
+  return pipeline(ctx, witness, rnd, chal, nullptr, proofs, status, nullptr, n, PIPE_PROVE);
 }
 int pb_plonk_prove_verify(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                           uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && u && proofs && status && verdict);
   ARG(ctx->vk_valid);
-  return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, n, 1);
+  return pipeline(ctx, witness, rnd, chal, u, proofs, status, verdict, n, PIPE_STRUCT);
 }
+// ---- compact output, packed wire v2, seeded mode (wire.cuh) ------------------------------------------------------------
+int pb_plonk_prove_verify_compact(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                                  uint8_t* proofs_dense, size_t* n_done, uint8_t* status, uint8_t* verdict, size_t n) {
+  if (n_done) *n_done = 0;
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(ctx && witness && rnd && chal && u && proofs_dense && n_done && status && verdict);
+  ARG(ctx->vk_valid);
+  return pipeline(ctx, witness, rnd, chal, u, proofs_dense, status, verdict, n, PIPE_COMPACT, n_done);
+}
+int pb_plonk_prove_verify_packed(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, size_t* n_done, uint8_t* sv, size_t n) {
+  if (n_done) *n_done = 0;
+  if (n == 0) return PB_OK;
+  ARG(ctx && packed_in && packed_proofs && n_done && sv);
+  ARG(ctx->vk_valid);
+  return pipeline(ctx, packed_in, nullptr, nullptr, nullptr, packed_proofs, sv, nullptr, n, PIPE_PACKED, n_done);
+}
+size_t pb_packed_workspace_bytes(size_t n) {
+  const size_t cap = (n + 127) & ~(size_t)127;
+  return cap * 34 + cap + cap + (cap / 128 + 4) * sizeof(uint32_t) + 64;   // proofs | status | verdict | offs
+}
+int pb_plonk_prove_verify_packed_dev(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, uint32_t* n_done_dev, uint8_t* sv,
+                                     void* workspace, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && packed_in && packed_proofs && n_done_dev && sv && workspace);
+  ARG(aligned16(packed_in) && aligned16(packed_proofs) && aligned16(workspace));
+  const size_t cap = (n + 127) & ~(size_t)127;
+  uint8_t* proofs = static_cast<uint8_t*>(workspace);
+  uint8_t* status = proofs + cap * 34;
+  uint8_t* verdict = status + cap;
+  uint32_t* offs = reinterpret_cast<uint32_t*>(verdict + cap);
+  int rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed_in);
+  if (rc) return rc;
+  return launch_gather(proofs, status, verdict, n, offs, n_done_dev, packed_proofs, sv, true, S(stream));
+}
+int pb_gather_completed_dev(const uint8_t* proofs, const uint8_t* status, uint8_t* proofs_dense, uint32_t* n_done_dev, uint32_t* offs_scratch,
+                            size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(proofs && status && proofs_dense && n_done_dev && offs_scratch);
+  ARG(aligned16(proofs) && aligned16(proofs_dense));
+  return launch_gather(proofs, status, nullptr, n, offs_scratch, n_done_dev, proofs_dense, nullptr, false, S(stream));
+}
+
+// format conversion on the host (no arithmetic of the path): the reference's structs <-> packed wire v2
+int pb_wire_pack_inputs(const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u, uint8_t* packed, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(witness && rnd && chal && u && packed);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t v[PACKED_VALUES], w[4];
+    for (int k = 0; k < 12; k++) v[k] = witness[i * 12 + k];
+    for (int k = 0; k < 9; k++) v[12 + k] = rnd[i * 9 + k];
+    for (int k = 0; k < 5; k++) v[21 + k] = chal[i * 5 + k];
+    v[26] = u[i];
+    bool ok = true;
+    for (int k = 0; k < PACKED_VALUES; k++) ok = ok && v[k] < 17u;
+    if (ok) pack_input16(v, w);
+    else w[0] = w[1] = w[2] = w[3] = 0xFFFFFFFFu;   // not an encoding: the prover reports PB_PROVE_BAD_INPUT, as for the struct bytes
+    for (int k = 0; k < 4; k++) for (int b = 0; b < 4; b++) packed[i * 16 + 4 * k + b] = (uint8_t)(w[k] >> (8 * b));
+  }
+  return PB_OK;
+}
+int pb_wire_unpack_inputs(const uint8_t* packed, uint8_t* witness, uint8_t* rnd, uint8_t* chal, uint8_t* u, uint8_t* valid, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(packed && witness && rnd && chal && u);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[4], v[PACKED_VALUES];
+    for (int k = 0; k < 4; k++) { w[k] = 0; for (int b = 0; b < 4; b++) w[k] |= (uint32_t)packed[i * 16 + 4 * k + b] << (8 * b); }
+    const bool ok = unpack_input16(w[0], w[1], w[2], w[3], v);
+    for (int k = 0; k < 12; k++) witness[i * 12 + k] = ok ? (uint8_t)v[k] : 0xFF;
+    for (int k = 0; k < 9; k++) rnd[i * 9 + k] = ok ? (uint8_t)v[12 + k] : 0xFF;
+    for (int k = 0; k < 5; k++) chal[i * 5 + k] = ok ? (uint8_t)v[21 + k] : 0xFF;
+    u[i] = ok ? (uint8_t)v[26] : 0xFF;
+    if (valid) valid[i] = ok ? 1 : 0;
+  }
+  return PB_OK;
+}
+int pb_wire_pack_proofs(const uint8_t* proofs, uint8_t* packed, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(proofs && packed);
+  for (size_t i = 0; i < n; i++) {
+    uint16_t r[11];
+    pack_proof22(proofs + i * 34, r);
+    for (int k = 0; k < 11; k++) { packed[i * 22 + 2 * k] = (uint8_t)(r[k] & 0xFF); packed[i * 22 + 2 * k + 1] = (uint8_t)(r[k] >> 8); }
+  }
+  return PB_OK;
+}
+int pb_wire_unpack_proofs(const uint8_t* packed, uint8_t* proofs, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(packed && proofs);
+  for (size_t i = 0; i < n; i++) {
+    uint16_t r[11];
+    for (int k = 0; k < 11; k++) r[k] = (uint16_t)(packed[i * 22 + 2 * k] | packed[i * 22 + 2 * k + 1] << 8);
+    if (!unpack_proof22(r, proofs + i * 34)) return fail(PB_ERR_ARG, "plonk_b200: packed proof record is not a canonical encoding");
+  }
+  return PB_OK;
+}
+// dense completed proofs + status bytes -> the full [n][34] array of the struct API (zero records where status != 0)
+int pb_wire_scatter_proofs(const uint8_t* proofs_dense, const uint8_t* status, uint8_t* proofs, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(proofs_dense && status && proofs);
+  size_t k = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (status[i] == 0) memcpy(proofs + i * 34, proofs_dense + (k++) * 34, 34);
+    else memset(proofs + i * 34, 0, 34);
+  }
+  return PB_OK;
+}
+int pb_wire_split_sv(const uint8_t* sv, uint8_t* status, uint8_t* verdict, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(sv);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t s = sv[i] & 15u, v = sv[i] >> 4;
+    if (status) status[i] = s == 15u ? 254 : s;
+    if (verdict) verdict[i] = v == 15u ? 0xFF : v;
+  }
+  return PB_OK;
+}
+
+// seeded mode: inputs are generated on the device from (seed, start, count) -- the counter-based stream of
+// plonk.c_b200/workload.py -- and only the 18 counters come back.  No batch data crosses PCIe.
+static int seeded_tables(pb_ctx* ctx) {
+  if (ctx->d_wtab) return PB_OK;
+  uint8_t tab[SYNTH_WITNESS_ROWS * 12];
+  int rows = 0;
+  for (uint32_t x = 0; x < 17; x++)
+    for (uint32_t y = 0; y < 17; y++)
+      for (uint32_t z = 0; z < 17; z++)
+        if ((x * x + y * y) % 17u == (z * z) % 17u) {
+          const uint8_t xx = (uint8_t)(x * x % 17u), yy = (uint8_t)(y * y % 17u), zz = (uint8_t)(z * z % 17u);
+          const uint8_t row[12] = {(uint8_t)x, (uint8_t)y, (uint8_t)z, xx, (uint8_t)x, (uint8_t)y, (uint8_t)z, yy, xx, yy, zz, zz};
+          if (rows < SYNTH_WITNESS_ROWS) memcpy(tab + 12 * rows, row, 12);
+          rows++;
+        }
+  if (rows != SYNTH_WITNESS_ROWS) return fail(PB_ERR_CUDA, "plonk_b200: witness table does not have 289 rows");
+  CU(cudaMalloc(&ctx->d_wtab, sizeof tab));
+  CU(cudaMemcpy(ctx->d_wtab, tab, sizeof tab, cudaMemcpyHostToDevice));
+  return PB_OK;
+}
+size_t pb_seeded_workspace_bytes(size_t n) { return ((n + 127) & ~(size_t)127) * 16 + pb_packed_workspace_bytes(n); }
+int pb_synth_batch_dev(const pb_ctx* cctx, uint64_t seed, uint64_t start, size_t n, int variant, uint8_t* witness, uint8_t* rnd, uint8_t* chal,
+                       uint8_t* u, uint8_t* packed, void* stream) {
+  if (n == 0) return PB_OK;
+  pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
+  ARG(ctx && (variant == 0 || variant == 1));
+  ARG(packed || (witness && rnd && chal && u));
+  ARG(aligned16(packed));
+  if (!ctx->d_wtab) {   // first use on this context (pb_plonk_prove_verify_seeded has done this already, under the same lock)
+    std::lock_guard<std::mutex> lock(ctx->pipe_mu);
+    int rc = seeded_tables(ctx);
+    if (rc) return rc;
+  }
+  if (packed) synth_packed_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(seed, start, variant, ctx->d_wtab, packed, n);
+  if (witness) synth_struct_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(seed, start, variant, ctx->d_wtab, witness, rnd, chal, u, n);
+  LAUNCH_CHECK("synth_kernel");
+  return PB_OK;
+}
+int pb_plonk_prove_verify_seeded_dev(const pb_ctx* ctx, uint64_t seed, uint64_t start, size_t n, int variant, void* workspace,
+                                     int64_t* counts_dev, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && workspace && counts_dev && aligned16(workspace));
+  ARG(ctx->vk_valid);
+  const size_t cap = (n + 127) & ~(size_t)127;
+  uint8_t* packed = static_cast<uint8_t*>(workspace);
+  uint8_t* proofs = packed + cap * 16;
+  uint8_t* status = proofs + cap * 34;
+  uint8_t* verdict = status + cap;
+  int rc = pb_synth_batch_dev(ctx, seed, start, n, variant, nullptr, nullptr, nullptr, nullptr, packed, stream);
+  if (!rc) rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed);
+  if (!rc) rc = pb_tally_dev(proofs, status, verdict, n, counts_dev, stream);
+  return rc;
+}
+int pb_plonk_prove_verify_seeded(const pb_ctx* cctx, uint64_t seed, uint64_t start, size_t count, int variant, int64_t counts[18]) {
+  ARG(cctx && counts);
+  ARG(cctx->vk_valid);
+  for (int k = 0; k < 18; k++) counts[k] = 0;
+  if (count == 0) return PB_OK;
+  pb_ctx* ctx = const_cast<pb_ctx*>(cctx);
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(PB_ERR_CUDA, "plonk_b200: cudaSetDevice failed");
+  const size_t chunk = 1u << 21;
+  const size_t items = count < chunk ? count : chunk;
+  int64_t* d_counts = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx->pipe_mu);
+    if (ctx->seed_ws_items < items) {
+      if (ctx->d_seed_ws) CU(cudaFree(ctx->d_seed_ws));
+      ctx->d_seed_ws = nullptr; ctx->seed_ws_items = 0;
+      CU(cudaMalloc(&ctx->d_seed_ws, pb_seeded_workspace_bytes(items) + 256));
+      ctx->seed_ws_items = items;
+    }
+    int rc = pipe_init(ctx, 128);
+    if (!rc) rc = seeded_tables(ctx);
+    if (rc) return rc;
+    d_counts = reinterpret_cast<int64_t*>(ctx->d_seed_ws + ((pb_seeded_workspace_bytes(items) + 15) & ~(size_t)15));
+    CU(cudaMemsetAsync(d_counts, 0, 18 * sizeof(int64_t), ctx->s_k));
+    for (size_t done = 0; done < count; done += chunk) {
+      const size_t m = count - done < chunk ? count - done : chunk;
+      rc = pb_plonk_prove_verify_seeded_dev(ctx, seed, start + done, m, variant, ctx->d_seed_ws, d_counts, ctx->s_k);
+      if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(counts, d_counts, 18 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->s_k));
+    CU(cudaStreamSynchronize(ctx->s_k));
+  }
+  return PB_OK;
+}
+
 int pb_plonk_prove_fs(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status, uint8_t* chal_out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && proofs && status);
-  if (!chal_out) return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, nullptr, n, 0);
+  if (!chal_out) return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, nullptr, n, PIPE_PROVE);
   DeviceGuard g(ctx->device);   // with the challenge read-back: one unchunked launch
   DEV(dw, n * 12); DEV(dr, n * 9); DEV(dp, n * 34); DEV(ds, n); DEV(dc, n * 6);
   H2D(dw, witness, n * 12); H2D(dr, rnd, n * 9);
@@ -1315,7 +1614,7 @@ int pb_plonk_prove_verify_fs(const pb_ctx* ctx, const uint8_t* witness, const ui
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && proofs && status && verdict);
   ARG(ctx->vk_valid);
-  return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, verdict, n, 1);
+  return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, verdict, n, PIPE_STRUCT);
 }
 int pb_plonk_verify_fs(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* verdict, uint8_t* gt, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer

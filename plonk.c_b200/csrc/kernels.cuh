@@ -3,6 +3,7 @@
 #pragma once
 #include "prover.cuh"
 #include "verifier.cuh"
+#include "wire.cuh"
 
 namespace pb {
 
@@ -618,7 +619,9 @@ struct __align__(16) ProveSmem {
 #endif
 // FS = true (Fiat-Shamir mode, transcript.cuh): `chal` is not read; chal_out (optional) [n][6] receives the challenges
 // drawn before the item's first exit (alpha beta gamma z v u), 0xFF for the ones not drawn.
-template <typename Tables, bool FS = false>
+// PACKED = true (packed wire v2, wire.cuh): `wit` holds the 16-byte packed input records, one 128-bit load per lane and no
+// shared-memory staging of the inputs; `rnd` and `chal` are not read.
+template <typename Tables, bool FS = false, bool PACKED = false>
 __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const __grid_constant__ CircuitConst cc, const Tables* __restrict__ gtb,
                                                       const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
@@ -630,6 +633,29 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   for (int k = tid; k < (int)(sizeof(Tables) / 4); k += PBLOCK)
     reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
   const size_t first = (size_t)blockIdx.x * PBLOCK;
+  static_assert(!(FS && PACKED), "the packed records carry the challenges");
+  const bool live = first + tid < n;
+  uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
+  bool bad = false;
+  if constexpr (PACKED) {
+#if PB_PROVE_PREFETCH
+    {
+      const size_t pf = first + (size_t)PB_PROVE_PREFETCH * PBLOCK;   // 16 lines of 128 bytes per block
+      if (pf + PBLOCK <= n && tid < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(wit + pf * 16 + tid * 128));
+    }
+#endif
+    uint32_t v[PACKED_VALUES];
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (live) q = reinterpret_cast<const uint4*>(wit)[first + tid];
+    bad = !unpack_input16(q.x, q.y, q.z, q.w, v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { wa[k] = v[k]; wb[k] = v[4 + k]; wc[k] = v[8 + k]; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = v[12 + k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = v[21 + k];
+    __syncthreads();   // tables staged
+  } else {
 #if PB_PROVE_PREFETCH
   {
     // pull the inputs of the block that will take this block's slot next (~ one resident wave ahead) into L2, so that its
@@ -645,9 +671,6 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   stage_in<9, PBLOCK>(sm.rnd, rnd, first, n);
   if constexpr (!FS) stage_in<5, PBLOCK>(sm.chal, chal, first, n);
   __syncthreads();
-  const bool live = first + tid < n;
-  uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
-  bool bad = false;
 #pragma unroll
   for (int k = 0; k < 4; k++) { wa[k] = sm.wit[tid * 12 + k]; wb[k] = sm.wit[tid * 12 + 4 + k]; wc[k] = sm.wit[tid * 12 + 8 + k]; }
 #pragma unroll
@@ -660,6 +683,7 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   for (int k = 0; k < 9; k++) bad |= r[k] > 16u;
 #pragma unroll
   for (int k = 0; k < 5; k++) bad |= ch[k] > 16u;
+  }
   if (bad || !live) {   // keep table indices in range; the item is reported as PB_PROVE_BAD_INPUT
 #pragma unroll
     for (int k = 0; k < 4; k++) { wa[k] = 0; wb[k] = 0; wc[k] = 0; }
@@ -735,17 +759,19 @@ struct __align__(16) VerifySmem {
 };
 
 // status (optional): items whose status byte is non-zero are skipped and get verdict 0xFF
+// packed (optional): the 16-byte packed input records (wire.cuh); the challenges and u are then word 3 of the item's record
+// and `chal` / `u` are not read.
 __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ VerifyKey key, const uint8_t* __restrict__ proofs,
                                                        const uint8_t* __restrict__ chal, const uint8_t* __restrict__ u,
                                                        const uint8_t* __restrict__ status, uint8_t* __restrict__ verdict,
-                                                       uint8_t* __restrict__ gt, size_t n) {
+                                                       uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr) {
   __shared__ VerifySmem sm;
   const int tid = threadIdx.x;
   build_field_tables(sm.ft);
   const size_t first = (size_t)blockIdx.x * BLOCK;
-  const bool fs = chal == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
+  const bool fs = chal == nullptr && packed == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
   stage_in<34, BLOCK>(sm.proof, proofs, first, n);
-  if (!fs) stage_in<5, BLOCK>(sm.chal, chal, first, n);
+  if (chal) stage_in<5, BLOCK>(sm.chal, chal, first, n);
   __syncthreads();
   const size_t i = first + tid;
   if (i >= n) return;
@@ -762,6 +788,12 @@ __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ V
   uint32_t uu;
   if (fs) {
     fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  } else if (packed) {
+    uint32_t d[7];
+    unpack7(packed[i * 4 + 3], d);      // a non-canonical word never gets here: the prover reports the item as bad input
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = d[k];
+    uu = d[5];
   } else {
 #pragma unroll
     for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
@@ -788,7 +820,7 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
                                                             const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                             const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
                                                             const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
-                                                            uint8_t* __restrict__ gt, size_t n) {
+                                                            uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr) {
   __shared__ VerifyFastSmem sm;
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * BLOCK;
@@ -799,7 +831,7 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
     reinterpret_cast<uint32_t*>(&sm.vt)[k] = reinterpret_cast<const uint32_t*>(gvt)[k];
   size_t item = first + tid;
   const bool live = item < limit;
-  const bool fs = chal == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
+  const bool fs = chal == nullptr && packed == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
   uint32_t pbytes[27], op[7], ch[5];
   if (done_list) {
     // dense-list mode: the items of a block are scattered, so each lane reads its own 34-byte record straight into
@@ -815,27 +847,36 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
     for (int k = 0; k < 27; k++) pbytes[k] = b[k];
 #pragma unroll
     for (int k = 0; k < 7; k++) op[k] = b[27 + k];
-    if (!fs) {
+    if (chal) {
 #pragma unroll
       for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
     }
   } else {
     stage_in<34, BLOCK>(sm.proof, proofs, first, n);
-    if (!fs) stage_in<5, BLOCK>(sm.chal, chal, first, n);
+    if (chal) stage_in<5, BLOCK>(sm.chal, chal, first, n);
     __syncthreads();
     if (!live) return;
 #pragma unroll
     for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
 #pragma unroll
     for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
-    if (!fs) {
+    if (chal) {
 #pragma unroll
       for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
     }
   }
   uint32_t uu;
-  if (fs) fs_derive(key.fs_seed, pbytes, op, ch, uu);
-  else uu = u[item];
+  if (fs) {
+    fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  } else if (packed) {
+    uint32_t d[7];
+    unpack7(packed[item * 4 + 3], d);   // a non-canonical word never gets here: the prover reports the item as bad input
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = d[k];
+    uu = d[5];
+  } else {
+    uu = u[item];
+  }
   VerifyOut o;
   verify_one_fast<WANT_GT>(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
   verdict[item] = (uint8_t)o.verdict;
@@ -856,6 +897,153 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) compact_kernel(const uint8_t* __r
   base = __shfl_sync(0xFFFFFFFFu, base, leader < 0 ? 0 : leader);
   if (done) done_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
   if (live && !done) verdict[i] = 0xFF;
+}
+
+// ------------------------------------------------------------------ compact / packed outputs, synthetic inputs (wire.cuh)
+// Only the proofs that exist travel back to the host: a dense array of the completed proofs (status 0) in item order.
+// Step 1: offs[g] = number of completed items before group g (GBLOCK items per group), *total = all of them.
+// One block: the status bytes of a chunk are at most a megabyte and hot in L2.
+constexpr int GBLOCK = 128;
+__global__ void __launch_bounds__(1024) done_offsets_kernel(const uint8_t* __restrict__ status, size_t m, uint32_t* __restrict__ offs,
+                                                            uint32_t* __restrict__ total) {
+  __shared__ uint32_t wsum[32];
+  const uint32_t G = (uint32_t)((m + GBLOCK - 1) / GBLOCK);
+  const bool al = (reinterpret_cast<uintptr_t>(status) & 15u) == 0;
+  for (uint32_t g = threadIdx.x; g < G; g += 1024u) {
+    const size_t lo = (size_t)g * GBLOCK, hi = lo + GBLOCK < m ? lo + GBLOCK : m;
+    uint32_t c = 0;
+    if (al && hi - lo == GBLOCK) {
+#pragma unroll
+      for (int k = 0; k < GBLOCK / 16; k++) {
+        const uint4 q = reinterpret_cast<const uint4*>(status + lo)[k];
+        c += (uint32_t)(__popc(__vcmpeq4(q.x, 0u)) + __popc(__vcmpeq4(q.y, 0u)) + __popc(__vcmpeq4(q.z, 0u)) + __popc(__vcmpeq4(q.w, 0u))) >> 3;
+      }
+    } else {
+      for (size_t i = lo; i < hi; i++) c += status[i] == 0 ? 1u : 0u;
+    }
+    offs[g] = c;
+  }
+  __syncthreads();
+  // exclusive scan in place: thread t owns the contiguous groups [t * per, (t + 1) * per)
+  const uint32_t per = (G + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per < G ? threadIdx.x * per : G, hi = lo + per < G ? lo + per : G;
+  uint32_t mine = 0;
+  for (uint32_t g = lo; g < hi; g++) mine += offs[g];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((threadIdx.x & 31) >= d) incl += t; }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = wsum[threadIdx.x], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)threadIdx.x >= d) wi += t; }
+    wsum[threadIdx.x] = wi - w;
+    if (threadIdx.x == 31) *total = wi;
+  }
+  __syncthreads();
+  uint32_t run = wsum[threadIdx.x >> 5] + incl - mine;
+  for (uint32_t g = lo; g < hi; g++) { const uint32_t c = offs[g]; offs[g] = run; run += c; }
+}
+
+// Step 2: block g moves its completed PROOF records to dense[offs[g]...], as 34-byte structs (PACK = false) or as 22-byte
+// packed records (PACK = true; then sv[i] = status/verdict nibbles is written for every item as well).  The records of a
+// block form one contiguous run of the output; it is assembled in shared memory at the same 16-byte phase as its
+// destination, so that the body goes out in 128-bit stores.  dense must be 16-byte aligned.
+template <bool PACK>
+__global__ void __launch_bounds__(GBLOCK) gather_done_kernel(const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ status,
+                                                             const uint8_t* __restrict__ verdict, size_t m, const uint32_t* __restrict__ offs,
+                                                             uint8_t* __restrict__ dense, uint8_t* __restrict__ sv) {
+  constexpr int REC = PACK ? PACKED_PROOF_BYTES : 34;
+  __shared__ __align__(16) uint8_t src[GBLOCK * 34];
+  __shared__ __align__(16) uint8_t dst[GBLOCK * REC + 16];
+  __shared__ uint32_t wcnt[GBLOCK / 32];
+  const int tid = threadIdx.x;
+  const size_t first = (size_t)blockIdx.x * GBLOCK;
+  const bool live = first + tid < m;
+  stage_in<34, GBLOCK>(src, proofs, first, m);
+  const uint32_t st = live ? status[first + tid] : 1u;
+  if (PACK && live) sv[first + tid] = (uint8_t)sv_byte(st, verdict ? verdict[first + tid] : 0xFFu);
+  const bool done = live && st == 0u;
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, done);
+  if ((tid & 31) == 0) wcnt[tid >> 5] = (uint32_t)__popc(bal);
+  __syncthreads();
+  uint32_t rank = (uint32_t)__popc(bal & ((1u << (tid & 31)) - 1u)), cnt = 0;
+#pragma unroll
+  for (int w = 0; w < GBLOCK / 32; w++) { if (w < (tid >> 5)) rank += wcnt[w]; cnt += wcnt[w]; }
+  const size_t g0 = (size_t)offs[blockIdx.x] * REC;
+  const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(dense) + g0) & 15u);   // even: REC is even
+  if (done) {
+    uint16_t* o = reinterpret_cast<uint16_t*>(dst + skew + rank * REC);
+    if (PACK) {
+      uint16_t rec[11];
+      pack_proof22(src + tid * 34, rec);
+#pragma unroll
+      for (int k = 0; k < 11; k++) o[k] = rec[k];
+    } else {
+      const uint16_t* i16 = reinterpret_cast<const uint16_t*>(src + tid * 34);
+#pragma unroll
+      for (int k = 0; k < 17; k++) o[k] = i16[k];
+    }
+  }
+  __syncthreads();
+  const uint32_t total = cnt * REC;
+  uint32_t head = (16u - skew) & 15u;
+  if (head > total) head = total;
+  const uint32_t body = (total - head) & ~15u;
+  uint8_t* out = dense + g0;
+  const uint8_t* in = dst + skew;
+  for (uint32_t k = 2u * tid; k < head; k += 2u * GBLOCK) *reinterpret_cast<uint16_t*>(out + k) = *reinterpret_cast<const uint16_t*>(in + k);
+  for (uint32_t k = tid; k < body / 16u; k += GBLOCK) reinterpret_cast<uint4*>(out + head)[k] = reinterpret_cast<const uint4*>(in + head)[k];
+  for (uint32_t k = head + body + 2u * tid; k < total; k += 2u * GBLOCK) *reinterpret_cast<uint16_t*>(out + k) = *reinterpret_cast<const uint16_t*>(in + k);
+}
+
+// items [start, start + n) of the synthetic stream `seed` (wire.cuh: synth_item = workload.py make_batch) as packed input
+// records: one 128-bit store per lane.  wtab: the 289-row witness table [289][12].
+__global__ void __launch_bounds__(BLOCK_LIGHT) synth_packed_kernel(unsigned long long seed, unsigned long long start, int variant,
+                                                                   const uint8_t* __restrict__ wtab, uint8_t* __restrict__ packed, size_t n) {
+  __shared__ uint8_t tab[SYNTH_WITNESS_ROWS * 12];
+  for (int k = threadIdx.x; k < SYNTH_WITNESS_ROWS * 12; k += BLOCK_LIGHT) tab[k] = wtab[k];
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * BLOCK_LIGHT + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v[PACKED_VALUES], w[4];
+  synth_item(seed, start + i, variant, tab, v);
+  pack_input16(v, w);
+  reinterpret_cast<uint4*>(packed)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// the same items as the reference's structs: witness[n][12], rnd[n][9], chal[n][5], u[n]
+__global__ void __launch_bounds__(BLOCK_LIGHT) synth_struct_kernel(unsigned long long seed, unsigned long long start, int variant,
+                                                                   const uint8_t* __restrict__ wtab, uint8_t* __restrict__ wit,
+                                                                   uint8_t* __restrict__ rnd, uint8_t* __restrict__ chal, uint8_t* __restrict__ u, size_t n) {
+  __shared__ uint8_t tab[SYNTH_WITNESS_ROWS * 12];
+  for (int k = threadIdx.x; k < SYNTH_WITNESS_ROWS * 12; k += BLOCK_LIGHT) tab[k] = wtab[k];
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * BLOCK_LIGHT + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v[PACKED_VALUES];
+  synth_item(seed, start + i, variant, tab, v);
+  for (int k = 0; k < 12; k++) wit[i * 12 + k] = (uint8_t)v[k];
+  for (int k = 0; k < 9; k++) rnd[i * 9 + k] = (uint8_t)v[12 + k];
+  for (int k = 0; k < 5; k++) chal[i * 5 + k] = (uint8_t)v[21 + k];
+  u[i] = (uint8_t)v[26];
+}
+// struct arrays <-> packed records on the device (format conversion for callers that hold one and want the other)
+__global__ void __launch_bounds__(BLOCK_LIGHT) pack_inputs_kernel(const uint8_t* __restrict__ wit, const uint8_t* __restrict__ rnd,
+                                                                  const uint8_t* __restrict__ chal, const uint8_t* __restrict__ u,
+                                                                  uint8_t* __restrict__ packed, size_t n) {
+  const size_t i = (size_t)blockIdx.x * BLOCK_LIGHT + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v[PACKED_VALUES], w[4];
+  for (int k = 0; k < 12; k++) v[k] = wit[i * 12 + k];
+  for (int k = 0; k < 9; k++) v[12 + k] = rnd[i * 9 + k];
+  for (int k = 0; k < 5; k++) v[21 + k] = chal[i * 5 + k];
+  v[26] = u[i];
+  bool ok = true;
+  for (int k = 0; k < PACKED_VALUES; k++) ok &= v[k] < 17u;
+  pack_input16(v, w);
+  if (!ok) w[0] = w[1] = w[2] = w[3] = 0xFFFFFFFFu;     // not an encoding: the prover reports PB_PROVE_BAD_INPUT, as it does for the struct bytes
+  reinterpret_cast<uint4*>(packed)[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // pair tables from single-point rows: out[j][c0*17 + c1] = g1_add(T[2j][c0], T[2j+1][c1]) (row beyond `rows`: identity)

@@ -94,6 +94,20 @@ class _Call:
         self.keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
 
+    def outbuf(self, x, shape):
+        """A caller-owned OUTPUT buffer: it must already be C-contiguous uint8 of the right size -- coercing it would make
+        the library write into a temporary copy and leave the caller's buffer untouched."""
+        if self.dev:
+            if not (_is_torch(x) and x.dtype == self.torch.uint8 and x.is_contiguous() and tuple(x.shape) == tuple(shape)):
+                raise ValueError(f"output buffer must be a contiguous torch.uint8 CUDA tensor of shape {tuple(shape)}")
+            self.keep.append(x)
+            return C.c_void_p(x.data_ptr())
+        if not (isinstance(x, np.ndarray) and x.dtype == np.uint8 and x.flags.c_contiguous and x.flags.writeable
+                and tuple(x.shape) == tuple(shape)):
+            raise ValueError(f"output buffer must be a writeable C-contiguous uint8 numpy array of shape {tuple(shape)}")
+        self.keep.append(x)
+        return x.ctypes.data_as(C.c_void_p)
+
     def out(self, shape, dtype=np.uint8):
         if self.dev:
             t = self.torch.empty(shape, dtype=self.torch.uint8 if dtype == np.uint8 else self.torch.int64, device=self.device)
@@ -499,8 +513,8 @@ class Plonk:
     def prove_verify_fs_into(self, witness, rnd, proofs, status, verdict, mid_event=None):
         c = _Call("pb_plonk_prove_verify_fs", witness, rnd, proofs, status, verdict)
         n = _n(witness)
-        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(proofs), c.inp(status), c.inp(verdict), C.c_size_t(n),
-              dev_tail=(mid_event,))
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.outbuf(proofs, (n, 34)), c.outbuf(status, (n,)), c.outbuf(verdict, (n,)),
+              C.c_size_t(n), dev_tail=(mid_event,))
 
     def fs_challenges(self, proofs):
         """the six challenges of each PROOF record as a verifier derives them -> chal[n][6]"""
@@ -515,8 +529,157 @@ class Plonk:
         on the call path.  This is what bench.py times."""
         c = _Call("pb_plonk_prove_verify", witness, rnd, chal, u, proofs, status, verdict)
         n = _n(witness)
-        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), c.inp(proofs), c.inp(status), c.inp(verdict),
-              C.c_size_t(n))
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), c.outbuf(proofs, (n, 34)), c.outbuf(status, (n,)),
+              c.outbuf(verdict, (n,)), C.c_size_t(n))
+
+    # ---- outputs that cost less PCIe (include/plonk_b200.h: compact output, packed wire v2, seeded mode)
+    def prove_verify_compact_into(self, witness, rnd, chal, u, proofs_dense, status, verdict):
+        """Host path (numpy).  proofs_dense: caller-owned [n][34] capacity; returns the number of completed proofs, whose
+        PROOF structs are proofs_dense[:n_done] in item order."""
+        c = _Call("pb_plonk_prove_verify_compact", witness, rnd, chal, u)
+        assert not c.dev
+        n = _n(witness)
+        n_done = C.c_size_t(0)
+        c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), c.outbuf(proofs_dense, (n, 34)), C.byref(n_done),
+              c.outbuf(status, (n,)), c.outbuf(verdict, (n,)), C.c_size_t(n))
+        return int(n_done.value)
+
+    def prove_verify_compact(self, witness, rnd, chal, u):
+        n = _n(witness)
+        dense, status, verdict = np.empty((n, 34), np.uint8), np.empty(n, np.uint8), np.empty(n, np.uint8)
+        k = self.prove_verify_compact_into(witness, rnd, chal, u, dense, status, verdict)
+        return dense[:k], status, verdict
+
+    def prove_verify_packed_into(self, packed_in, packed_proofs, sv):
+        """Host path (numpy), packed wire v2: packed_in [n][16] -> packed_proofs[:n_done] ([n][22] capacity), sv[n]."""
+        c = _Call("pb_plonk_prove_verify_packed", packed_in)
+        assert not c.dev
+        n = _n(packed_in)
+        n_done = C.c_size_t(0)
+        c.run(self._h, c.inp(packed_in), c.outbuf(packed_proofs, (n, 22)), C.byref(n_done), c.outbuf(sv, (n,)), C.c_size_t(n))
+        return int(n_done.value)
+
+    def prove_verify_packed(self, packed_in):
+        n = _n(packed_in)
+        pp, sv = np.empty((n, 22), np.uint8), np.empty(n, np.uint8)
+        k = self.prove_verify_packed_into(packed_in, pp, sv)
+        return pp[:k], sv
+
+    def prove_verify_packed_dev(self, packed_in):
+        """Device path (torch CUDA tensors): -> (packed_proofs [n][22] capacity, n_done (device int32[1]), sv[n])."""
+        import torch
+        n = _n(packed_in)
+        dev = packed_in.device
+        lib().pb_packed_workspace_bytes.restype = C.c_size_t
+        ws = torch.empty(lib().pb_packed_workspace_bytes(C.c_size_t(n)), dtype=torch.uint8, device=dev)
+        pp = torch.empty((n, 22), dtype=torch.uint8, device=dev)
+        sv = torch.empty(n, dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _check(lib().pb_plonk_prove_verify_packed_dev(self._h, C.c_void_p(packed_in.data_ptr()), C.c_void_p(pp.data_ptr()),
+                                                          C.c_void_p(cnt.data_ptr()), C.c_void_p(sv.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                                          C.c_size_t(n), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return pp, cnt, sv
+
+    def prove_verify_seeded(self, seed, start, count, variant="U17"):
+        """Inputs generated on the device from (seed, start, count); only the 18 counters come back."""
+        counts = np.zeros(18, np.int64)
+        _check(lib().pb_plonk_prove_verify_seeded(self._h, C.c_uint64(seed), C.c_uint64(start), C.c_size_t(count),
+                                                  C.c_int(VARIANTS[variant]), counts.ctypes.data_as(C.c_void_p)))
+        return counts
+
+    def seeded_workspace(self, n, device):
+        import torch
+        lib().pb_seeded_workspace_bytes.restype = C.c_size_t
+        return torch.empty(lib().pb_seeded_workspace_bytes(C.c_size_t(n)), dtype=torch.uint8, device=device)
+
+    def prove_verify_seeded_dev(self, seed, start, n, variant, workspace, counts):
+        """Enqueue on torch's current stream: counts (torch int64[18], CUDA) += the tally of items [start, start + n)."""
+        import torch
+        with torch.cuda.device(counts.device):
+            _check(lib().pb_plonk_prove_verify_seeded_dev(self._h, C.c_uint64(seed), C.c_uint64(start), C.c_size_t(n),
+                                                          C.c_int(VARIANTS[variant]), C.c_void_p(workspace.data_ptr()),
+                                                          C.c_void_p(counts.data_ptr()),
+                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def synth_batch(self, seed, start, n, variant="U17", device=None):
+        """The synthetic stream generated on the device: -> (witness, rnd, chal, u, packed) as torch CUDA tensors."""
+        import torch
+        dev = torch.device("cuda", self.device) if device is None else device
+        mk = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)
+        wit, rnd, chal, u, packed = mk(n, 12), mk(n, 9), mk(n, 5), mk(n), mk(n, 16)
+        with torch.cuda.device(dev):
+            _check(lib().pb_synth_batch_dev(self._h, C.c_uint64(seed), C.c_uint64(start), C.c_size_t(n), C.c_int(VARIANTS[variant]),
+                                            *(C.c_void_p(t.data_ptr()) for t in (wit, rnd, chal, u, packed)),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return wit, rnd, chal, u, packed
+
+
+VARIANTS = {"U17": 0, "NZ": 1}
+
+
+def gather_completed(proofs, status):
+    """torch CUDA tensors proofs[n][34], status[n] -> (dense [n][34] capacity, n_done device int32[1]): the PROOF structs of
+    the completed items (status 0) in item order."""
+    import torch
+    n = _n(proofs)
+    dev = proofs.device
+    dense = torch.empty((n, 34), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    offs = torch.empty(n // 128 + 4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().pb_gather_completed_dev(C.c_void_p(proofs.data_ptr()), C.c_void_p(status.data_ptr()), C.c_void_p(dense.data_ptr()),
+                                             C.c_void_p(cnt.data_ptr()), C.c_void_p(offs.data_ptr()), C.c_size_t(n),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return dense, cnt
+
+
+# ---- packed wire v2: the C helpers (host-side format conversion; plonk.c_b200/wire.py is the numpy twin)
+def wire_pack_inputs(witness, rnd, chal, u):
+    n = _n(witness)
+    out = np.empty((n, 16), np.uint8)
+    a = [np.ascontiguousarray(x, np.uint8) for x in (witness, rnd, chal, u)]
+    _check(lib().pb_wire_pack_inputs(*(x.ctypes.data_as(C.c_void_p) for x in a), out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+    return out
+
+
+def wire_unpack_inputs(packed):
+    packed = np.ascontiguousarray(packed, np.uint8)
+    n = _n(packed)
+    wit, rnd, chal, u, valid = np.empty((n, 12), np.uint8), np.empty((n, 9), np.uint8), np.empty((n, 5), np.uint8), np.empty(n, np.uint8), np.empty(n, np.uint8)
+    _check(lib().pb_wire_unpack_inputs(packed.ctypes.data_as(C.c_void_p), *(x.ctypes.data_as(C.c_void_p) for x in (wit, rnd, chal, u, valid)),
+                                       C.c_size_t(n)))
+    return wit, rnd, chal, u, valid.astype(bool)
+
+
+def wire_pack_proofs(proofs):
+    proofs = np.ascontiguousarray(proofs, np.uint8).reshape(-1, 34)
+    out = np.empty((proofs.shape[0], 22), np.uint8)
+    _check(lib().pb_wire_pack_proofs(proofs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(proofs.shape[0])))
+    return out
+
+
+def wire_unpack_proofs(packed):
+    packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, 22)
+    out = np.empty((packed.shape[0], 34), np.uint8)
+    _check(lib().pb_wire_unpack_proofs(packed.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(packed.shape[0])))
+    return out
+
+
+def wire_scatter_proofs(proofs_dense, status):
+    status = np.ascontiguousarray(status, np.uint8)
+    dense = np.ascontiguousarray(proofs_dense, np.uint8)
+    out = np.empty((status.shape[0], 34), np.uint8)
+    _check(lib().pb_wire_scatter_proofs(dense.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                        C.c_size_t(status.shape[0])))
+    return out
+
+
+def wire_split_sv(sv):
+    sv = np.ascontiguousarray(sv, np.uint8)
+    st, vd = np.empty_like(sv), np.empty_like(sv)
+    _check(lib().pb_wire_split_sv(sv.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), vd.ctypes.data_as(C.c_void_p), C.c_size_t(sv.shape[0])))
+    return st, vd
 
 
 def tally(proofs, status, verdict, counts):

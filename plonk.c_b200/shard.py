@@ -42,3 +42,40 @@ def reduce_counters(counts, elapsed_ms, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         elapsed_ms = float(t.item())
     return counts.cpu().numpy(), float(elapsed_ms)
+
+
+def _world():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def gather_scalar(x, device):
+    """Every rank's value of a scalar, as a list indexed by rank (one all_gather of a float64)."""
+    import torch
+    dist = _world()
+    if dist is None:
+        return [float(x)]
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
+def reduce_max(x, device):
+    import torch
+    dist = _world()
+    if dist is None:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(x, device):
+    import torch
+    dist = _world()
+    if dist is None:
+        return int(x)
+    t = torch.tensor([int(x)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())

@@ -7,6 +7,7 @@
 #include <cstring>
 #include "../../plonk.c_b200/csrc/prover.cuh"
 #include "../../plonk.c_b200/csrc/verifier.cuh"
+#include "../../plonk.c_b200/csrc/wire.cuh"
 
 using namespace pb;
 
@@ -302,6 +303,44 @@ uint64_t hc_check_barrett(uint32_t* first_bad17, uint32_t* first_bad101) {
   for (uint64_t x = 1ull << 28; x < (1ull << 32); x++) if (f17((uint32_t)x) != (uint32_t)x % 17u) { *first_bad17 = (uint32_t)x; break; }
   for (uint64_t x = 1ull << 26; x < (1ull << 32); x++) if (f101((uint32_t)x) != (uint32_t)x % 101u) { *first_bad101 = (uint32_t)x; break; }
   return bad;
+}
+// packed wire v2 and the synthetic stream (wire.cuh): the device functions the kernels call, run on the host
+void hc_synth(uint64_t seed, uint64_t start, int variant, const uint8_t* wtab, uint8_t* wit, uint8_t* rnd, uint8_t* chal, uint8_t* u,
+              uint8_t* packed, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t v[PACKED_VALUES], w[4];
+    synth_item(seed, start + i, variant, wtab, v);
+    for (int k = 0; k < 12; k++) wit[12 * i + k] = (uint8_t)v[k];
+    for (int k = 0; k < 9; k++) rnd[9 * i + k] = (uint8_t)v[12 + k];
+    for (int k = 0; k < 5; k++) chal[5 * i + k] = (uint8_t)v[21 + k];
+    u[i] = (uint8_t)v[26];
+    pack_input16(v, w);
+    memcpy(packed + 16 * i, w, 16);
+  }
+}
+// every 32-bit word through unpack7: returns the number of words whose digits / validity flag differ from plain division
+uint64_t hc_check_unpack7(uint32_t lo, uint32_t hi, uint32_t step) {
+  uint64_t bad = 0;
+  for (uint64_t x = lo; x < hi; x += step) {
+    uint32_t d[7];
+    const bool ok = unpack7((uint32_t)x, d);
+    uint32_t q = (uint32_t)x;
+    bool same = true;
+    for (int k = 0; k < 6; k++) { same = same && d[k] == q % 17u; q /= 17u; }
+    same = same && d[6] == q && ok == (x < P17_7);
+    if (ok) same = same && pack7(d) == (uint32_t)x;
+    bad += !same;
+  }
+  return bad;
+}
+// prove_kernel<.., PACKED> front end + verifier word 3: packed record -> the values the kernels use, 0xFF where not an encoding
+void hc_unpack_input16(const uint8_t* packed, uint8_t* v27, uint8_t* ok, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[4], v[PACKED_VALUES];
+    memcpy(w, packed + 16 * i, 16);
+    ok[i] = unpack_input16(w[0], w[1], w[2], w[3], v) ? 1 : 0;
+    for (int k = 0; k < PACKED_VALUES; k++) v27[PACKED_VALUES * i + k] = (uint8_t)v[k];
+  }
 }
 int hc_bounds_checked() {
 #ifdef PB_CHECK_BOUNDS

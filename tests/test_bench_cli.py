@@ -19,7 +19,7 @@ def _run(*args, env=None):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--items", "65536")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -29,6 +29,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+    # the CPU arm runs the SAME configuration as the CUDA arm: same items per step, no arm-specific key in `config`
+    assert d["config"]["items_per_gpu_per_step"] == 65536 and "items_per_step_reference_arm" not in d["config"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

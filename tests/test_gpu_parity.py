@@ -319,3 +319,146 @@ def test_field_new(host, oracle):
 
 def test_whole_curve_srs(dev, oracle, W):
     ps.check_whole_curve_srs(dev, oracle, W)
+
+
+# ---------------------------------------------------------------- compact output, packed wire v2, seeded mode
+def _oracle_pv(oracle, W, circuit, g1s, g2, wit, rnd, chal, u):
+    rp, rs = oracle.plonk_prove_batch(circuit, g1s, g2, wit, rnd, chal)
+    rv, _ = oracle.plonk_verify_batch(circuit, g1s, g2, rp, chal, u)
+    return rp, rs, np.where(rs == 0, rv, 0xFF).astype(np.uint8)
+
+
+@pytest.mark.parametrize("n", [0, 1, 127, 129, 4097, 300007])
+def test_compact_and_packed_outputs(host, oracle, W, n):
+    """pb_plonk_prove_verify_compact / _packed (host-pointer pipelines) against the oracle: the dense list is exactly the
+    completed proofs in item order, the packed records are the wire.py packing of them, sv the packed status/verdict."""
+    from plonk_c_b200 import wire
+    for mode in ("generator9", "identity6", "garbage"):
+        import util
+        g1s, g2 = util.garbage_srs() if mode == "garbage" else util.SRS_MODES[mode](W)
+        if mode != "generator9" and n > 5000:
+            continue
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+        wit, rnd, chal, u = W.make_batch(55, 7, n, "U17")
+        if n > 100:
+            wit[5, 3] = 17          # a byte outside F17: status 254 in both formats
+        dense, status, verdict = pk.prove_verify_compact(wit, rnd, chal, u)
+        packed_in = wire.pack_inputs(wit, rnd, chal, u)
+        pp, sv = pk.prove_verify_packed(packed_in)
+        if n == 0:
+            assert dense.shape == (0, 34) and pp.shape == (0, 22)
+            continue
+        if n > 100:
+            wit_ok = wit.copy(); wit_ok[5] = 0
+            rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit_ok, rnd, chal, u)
+            rp[5] = 0; rs[5] = 254; rv[5] = 0xFF
+        else:
+            rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u)
+        ps.eq(f"compact {mode}", (dense, status, verdict), (rp[rs == 0], rs, rv))
+        ps.eq(f"compact {mode}: scatter", host.wire_scatter_proofs(dense, status), rp)
+        ps.eq(f"packed {mode}", (pp, sv), (wire.pack_proofs(rp[rs == 0]), wire.make_sv(rs, rv)))
+        ps.eq(f"packed {mode}: unpack", wire.scatter_proofs(wire.unpack_proofs(pp), wire.split_sv(sv)[0]), rp)
+
+
+def test_packed_device_path_and_gather(host, oracle, W):
+    """pb_plonk_prove_verify_packed_dev and pb_gather_completed_dev on device buffers; non-encodings are flagged."""
+    import torch
+    from plonk_c_b200 import wire
+    n = 70001
+    g1s, g2 = W.generator_srs(9)
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+    wit, rnd, chal, u = W.make_batch(56, 0, n, "U17")
+    packed = wire.pack_inputs(wit, rnd, chal, u)
+    packed[11] = 0xFF                                   # word >= 17^7
+    packed[12].view("<u4")[3] += 16 * 17 ** 6          # spare digit != 0
+    pp, cnt, sv = pk.prove_verify_packed_dev(torch.from_numpy(packed).cuda())
+    rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u)
+    for i in (11, 12):
+        rp[i] = 0; rs[i] = 254; rv[i] = 0xFF
+    k = int(cnt.item())
+    assert k == int((rs == 0).sum())
+    ps.eq("packed dev", (pp[:k].cpu().numpy(), sv.cpu().numpy()), (wire.pack_proofs(rp[rs == 0]), wire.make_sv(rs, rv)))
+    d = [torch.from_numpy(x).cuda() for x in (wit, rnd, chal)]
+    proofs, status = pk.prove(*d)
+    dense, cnt2 = host.gather_completed(proofs, status)
+    k2 = int(cnt2.item())
+    p_h, s_h = proofs.cpu().numpy(), status.cpu().numpy()
+    ps.eq("gather", dense[:k2].cpu().numpy(), p_h[s_h == 0])
+    # all-failed and all-completed extremes of the dense list
+    st0 = torch.zeros_like(status)
+    dense, cnt3 = host.gather_completed(proofs, st0)
+    assert int(cnt3.item()) == n and torch.equal(dense, proofs)
+    st1 = torch.full_like(status, 8)
+    _, cnt4 = host.gather_completed(proofs, st1)
+    assert int(cnt4.item()) == 0
+
+
+def test_packed_exact_path_forced(host, oracle, W):
+    import os
+    from plonk_c_b200 import wire
+    os.environ["PB_FORCE_EXACT"] = "1"
+    try:
+        n = 20000
+        g1s, g2 = W.generator_srs(9)
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+        wit, rnd, chal, u = W.make_batch(57, 0, n, "NZ")
+        pp, sv = pk.prove_verify_packed(wire.pack_inputs(wit, rnd, chal, u))
+        rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u)
+        ps.eq("packed, exact kernels", (pp, sv), (wire.pack_proofs(rp[rs == 0]), wire.make_sv(rs, rv)))
+    finally:
+        del os.environ["PB_FORCE_EXACT"]
+
+
+def test_seeded_mode(host, oracle, W):
+    """Seeded mode: the device-generated stream equals workload.make_batch, and the counters equal the tally of the
+    oracle's results on those items (both variants, a start offset, a count that is not a multiple of anything)."""
+    from plonk_c_b200 import shard, wire
+    g1s, g2 = W.generator_srs(9)
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+    for seed, start, n, variant in ((2025, 0, 50000, "U17"), (99, 2**33 + 11, 30011, "NZ")):
+        got = [t.cpu().numpy() for t in pk.synth_batch(seed, start, n, variant)]
+        wit, rnd, chal, u = W.make_batch(seed, start, n, variant)
+        ps.eq(f"device generator {variant}", tuple(got), (wit, rnd, chal, u, wire.pack_inputs(wit, rnd, chal, u)))
+        counts = pk.prove_verify_seeded(seed, start, n, variant)
+        rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u)
+        ps.eq(f"seeded counters {variant}", counts, shard.tally_host(rp, rs, rv))
+    # a count spanning several internal chunks: compared with the struct path on the GPU itself
+    import torch
+    n = (1 << 21) + 12345
+    counts = pk.prove_verify_seeded(5, 1000, n, "U17")
+    wit, rnd, chal, u = W.make_batch(5, 1000, n, "U17")
+    proofs, status, verdict = pk.prove_verify(*[torch.from_numpy(x).cuda() for x in (wit, rnd, chal, u)])
+    ps.eq("seeded counters, 2^21 + 12345 items", counts, shard.tally_host(proofs.cpu().numpy(), status.cpu().numpy(), verdict.cpu().numpy()))
+
+
+def test_output_buffers_are_not_coerced(host, W):
+    """a non-contiguous or wrongly typed output buffer must raise, not be silently copied."""
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    n = 256
+    wit, rnd, chal, u = W.make_batch(3, 0, n)
+    good = [np.empty((n, 34), np.uint8), np.empty(n, np.uint8), np.empty(n, np.uint8)]
+    pk.prove_verify_into(wit, rnd, chal, u, *good)
+    with pytest.raises(ValueError):
+        pk.prove_verify_into(wit, rnd, chal, u, np.empty((n, 68), np.uint8)[:, ::2], good[1], good[2])
+    with pytest.raises(ValueError):
+        pk.prove_verify_into(wit, rnd, chal, u, good[0], np.empty(n, np.int32), good[2])
+    with pytest.raises(ValueError):
+        pk.prove_verify_into(wit, rnd, chal, u, good[0], good[1], np.empty(n + 1, np.uint8))
+
+
+def test_compact_and_packed_many_chunks(host, W):
+    """A batch long enough to wrap the pipeline's ring of buffer sets (11 chunks over 6 slots): compact and packed outputs
+    against the struct-array pipeline (itself checked against the oracle above)."""
+    from plonk_c_b200 import wire
+    n = (1 << 21) + 77
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    wit, rnd, chal, u = W.make_batch(58, 0, n, "U17")
+    proofs, status, verdict = pk.prove_verify(wit, rnd, chal, u)
+    dense, s2, v2 = pk.prove_verify_compact(wit, rnd, chal, u)
+    ps.eq("compact, many chunks", (dense, s2, v2), (proofs[status == 0], status, verdict))
+    pp, sv = pk.prove_verify_packed(wire.pack_inputs(wit, rnd, chal, u))
+    ps.eq("packed, many chunks", (pp, sv), (wire.pack_proofs(proofs[status == 0]), wire.make_sv(status, verdict)))
+    # and twice in a row on the same context (slot reuse across calls), with a smaller batch in between
+    pk.prove_verify_compact(wit[:1000], rnd[:1000], chal[:1000], u[:1000])
+    dense3, s3, v3 = pk.prove_verify_compact(wit, rnd, chal, u)
+    ps.eq("compact, second call", (dense3, s3, v3), (dense, s2, v2))
