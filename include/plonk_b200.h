@@ -301,6 +301,19 @@ int pb_plonk_prove_verify_fs(const pb_ctx *ctx, const uint8_t *witness, const ui
 /* the six challenges of each PROOF record as a verifier derives them: chal6[n][6] */
 int pb_fs_challenges_dev(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *chal6, size_t n, void *stream);
 int pb_fs_challenges(const pb_ctx *ctx, const uint8_t *proofs, uint8_t *chal6, size_t n);
+/* ---- circuit front-end (host side).  Lowers what the reference's expression compiler produces --
+ * a GATE_LIST: gates[n][5] = GATE{q_l q_r q_o q_m q_c} and the variable index on each gate's a / b / c wire
+ * (eval_expr, gate_list_append: constraints.h:227-309) -- to the 44-byte circuit of pb_ctx_create: selectors by gate,
+ * copy constraints by wiring every position to the next one (A1..A4 B1..B4 C1..C4, cyclically) that carries the same
+ * variable.  equal_pairs[n_equal][2] (optional) lists variables asserted equal, e.g. the outputs of two expressions.
+ * num_gates <= 4: the domain is fixed by omega = 4 of order 4 (plonk.h:12); unused rows become all-zero gates.  For
+ * the gate list mul(x,x) mul(y,y) mul(z,z) sum(xx,yy)=zz it yields exactly plonk-test.c's hand-written circuit. */
+int pb_circuit_from_gates(const uint8_t *gates, const size_t *a_idx, const size_t *b_idx, const size_t *c_idx,
+                          size_t num_gates, const size_t *equal_pairs, size_t n_equal, uint8_t circuit[PB_CIRCUIT_BYTES]);
+/* witness[n][12] = a[4] b[4] c[4] from per-item variable values var_values[n][n_vars] and the same wire indices */
+int pb_witness_from_values(const size_t *a_idx, const size_t *b_idx, const size_t *c_idx, size_t num_gates,
+                           const uint8_t *var_values, size_t n_vars, uint8_t *witness, size_t n);
+
 /* on-device tally: counts[0..15] += number of items per status byte (0..14, 15 = anything else),
  * counts[16] += verdict==1, counts[17] += a 64-bit sum of all proof bytes (checksum). counts: int64[18] device ptr */
 int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *verdict, size_t n, int64_t *counts, void *stream);

@@ -124,7 +124,8 @@ struct pb_ctx {
   size_t small_cap = 0;
   size_t slot_cap = 0;                // items each slot's buffers hold
   PipeSlot slots[PIPE_SLOTS];
-  uint32_t* h_count = nullptr;        // pinned, [PIPE_SLOTS]: completed proofs of the chunk in each slot
+  uint32_t* h_count = nullptr;        // pinned + mapped, [PIPE_SLOTS]: completed proofs of the chunk in each slot (written by the kernel)
+  uint32_t* h_count_dev = nullptr;    // the device-side address of h_count
   uint8_t* d_wtab = nullptr;          // seeded mode: the 289-row witness table of the synthetic stream
   uint8_t* d_seed_ws = nullptr;       // seeded mode: workspace (packed inputs, proofs, status, verdict, counters)
   size_t seed_ws_items = 0;
@@ -170,7 +171,10 @@ int pipe_init(pb_ctx* c, size_t cap) {
       if (!s.ev_k) CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
       if (!s.ev_out) CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     }
-    if (!c->h_count) CU(cudaHostAlloc(reinterpret_cast<void**>(&c->h_count), PIPE_SLOTS * sizeof(uint32_t), cudaHostAllocDefault));
+    if (!c->h_count) {
+      CU(cudaHostAlloc(reinterpret_cast<void**>(&c->h_count), PIPE_SLOTS * sizeof(uint32_t), cudaHostAllocMapped));
+      CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_count_dev), c->h_count, 0));
+    }
     c->pipe_ready = true;
   }
   cap = (cap + 4095) & ~(size_t)4095;
@@ -899,28 +903,31 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
   for (int s = 0; s < 5; s++) memcpy(c->circuit_dump + 24 + 4 * s, polys[s], 4);
   memcpy(c->circuit_dump + 44, polys[8], 4);
 
-  // SRS fixed-base table T[i][c] = g1_mul(g1s[i], c), and the prover's nine-row copy with the field tables
+  // SRS fixed-base table T[i][c] = g1_mul(g1s[i], c), and the prover's nine-row copy with the field tables.
+  // Every temporary is an RAII `Dev` (freed on every return path); every copy and launch is checked.
+#define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(cuda_fail(e__, #call)); } while (0)
+#define DEVB(name, bytes) Dev name(bytes); if (name.err != cudaSuccess) return bail(cuda_fail(name.err, "cudaMalloc"))
+#define LAUNCHB(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return bail(cuda_fail(e__, what)); } while (0)
   const uint32_t rows_full = srs_len;
-  uint8_t* d_g1s = nullptr;
-  if (cudaMalloc(&d_g1s, 3 * srs_len + 16) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-  cudaMemcpy(d_g1s, srs_g1s, 3 * srs_len, cudaMemcpyHostToDevice);
-  if (cudaMalloc(&c->d_srs_table, rows_full * 17 * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_g1s); return bail(cuda_fail(cudaGetLastError(), "cudaMalloc")); }
-  srs_table_kernel<<<1, 256>>>(d_g1s, srs_len, rows_full, c->d_srs_table);
   ProverTables pt;
   memset(&pt, 0, sizeof pt);
-  uint32_t* d_prow = nullptr;
-  if (cudaMalloc(&d_prow, PROVER_SRS_ROWS * 17 * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_g1s); return bail(cuda_fail(cudaGetLastError(), "cudaMalloc")); }
-  srs_table_kernel<<<1, 256>>>(d_g1s, srs_len, PROVER_SRS_ROWS, d_prow);
-  cudaError_t e = cudaMemcpy(pt.T, d_prow, sizeof pt.T, cudaMemcpyDeviceToHost);
-  cudaFree(d_prow);
-  cudaFree(d_g1s);
-  if (e != cudaSuccess) return bail(cuda_fail(e, "srs_table_kernel"));
+  {
+    DEVB(d_g1s, 3 * srs_len + 16);
+    DEVB(d_prow, PROVER_SRS_ROWS * 17 * sizeof(uint32_t));
+    CUB(cudaMemcpy(d_g1s.p, srs_g1s, 3 * srs_len, cudaMemcpyHostToDevice));
+    CUB(cudaMalloc(&c->d_srs_table, rows_full * 17 * sizeof(uint32_t)));
+    srs_table_kernel<<<1, 256>>>(d_g1s.as<uint8_t>(), srs_len, rows_full, c->d_srs_table);
+    LAUNCHB("srs_table_kernel");
+    srs_table_kernel<<<1, 256>>>(d_g1s.as<uint8_t>(), srs_len, PROVER_SRS_ROWS, d_prow.as<uint32_t>());
+    LAUNCHB("srs_table_kernel");
+    CUB(cudaMemcpy(pt.T, d_prow.p, sizeof pt.T, cudaMemcpyDeviceToHost));
+  }
   for (uint32_t i = 0; i < 256; i++) pt.ft.inv101[i] = (uint8_t)pow101(i % 101u, 99);
   for (uint32_t i = 0; i < 17; i++) pt.ft.inv17[i] = (uint8_t)pow17(i, 15);
   for (uint32_t zz = 0; zz < 17; zz++) for (uint32_t k = 0; k < 20; k++) pt.pow17[zz][k] = (uint8_t)pow17(zz, k);
   for (uint32_t i = 0; i < MOD17_RANGE; i++) pt.mod17[i] = (uint8_t)(i % 17u);
-  if (cudaMalloc(&c->d_tables, sizeof(ProverTables)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-  cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice);
+  CUB(cudaMalloc(&c->d_tables, sizeof(ProverTables)));
+  CUB(cudaMemcpy(c->d_tables, &pt, sizeof pt, cudaMemcpyHostToDevice));
   {
     // fast-path eligibility: canonical encodings (checked here) and curve membership (checked on the device)
     std::vector<uint8_t> on(srs_len);
@@ -933,56 +940,53 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
     c->srs_canonical = canon;
     if (const char* e2 = getenv("PB_FORCE_EXACT")) c->force_exact = e2[0] == '1';
     if (canon) {
-      ProverPairTables ppt;
+      std::vector<ProverPairTables> ppt_store(1);     // 7 KB: off the stack
+      ProverPairTables& ppt = ppt_store[0];
       memset(&ppt, 0, sizeof ppt);
       ppt.ft = pt.ft;
       memcpy(ppt.pow17, pt.pow17, sizeof ppt.pow17);
       memcpy(ppt.mod17, pt.mod17, sizeof ppt.mod17);
-      uint32_t *d_single = nullptr, *d_pairs = nullptr;
-      if (cudaMalloc(&d_single, sizeof pt.T) != cudaSuccess || cudaMalloc(&d_pairs, sizeof ppt.T2) != cudaSuccess)
-        return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-      cudaMemcpy(d_single, pt.T, sizeof pt.T, cudaMemcpyHostToDevice);
-      pair_table_kernel<<<8, 256>>>(d_single, PROVER_SRS_ROWS, PROVER_PAIR_ROWS, d_pairs);
-      cudaError_t e3 = cudaMemcpy(ppt.T2, d_pairs, sizeof ppt.T2, cudaMemcpyDeviceToHost);
-      cudaFree(d_single); cudaFree(d_pairs);
-      if (e3 != cudaSuccess) return bail(cuda_fail(e3, "pair_table_kernel"));
-      if (cudaMalloc(&c->d_pair_tables, sizeof ppt) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-      cudaMemcpy(c->d_pair_tables, &ppt, sizeof ppt, cudaMemcpyHostToDevice);
+      DEVB(d_single, sizeof pt.T);
+      {
+        DEVB(d_pairs, sizeof ppt.T2);
+        CUB(cudaMemcpy(d_single.p, pt.T, sizeof pt.T, cudaMemcpyHostToDevice));
+        pair_table_kernel<<<8, 256>>>(d_single.as<uint32_t>(), PROVER_SRS_ROWS, PROVER_PAIR_ROWS, d_pairs.as<uint32_t>());
+        LAUNCHB("pair_table_kernel");
+        CUB(cudaMemcpy(ppt.T2, d_pairs.p, sizeof ppt.T2, cudaMemcpyDeviceToHost));
+      }
+      CUB(cudaMalloc(&c->d_pair_tables, sizeof ppt));
+      CUB(cudaMemcpy(c->d_pair_tables, &ppt, sizeof ppt, cudaMemcpyHostToDevice));
       const char* ew = getenv("PB_WIDE_TABLES");
       if (!(ew && ew[0] == '0')) {
         // one-look-up commitments: T3 for SRS rows 0-2 / 3-5 / 6-8, then T6 = T3[0] (+) T3[1]  (prover.cuh)
         const size_t n16 = 3u * (size_t)WIDE_T3_ENTRIES + WIDE_T6_ENTRIES;
-        uint32_t* d_single2 = nullptr;
         if (cudaMalloc(&c->d_wide_store, n16 * sizeof(uint16_t)) != cudaSuccess) {
           // no room for the 48 MB table: not an error, the context stays on the pair tables (same results)
           cudaGetLastError();
           c->d_wide_store = nullptr;
         } else {
-        if (cudaMalloc(&d_single2, sizeof pt.T) != cudaSuccess || cudaMalloc(&c->d_wide_tables, sizeof(ProverWideTables)) != cudaSuccess)
-          return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-        cudaMemcpy(d_single2, pt.T, sizeof pt.T, cudaMemcpyHostToDevice);
-        uint16_t* t3 = c->d_wide_store;
-        uint16_t* t6 = c->d_wide_store + 3u * (size_t)WIDE_T3_ENTRIES;
-        wide_t3_kernel<<<58, 256>>>(d_single2, PROVER_SRS_ROWS, t3);
-        wide_t6_kernel<<<148 * 8, 256>>>(t3, t6);
-        cudaError_t e5 = cudaDeviceSynchronize();
-        cudaFree(d_single2);
-        if (e5 != cudaSuccess) return bail(cuda_fail(e5, "wide_t6_kernel"));
-        ProverWideTables wt;
-        memset(&wt, 0, sizeof wt);
-        wt.ft = pt.ft;
-        memcpy(wt.pow17, pt.pow17, sizeof wt.pow17);
-        memcpy(wt.mod17, pt.mod17, sizeof wt.mod17);
-        wt.T6 = t6;
-        wt.T3 = t3 + 2u * (size_t)WIDE_T3_ENTRIES;
-        cudaMemcpy(c->d_wide_tables, &wt, sizeof wt, cudaMemcpyHostToDevice);
+          CUB(cudaMalloc(&c->d_wide_tables, sizeof(ProverWideTables)));
+          uint16_t* t3 = c->d_wide_store;
+          uint16_t* t6 = c->d_wide_store + 3u * (size_t)WIDE_T3_ENTRIES;
+          wide_t3_kernel<<<58, 256>>>(d_single.as<uint32_t>(), PROVER_SRS_ROWS, t3);
+          LAUNCHB("wide_t3_kernel");
+          wide_t6_kernel<<<148 * 8, 256>>>(t3, t6);
+          LAUNCHB("wide_t6_kernel");
+          CUB(cudaDeviceSynchronize());
+          ProverWideTables wt;
+          memset(&wt, 0, sizeof wt);
+          wt.ft = pt.ft;
+          memcpy(wt.pow17, pt.pow17, sizeof wt.pow17);
+          memcpy(wt.mod17, pt.mod17, sizeof wt.mod17);
+          wt.T6 = t6;
+          wt.T3 = t3 + 2u * (size_t)WIDE_T3_ENTRIES;
+          CUB(cudaMemcpy(c->d_wide_tables, &wt, sizeof wt, cudaMemcpyHostToDevice));
         }
       }
     }
   }
   std::vector<uint32_t> tab(rows_full * 17);
-  e = cudaMemcpy(tab.data(), c->d_srs_table, tab.size() * 4, cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return bail(cuda_fail(e, "srs table read-back"));
+  CUB(cudaMemcpy(tab.data(), c->d_srs_table, tab.size() * 4, cudaMemcpyDeviceToHost));
   c->table_bytes.resize(tab.size() * 3);
   for (size_t k = 0; k < tab.size(); k++) {
     c->table_bytes[3 * k] = tab[k] & 0xFF; c->table_bytes[3 * k + 1] = (tab[k] >> 8) & 0xFF; c->table_bytes[3 * k + 2] = (tab[k] >> 16) & 1;
@@ -993,14 +997,15 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
     const int order[8] = {3, 0, 1, 2, 4, 5, 6, 7};
     uint8_t kp[8][4];
     for (int j = 0; j < 8; j++) memcpy(kp[j], polys[order[j]], 4);
-    uint8_t* d_kp = nullptr; uint32_t* d_out = nullptr;
-    if (cudaMalloc(&d_kp, 32) != cudaSuccess || cudaMalloc(&d_out, 32) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-    cudaMemcpy(d_kp, kp, 32, cudaMemcpyHostToDevice);
-    verifier_key_kernel<<<1, 32>>>(c->d_srs_table, srs_len, d_kp, d_out);
     uint32_t packed[8];
-    e = cudaMemcpy(packed, d_out, 32, cudaMemcpyDeviceToHost);
-    cudaFree(d_kp); cudaFree(d_out);
-    if (e != cudaSuccess) return bail(cuda_fail(e, "verifier_key_kernel"));
+    {
+      DEVB(d_kp, 32);
+      DEVB(d_out, 32);
+      CUB(cudaMemcpy(d_kp.p, kp, 32, cudaMemcpyHostToDevice));
+      verifier_key_kernel<<<1, 32>>>(c->d_srs_table, srs_len, d_kp.as<uint8_t>(), d_out.as<uint32_t>());
+      LAUNCHB("verifier_key_kernel");
+      CUB(cudaMemcpy(packed, d_out.p, 32, cudaMemcpyDeviceToHost));
+    }
     G1* dst[8] = {&c->vk.qm, &c->vk.ql, &c->vk.qr, &c->vk.qo, &c->vk.qc, &c->vk.s1, &c->vk.s2, &c->vk.s3};
     for (int j = 0; j < 8; j++) {
       if (packed[j] == 0xFFFFFFFFu) { c->vk_valid = false; packed[j] = pack_g1(0, 0, 1); }
@@ -1022,18 +1027,20 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
     }
     c->key_canonical = canon;
     if (canon) {
-      uint8_t* d_key = nullptr; uint32_t* d_kt = nullptr;
-      if (cudaMalloc(&d_key, 32) != cudaSuccess || cudaMalloc(&d_kt, 9 * 17 * 4) != cudaSuccess ||
-          cudaMalloc(&c->d_verify_tables, sizeof(VerifyTables)) != cudaSuccess)
-        return bail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
-      cudaMemcpy(d_key, c->vkey_bytes, 27, cudaMemcpyHostToDevice);
-      srs_table_kernel<<<1, 256>>>(d_key, 9, 9, d_kt);                  // rows c * K_j by the reference's g1_mul
-      verify_tables_kernel<<<1, 256>>>(d_kt, c->d_verify_tables);
-      cudaError_t e4 = cudaDeviceSynchronize();
-      cudaFree(d_key); cudaFree(d_kt);
-      if (e4 != cudaSuccess) return bail(cuda_fail(e4, "verify_tables_kernel"));
+      DEVB(d_key, 32);
+      DEVB(d_kt, 9 * 17 * 4);
+      CUB(cudaMalloc(&c->d_verify_tables, sizeof(VerifyTables)));
+      CUB(cudaMemcpy(d_key.p, c->vkey_bytes, 27, cudaMemcpyHostToDevice));
+      srs_table_kernel<<<1, 256>>>(d_key.as<uint8_t>(), 9, 9, d_kt.as<uint32_t>());                  // rows c * K_j by the reference's g1_mul
+      LAUNCHB("srs_table_kernel");
+      verify_tables_kernel<<<1, 256>>>(d_kt.as<uint32_t>(), c->d_verify_tables);
+      LAUNCHB("verify_tables_kernel");
+      CUB(cudaDeviceSynchronize());
     }
   }
+#undef CUB
+#undef DEVB
+#undef LAUNCHB
   *out = c;
   return PB_OK;
 }
@@ -1224,8 +1231,8 @@ int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal
 
 // dense list of the completed proofs of a chunk (stream-ordered): offs[0 .. groups) and the count in offs[cap / 128 + 3]
 static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t m, uint32_t* offs, uint32_t* count,
-                         uint8_t* dense, uint8_t* sv, bool pack, cudaStream_t st) {
-  done_offsets_kernel<<<1, 1024, 0, st>>>(status, m, offs, count);
+                         uint8_t* dense, uint8_t* sv, bool pack, cudaStream_t st, uint32_t* count_host = nullptr) {
+  done_offsets_kernel<<<1, 1024, 0, st>>>(status, m, offs, count, count_host);
   LAUNCH_CHECK("done_offsets_kernel");
   if (pack) gather_done_kernel<true><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
   else gather_done_kernel<false><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
@@ -1339,8 +1346,9 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     if (rc) return rc;
     if (dense) {
       uint32_t* cnt = s.offs + ctx->slot_cap / 128 + 3;
-      if ((rc = launch_gather(s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.offs, cnt, s.dense, ctx->d_sv + done, packed, ctx->s_k))) return rc;
-      CU(cudaMemcpyAsync(ctx->h_count + c % PIPE_SLOTS, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_k));
+      // the count also lands in mapped pinned memory (a store by the kernel, not a copy queued behind the D2H engine's proofs)
+      if ((rc = launch_gather(s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.offs, cnt, s.dense, ctx->d_sv + done, packed, ctx->s_k,
+                              ctx->h_count_dev + c % PIPE_SLOTS))) return rc;
     }
     CU(cudaEventRecord(s.ev_k, ctx->s_k));
     if (trace) CU(cudaEventRecord(tev[3 * c + 1], ctx->s_k));
@@ -1652,6 +1660,62 @@ int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* cha
   CU(cudaDeviceSynchronize());
   D2H(verdict, dv, n);
   if (gt) D2H(gt, dg, n * 4);
+  return PB_OK;
+}
+
+// ---- circuit front-end: what eval_expr / gate_list_append produce (constraints.h:227-309) -> the
+// 44-byte circuit a context takes.  Host-side authoring, no arithmetic of the path.  The reference never lowers a GATE_LIST
+// itself: plonk-test.c:139-213 fills CONSTRAINTS by hand; this is that hand work, mechanised.
+int pb_circuit_from_gates(const uint8_t* gates, const size_t* a_idx, const size_t* b_idx, const size_t* c_idx, size_t num_gates,
+                          const size_t* equal_pairs, size_t n_equal, uint8_t circuit[PB_CIRCUIT_BYTES]) {
+  ARG(circuit && (num_gates == 0 || (gates && a_idx && b_idx && c_idx)) && (n_equal == 0 || equal_pairs));
+  if (num_gates > 4)
+    return fail(PB_ERR_ARG, "plonk_b200: a circuit has at most 4 gates: the domain H is generated by omega = 4, of order 4 in F17 "
+                            "(plonk.h:12), and interpolate_at_h exits unless num_constraints == h_len (plonk.h:164-167)");
+  for (size_t i = 0; i < 5 * num_gates; i++) ARG(gates[i] < 17);
+  memset(circuit, 0, PB_CIRCUIT_BYTES);
+  for (size_t i = 0; i < num_gates; i++)
+    for (int s = 0; s < 5; s++) circuit[4 * s + i] = gates[5 * i + s];        // GATE{q_l q_r q_o q_m q_c} -> q_l[4] q_r[4] ...
+  // the variable on each of the twelve wire positions, type-major: A1..A4 B1..B4 C1..C4; an unused row gets a variable of its own
+  size_t var[12], next_free = 0;
+  for (size_t i = 0; i < num_gates; i++) {
+    var[i] = a_idx[i]; var[4 + i] = b_idx[i]; var[8 + i] = c_idx[i];
+    for (size_t v : {a_idx[i], b_idx[i], c_idx[i]}) if (v + 1 > next_free) next_free = v + 1;
+  }
+  for (size_t k = 0; k < n_equal; k++) for (int j = 0; j < 2; j++) if (equal_pairs[2 * k + j] + 1 > next_free) next_free = equal_pairs[2 * k + j] + 1;
+  for (size_t i = num_gates; i < 4; i++) { var[i] = next_free++; var[4 + i] = next_free++; var[8 + i] = next_free++; }
+  // variables asserted equal (an expression's output that must equal another's) share one copy cycle: union-find over the pairs
+  std::map<size_t, size_t> parent;
+  auto find = [&](size_t v) { while (parent.count(v) && parent[v] != v) v = parent[v]; return v; };
+  for (size_t k = 0; k < n_equal; k++) {
+    const size_t a = find(equal_pairs[2 * k]), b = find(equal_pairs[2 * k + 1]);
+    if (a != b) parent[a > b ? a : b] = a > b ? b : a;
+  }
+  // copy constraints: every position points at the next position (in type-major order, cyclically) that holds the same variable
+  for (int p = 0; p < 12; p++) {
+    int q = p;
+    for (int step = 1; step <= 12; step++) {
+      const int cand = (p + step) % 12;
+      if (find(var[cand]) == find(var[p])) { q = cand; break; }
+    }
+    circuit[20 + 8 * (p / 4) + (p % 4)] = (uint8_t)(q / 4);              // COPY_OF.type: COPYOF_A / _B / _C
+    circuit[24 + 8 * (p / 4) + (p % 4)] = (uint8_t)(q % 4 + 1);          // COPY_OF.index, 1-based (plonk.h:144)
+  }
+  return PB_OK;
+}
+// witness rows a[4] b[4] c[4] of each item from its variable values: var_values[n][n_vars] (rows beyond num_gates are zero)
+int pb_witness_from_values(const size_t* a_idx, const size_t* b_idx, const size_t* c_idx, size_t num_gates, const uint8_t* var_values,
+                           size_t n_vars, uint8_t* witness, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(num_gates <= 4 && a_idx && b_idx && c_idx && var_values && witness);
+  for (size_t i = 0; i < num_gates; i++) ARG(a_idx[i] < n_vars && b_idx[i] < n_vars && c_idx[i] < n_vars);
+  for (size_t k = 0; k < n; k++) {
+    uint8_t* w = witness + 12 * k;
+    memset(w, 0, 12);
+    for (size_t i = 0; i < num_gates; i++) {
+      w[i] = var_values[k * n_vars + a_idx[i]]; w[4 + i] = var_values[k * n_vars + b_idx[i]]; w[8 + i] = var_values[k * n_vars + c_idx[i]];
+    }
+  }
   return PB_OK;
 }
 

@@ -904,8 +904,10 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) compact_kernel(const uint8_t* __r
 // Step 1: offs[g] = number of completed items before group g (GBLOCK items per group), *total = all of them.
 // One block: the status bytes of a chunk are at most a megabyte and hot in L2.
 constexpr int GBLOCK = 128;
+// total_host (optional): a second copy of the count in mapped pinned host memory -- the host-pointer pipelines read it after
+// the chunk's event instead of queueing a 4-byte D2H copy behind megabytes of proofs on the copy engine.
 __global__ void __launch_bounds__(1024) done_offsets_kernel(const uint8_t* __restrict__ status, size_t m, uint32_t* __restrict__ offs,
-                                                            uint32_t* __restrict__ total) {
+                                                            uint32_t* __restrict__ total, uint32_t* __restrict__ total_host = nullptr) {
   __shared__ uint32_t wsum[32];
   const uint32_t G = (uint32_t)((m + GBLOCK - 1) / GBLOCK);
   const bool al = (reinterpret_cast<uintptr_t>(status) & 15u) == 0;
@@ -939,7 +941,7 @@ __global__ void __launch_bounds__(1024) done_offsets_kernel(const uint8_t* __res
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)threadIdx.x >= d) wi += t; }
     wsum[threadIdx.x] = wi - w;
-    if (threadIdx.x == 31) *total = wi;
+    if (threadIdx.x == 31) { *total = wi; if (total_host) *total_host = wi; }
   }
   __syncthreads();
   uint32_t run = wsum[threadIdx.x >> 5] + incl - mine;
