@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--min-seconds", type=float, default=0.0,
                     help="sustained run: raise --steps until the timed region of `value` lasts at least this long (for the clock/power record)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: only `value` and the two kernel times (no e2e, no probes, no CPU arm)")
     ap.add_argument("--workload", default="prove_verify", choices=["prove_verify", "prove_verify_fs", "poly", "g1_mul", "pairing", "field"],
                     help="prove_verify = BASELINE config 5 (the headline, what the driver runs); poly / g1_mul / pairing = "
                          "configs 2 / 3 / 4 (single GPU, device-resident; extra lines for profiles/)")
@@ -369,6 +370,15 @@ def run_b200(args):
     per_rank = shard.gather_scalar(elapsed_ms / args.steps, dev)        # every rank's own ms per step (device time)
     gcounts, elapsed_ms = shard.reduce_counters(counts, elapsed_ms)
     value = total * args.steps / (elapsed_ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            os.write(json_fd, (json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": elapsed_ms / args.steps,
+                                           "roofline": {"kernel_ms": {"prove_kernel": prove_ms, "verify_kernel": verify_ms}},
+                                           "outcome": {"proof_byte_checksum": int(gcounts[17]), "verified_accept": int(gcounts[16])},
+                                           "e2e": {"value": 0.0}, "quick": True}) + "\n").encode())
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     def timed_steps(fn, steps):
         """max over ranks of the device time of `steps` calls of fn(k), barrier + synchronize on both sides"""

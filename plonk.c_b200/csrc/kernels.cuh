@@ -31,10 +31,54 @@ struct FieldTablesImage {
     for (uint32_t i = 0; i < 256; i++) w[8 + i / 4] |= cpow(i % 101u, 99u, 101u) << (8u * (i % 4u));
   }
 };
-__device__ const FieldTablesImage g_field_tables_image = FieldTablesImage();
+__device__ __align__(16) const FieldTablesImage g_field_tables_image = FieldTablesImage();
 PB_D void build_field_tables(FieldTables& ft) {
   for (int i = threadIdx.x; i < (int)(sizeof(FieldTables) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&ft)[i] = g_field_tables_image.w[i];
+}
+
+// ---- 1-D bulk asynchronous copies (cp.async.bulk, the TMA engine without a tensor map; UBLKCP in SASS) with an mbarrier.
+// One elected thread issues the copies of a block's tables and input slices; they cost no LSU issue slots and ONE memory
+// round trip, where per-thread LDG -> STS loops cost one round trip per iteration (ncu r1: the table loop and the three
+// staging loops were 13 % of the prover's stall samples, profiles/r2/NOTES.md).  Sizes and addresses are multiples of 16.
+#ifndef PB_BULK
+#define PB_BULK 1
+#endif
+PB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PB_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PB_D void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PB_D void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+PB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// shared -> global: the writers fence their generic-proxy stores, the block synchronises, one thread issues and waits until the
+// engine has READ shared memory (the block may then retire; the global writes complete on their own)
+PB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PB_D void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+PB_D void bulk_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 PB_D G1 load_g1(const uint8_t* p) { return G1{p[0], p[1], p[2] != 0 ? 1u : 0u}; }
@@ -630,10 +674,29 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
                                                       uint8_t* __restrict__ chal_out = nullptr) {
   __shared__ ProveSmem<Tables> sm;
   const int tid = threadIdx.x;
-  for (int k = tid; k < (int)(sizeof(Tables) / 4); k += PBLOCK)
-    reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
   const size_t first = (size_t)blockIdx.x * PBLOCK;
   static_assert(!(FS && PACKED), "the packed records carry the challenges");
+  static_assert(sizeof(Tables) % 16 == 0, "bulk copies move multiples of 16 bytes");
+#if PB_BULK
+  // tables and (struct inputs of a full block) the three input slices: bulk copies issued by one thread, one mbarrier
+  __shared__ __align__(8) uint64_t mbar;
+  const bool bulk_in = !PACKED && first + PBLOCK <= n;
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&mbar, (uint32_t)sizeof(Tables) + (bulk_in ? (uint32_t)PBLOCK * (12u + 9u + (FS ? 0u : 5u)) : 0u));
+    bulk_load(&sm.tb, gtb, (uint32_t)sizeof(Tables), &mbar);
+    if (bulk_in) {
+      bulk_load(sm.wit, wit + first * 12, PBLOCK * 12, &mbar);
+      bulk_load(sm.rnd, rnd + first * 9, PBLOCK * 9, &mbar);
+      if constexpr (!FS) bulk_load(sm.chal, chal + first * 5, PBLOCK * 5, &mbar);
+    }
+  }
+#else
+  constexpr bool bulk_in = false;
+  for (int k = tid; k < (int)(sizeof(Tables) / 4); k += PBLOCK)
+    reinterpret_cast<uint32_t*>(&sm.tb)[k] = reinterpret_cast<const uint32_t*>(gtb)[k];
+#endif
   const bool live = first + tid < n;
   uint32_t wa[4], wb[4], wc[4], r[9], ch[5];
   bool bad = false;
@@ -654,7 +717,11 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
     for (int k = 0; k < 9; k++) r[k] = v[12 + k];
 #pragma unroll
     for (int k = 0; k < 5; k++) ch[k] = v[21 + k];
+#if PB_BULK
+    mbar_wait(&mbar, 0);   // tables landed
+#else
     __syncthreads();   // tables staged
+#endif
   } else {
 #if PB_PROVE_PREFETCH
   {
@@ -667,10 +734,15 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
     }
   }
 #endif
-  stage_in<12, PBLOCK>(sm.wit, wit, first, n);
-  stage_in<9, PBLOCK>(sm.rnd, rnd, first, n);
-  if constexpr (!FS) stage_in<5, PBLOCK>(sm.chal, chal, first, n);
-  __syncthreads();
+  if (!bulk_in) {      // the ragged last block (or PB_BULK=0): per-thread staging copies
+    stage_in<12, PBLOCK>(sm.wit, wit, first, n);
+    stage_in<9, PBLOCK>(sm.rnd, rnd, first, n);
+    if constexpr (!FS) stage_in<5, PBLOCK>(sm.chal, chal, first, n);
+    __syncthreads();
+  }
+#if PB_BULK
+  mbar_wait(&mbar, 0);   // tables (and the bulk-copied inputs) landed
+#endif
 #pragma unroll
   for (int k = 0; k < 4; k++) { wa[k] = sm.wit[tid * 12 + k]; wb[k] = sm.wit[tid * 12 + 4 + k]; wc[k] = sm.wit[tid * 12 + 8 + k]; }
 #pragma unroll
@@ -710,8 +782,19 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
       co[5] = k5 ? (uint8_t)o.ch[5] : 0xFF;
     }
   }
-  uint8_t* po = sm.proof + tid * 34;
   const bool okp = o.status == 0u;     // a failed item's PROOF bytes are zero
+  // dense list of the completed proofs: the atomic is issued first and its result used last, so that the round trip to L2
+  // overlaps the writing of the record (it was 2.7 % of the kernel's stall samples when the warp waited for it on the spot)
+  const bool done = live && okp;
+  unsigned dmask = 0u;
+  int leader = -1;
+  uint32_t base = 0;
+  if (done_list) {
+    dmask = __ballot_sync(0xFFFFFFFFu, done);
+    leader = __ffs(dmask) - 1;
+    if (dmask && (tid & 31) == leader) base = atomicAdd(done_count, (uint32_t)__popc(dmask));
+  }
+  uint8_t* po = sm.proof + tid * 34;
 #pragma unroll
   for (int j = 0; j < 9; j++) {
     po[3 * j] = okp ? (uint8_t)o.pts[j].x : 0;
@@ -722,15 +805,22 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   for (int j = 0; j < 7; j++) po[27 + j] = okp ? (uint8_t)o.sc[j] : 0;
   sm.status[tid] = (uint8_t)o.status;
   if (done_list) {
-    const bool done = live && okp;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, done);
-    const int lane = tid & 31, leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (m && lane == leader) base = atomicAdd(done_count, (uint32_t)__popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader < 0 ? 0 : leader);
-    if (done) done_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(first + tid);
+    if (done) done_list[base + __popc(dmask & ((1u << (tid & 31)) - 1u))] = (uint32_t)(first + tid);
     if (live && !okp && verdict) verdict[first + tid] = 0xFF;
   }
+#if PB_BULK
+  if (first + PBLOCK <= n) {
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(proofs + first * 34, sm.proof, PBLOCK * 34);
+      bulk_store(status + first, sm.status, PBLOCK);
+      bulk_store_commit_wait();
+    }
+    return;
+  }
+#endif
   __syncthreads();
   stage_out<34, PBLOCK>(proofs, sm.proof, first, n);
   stage_out<1, PBLOCK>(status, sm.status, first, n);
@@ -826,9 +916,22 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
   const size_t first = (size_t)blockIdx.x * BLOCK;
   const size_t limit = done_list ? (size_t)*done_count : n;
   if (first >= limit) return;                                             // whole block beyond the dense list
+  static_assert(sizeof(VerifyTables) % 16 == 0 && sizeof(FieldTables) % 16 == 0, "bulk copies move multiples of 16 bytes");
+#if PB_BULK
+  // the 5 KB of tables arrive by two bulk copies issued by one thread (the per-thread loop was nine dependent L2 round trips)
+  __shared__ __align__(8) uint64_t mbar;
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&mbar, (uint32_t)(sizeof(VerifyTables) + sizeof(FieldTables)));
+    bulk_load(&sm.vt, gvt, (uint32_t)sizeof(VerifyTables), &mbar);
+    bulk_load(&sm.ft, &g_field_tables_image, (uint32_t)sizeof(FieldTables), &mbar);
+  }
+#else
   build_field_tables(sm.ft);
   for (int k = tid; k < (int)(sizeof(VerifyTables) / 4); k += BLOCK)
     reinterpret_cast<uint32_t*>(&sm.vt)[k] = reinterpret_cast<const uint32_t*>(gvt)[k];
+#endif
   size_t item = first + tid;
   const bool live = item < limit;
   const bool fs = chal == nullptr && packed == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
@@ -836,7 +939,9 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
   if (done_list) {
     // dense-list mode: the items of a block are scattered, so each lane reads its own 34-byte record straight into
     // registers (17 two-byte loads: records are 2-byte aligned) instead of staging it through shared memory
+#if !PB_BULK
     __syncthreads();                                                      // tables staged
+#endif
     if (!live) return;
     item = done_list[item];
     const uint16_t* pr = reinterpret_cast<const uint16_t*>(proofs + item * 34);
@@ -851,10 +956,16 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
 #pragma unroll
       for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
     }
+#if PB_BULK
+    mbar_wait(&mbar, 0);                                                  // tables landed (the record loads above are in flight meanwhile)
+#endif
   } else {
     stage_in<34, BLOCK>(sm.proof, proofs, first, n);
     if (chal) stage_in<5, BLOCK>(sm.chal, chal, first, n);
     __syncthreads();
+#if PB_BULK
+    mbar_wait(&mbar, 0);
+#endif
     if (!live) return;
 #pragma unroll
     for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];

@@ -2,7 +2,7 @@
 # usage: variant_sweep.sh variants/lib_*.so  -- runs the default bench with each library build (PB_LIB override) and prints
 # the prover / verifier kernel times and the outcome checksum (which must not change between variants)
 for lib in "$@"; do
-  PB_LIB=$lib python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+  PB_LIB=$lib python bench.py --steps 30 --warmup 5 --quick 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
 k = d['roofline']['kernel_ms']
