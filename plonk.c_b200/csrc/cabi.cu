@@ -496,9 +496,21 @@ int pb_config2_items_dev(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, 
   if (n == 0) return PB_OK;
   ARG(ctx && a && b && x && vals && prod && prod_len && quot && quot_len && rem && rem_len && evals && interp && interp_len);
   ARG(aligned16(a) && aligned16(b) && aligned16(vals) && aligned16(prod) && aligned16(quot) && aligned16(rem) && aligned16(interp));
-  config2_kernel<<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(ctx->cc, a, b, x, vals, prod, prod_len, quot, quot_len, rem, rem_len, evals,
-                                                                     interp, interp_len, n);
-  LAUNCH_CHECK("config2_kernel");
+  // full groups of PF4_ITEMS items: four items per thread, whole-word accesses (poly_fast.cuh); the ragged tail: one item per thread
+  const size_t blocks4 = (aligned16(x) && aligned16(prod_len) && aligned16(quot_len) && aligned16(rem_len) && aligned16(evals) && aligned16(interp_len))
+                             ? n / PF4_ITEMS : 0;
+  const size_t m = blocks4 * PF4_ITEMS;
+  if (blocks4) {
+    config2_kernel4<<<(unsigned)blocks4, PF4_BLOCK, 0, S(stream)>>>(ctx->cc, a, b, x, vals, prod, prod_len, quot, quot_len, rem, rem_len, evals, interp,
+                                                                   interp_len);
+    LAUNCH_CHECK("config2_kernel4");
+  }
+  if (n > m) {
+    config2_kernel<<<blocks_for(n - m, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(ctx->cc, a + 6 * m, b + 6 * m, x + m, vals + 4 * m, prod + 11 * m, prod_len + m,
+                                                                           quot + 7 * m, quot_len + m, rem + 4 * m, rem_len + m, evals + m,
+                                                                           interp + 4 * m, interp_len + m, n - m);
+    LAUNCH_CHECK("config2_kernel");
+  }
   return PB_OK;
 }
 

@@ -1,6 +1,7 @@
 // kernels.cuh -- __global__ entry points.  One item per thread everywhere: items are independent, a few
 // dozen bytes each, so there is no inter-thread communication beyond staging tables in shared memory.
 #pragma once
+#include <type_traits>
 #include "prover.cuh"
 #include "verifier.cuh"
 #include "wire.cuh"
@@ -765,7 +766,11 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
     for (int k = 0; k < 5; k++) ch[k] = 0;
   }
   ProofOut o;
-  prove_one<FS>(cc, sm.tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+#ifndef PB_PROVE_DEFER_WZ
+#define PB_PROVE_DEFER_WZ 1
+#endif
+  constexpr bool DEFER_WZ = PB_PROVE_DEFER_WZ && !FS && std::is_same<Tables, ProverWideTables>::value;
+  prove_one<FS, DEFER_WZ>(cc, sm.tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
   if (bad) o.status = 254u;
   if constexpr (FS) {
     if (chal_out && live) {
@@ -797,6 +802,7 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
   uint8_t* po = sm.proof + tid * 34;
 #pragma unroll
   for (int j = 0; j < 9; j++) {
+    if (DEFER_WZ && j == 7) continue;                     // [W_z] goes last: its gathers are still in flight
     po[3 * j] = okp ? (uint8_t)o.pts[j].x : 0;
     po[3 * j + 1] = okp ? (uint8_t)o.pts[j].y : 0;
     po[3 * j + 2] = okp ? (uint8_t)o.pts[j].inf : 0;
@@ -804,6 +810,12 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
 #pragma unroll
   for (int j = 0; j < 7; j++) po[27 + j] = okp ? (uint8_t)o.sc[j] : 0;
   sm.status[tid] = (uint8_t)o.status;
+  if constexpr (DEFER_WZ) {
+    const G1 wz = wz_finish(sm.tb, o.wz);
+    po[21] = okp ? (uint8_t)wz.x : 0;
+    po[22] = okp ? (uint8_t)wz.y : 0;
+    po[23] = okp ? (uint8_t)wz.inf : 0;
+  }
   if (done_list) {
     base = __shfl_sync(0xFFFFFFFFu, base, leader < 0 ? 0 : leader);
     if (done) done_list[base + __popc(dmask & ((1u << (tid & 31)) - 1u))] = (uint32_t)(first + tid);

@@ -241,4 +241,157 @@ __global__ void __launch_bounds__(PF_BLOCK) config2_kernel(const __grid_constant
   store_slice<7>(quot, sq, first, n);
 }
 
+// ---- four consecutive items per thread -------------------------------------------------------------------------------
+// One item per thread leaves these kernels issue-bound on bookkeeping: per-item address arithmetic, one narrow load per
+// record, one byte store per output coefficient (config2_kernel: 329 warp-instructions per item-warp for ~110 of
+// arithmetic, ncu profiles/r2).  Four consecutive items make every record group word-aligned -- 4 x 6 = 24 bytes in,
+// 4 x 11 = 44 and 4 x 7 = 28 bytes out -- so a thread moves whole 32/64/128-bit words: 8 loads and 11 + 7 shared-memory
+// word stores per FOUR items, output bytes inserted into their words with one PRMT each, lengths and one-byte results as
+// one word per array.  Same arithmetic, same results.  Full blocks only (PF4_ITEMS items); the caller runs the ragged
+// tail through the one-item-per-thread kernel.
+#ifndef PB_PF4_BLOCK
+#define PB_PF4_BLOCK 128
+#endif
+#ifndef PB_PF4_MINBLOCKS
+#define PB_PF4_MINBLOCKS 1
+#endif
+constexpr int PF4_BLOCK = PB_PF4_BLOCK;
+constexpr int PF4_ITEMS = 4 * PF4_BLOCK;
+// byte I of the word array w (compile-time I): one PRMT / shift
+template <int I, int NW>
+PB_D uint32_t byte_of(const uint32_t (&w)[NW]) { return __byte_perm(w[I >> 2], 0u, 0x4440 | (I & 3)); }
+// w's byte I := v (v < 256), compile-time I
+template <int I, int NW>
+PB_D void put_byte(uint32_t (&w)[NW], uint32_t v) {
+  constexpr uint32_t sel = (I & 3) == 0 ? 0x3214u : (I & 3) == 1 ? 0x3240u : (I & 3) == 2 ? 0x3410u : 0x4210u;
+  w[I >> 2] = __byte_perm(w[I >> 2], v, sel);
+}
+template <int N, int BASE, int NW>
+PB_D void get_bytes(uint32_t (&r)[N], const uint32_t (&w)[NW]) {
+  if constexpr (N > 0) {
+    uint32_t head[N > 1 ? N - 1 : 1];
+    if constexpr (N > 1) { get_bytes<N - 1, BASE>(head, w);
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) r[i] = head[i]; }
+    r[N - 1] = byte_of<BASE + N - 1>(w);
+  }
+}
+template <int N, int BASE, int NW>
+PB_D void put_bytes(uint32_t (&w)[NW], const uint32_t (&r)[N]) {
+  if constexpr (N > 0) {
+    if constexpr (N > 1) { uint32_t head[N - 1];
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) head[i] = r[i];
+      put_bytes<N - 1, BASE>(w, head); }
+    put_byte<BASE + N - 1>(w, r[N - 1]);
+  }
+}
+// the block's contiguous slice of an array with WORDS words per thread: shared memory (word stores at stride WORDS, an odd
+// number, so conflict-free) -> global as 128-bit stores
+template <int WORDS>
+PB_D void store_slice4(uint8_t* __restrict__ g, const uint32_t* smem, size_t block) {
+  constexpr int NV = PF4_BLOCK * WORDS / 4;
+  uint4* dst = reinterpret_cast<uint4*>(g + block * (size_t)(PF4_BLOCK * WORDS * 4));
+#pragma unroll
+  for (int k0 = 0; k0 < NV; k0 += PF4_BLOCK) {
+    const int k = k0 + (int)threadIdx.x;
+    if (k0 + PF4_BLOCK <= NV || k < NV) dst[k] = reinterpret_cast<const uint4*>(smem)[k];
+  }
+}
+
+template <int IT>
+PB_D void config2_item(const CircuitConst& cc, const uint32_t (&wa)[6], const uint32_t (&wb)[6], uint32_t xw, const uint32_t (&vw)[4],
+                       uint32_t (&pw)[11], uint32_t (&qw)[7], uint32_t (&rw)[4], uint32_t (&fw)[4], uint32_t (&lens)[4], uint32_t& yw) {
+  uint32_t ra[6], rb[6], p[11];
+  get_bytes<6, 6 * IT>(ra, wa);
+  get_bytes<6, 6 * IT>(rb, wb);
+#pragma unroll
+  for (int k = 0; k < 11; k++) p[k] = 0u;
+  mul_acc<6, 6>(p, ra, rb);                                     // poly_mul, poly.h:106-122
+#pragma unroll
+  for (int k = 0; k < 11; k++) p[k] = red17(p[k]);
+  put_bytes<11, 11 * IT>(pw, p);
+  // poly_divide by Z_H = x^4 - 1 (poly.h:124-177): q[j] = p[j+4] + q[j+4], remainder p[k] + q[k]
+  uint32_t q[7], r[4], f[4];
+  q[6] = p[10]; q[5] = p[9]; q[4] = p[8]; q[3] = p[7];
+  q[2] = add17(p[6], q[6]); q[1] = add17(p[5], q[5]); q[0] = add17(p[4], q[4]);
+  put_bytes<7, 7 * IT>(qw, q);
+#pragma unroll
+  for (int k = 0; k < 4; k++) r[k] = add17(p[k], q[k]);
+  rw[IT] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+  // poly_eval(A, x), Horner from the top (poly.h:265-272)
+  const uint32_t xv = __byte_perm(xw, 0u, 0x4440 | IT);
+  uint32_t y = 0u;
+#pragma unroll
+  for (int k = 5; k >= 0; k--) y = red17(y * xv + ra[k]);
+  yw |= y << (8 * IT);
+  // interpolate_at_h(vals) = h_pows_inv * vals (plonk.h:162-195)
+  const uint32_t v[4] = {vw[IT] & 0xFFu, __byte_perm(vw[IT], 0u, 0x4441), __byte_perm(vw[IT], 0u, 0x4442), vw[IT] >> 24};
+  interpolate(cc, v, f);
+  fw[IT] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
+  lens[0] |= canon_len(p) << (8 * IT);
+  lens[1] |= canon_len(q) << (8 * IT);
+  lens[2] |= canon_len(r) << (8 * IT);
+  lens[3] |= canon_len(f) << (8 * IT);
+}
+
+// BASELINE config 2, one launch, four items per thread; n_blocks * PF4_ITEMS items
+__global__ void __launch_bounds__(PF4_BLOCK, PB_PF4_MINBLOCKS) config2_kernel4(const __grid_constant__ CircuitConst cc, const uint8_t* __restrict__ a,
+                                                             const uint8_t* __restrict__ b, const uint8_t* __restrict__ x,
+                                                             const uint8_t* __restrict__ vals, uint8_t* __restrict__ prod,
+                                                             uint8_t* __restrict__ prod_len, uint8_t* __restrict__ quot,
+                                                             uint8_t* __restrict__ quot_len, uint8_t* __restrict__ rem,
+                                                             uint8_t* __restrict__ rem_len, uint8_t* __restrict__ evals,
+                                                             uint8_t* __restrict__ interp, uint8_t* __restrict__ interp_len) {
+  __shared__ __align__(16) uint32_t sp[PF4_BLOCK * 11];
+  __shared__ __align__(16) uint32_t sq[PF4_BLOCK * 7];
+  const int tid = threadIdx.x;
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + tid;      // this thread's items: 4 tg .. 4 tg + 3
+  uint32_t wa[6], wb[6], vw[4];
+  {
+    const uint2* A = reinterpret_cast<const uint2*>(a) + 3 * tg;
+    const uint2* B = reinterpret_cast<const uint2*>(b) + 3 * tg;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const uint2 u = A[k], v = B[k]; wa[2 * k] = u.x; wa[2 * k + 1] = u.y; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+    const uint4 v4 = reinterpret_cast<const uint4*>(vals)[tg];
+    vw[0] = v4.x; vw[1] = v4.y; vw[2] = v4.z; vw[3] = v4.w;
+  }
+  const uint32_t xw = reinterpret_cast<const uint32_t*>(x)[tg];
+  uint32_t pw[11], qw[7], rw[4], fw[4], lens[4] = {0u, 0u, 0u, 0u}, yw = 0u;
+#pragma unroll
+  for (int k = 0; k < 11; k++) pw[k] = 0u;
+#pragma unroll
+  for (int k = 0; k < 7; k++) qw[k] = 0u;
+  config2_item<0>(cc, wa, wb, xw, vw, pw, qw, rw, fw, lens, yw);
+  config2_item<1>(cc, wa, wb, xw, vw, pw, qw, rw, fw, lens, yw);
+  config2_item<2>(cc, wa, wb, xw, vw, pw, qw, rw, fw, lens, yw);
+  config2_item<3>(cc, wa, wb, xw, vw, pw, qw, rw, fw, lens, yw);
+  reinterpret_cast<uint4*>(rem)[tg] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+  reinterpret_cast<uint4*>(interp)[tg] = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+  reinterpret_cast<uint32_t*>(evals)[tg] = yw;
+  reinterpret_cast<uint32_t*>(prod_len)[tg] = lens[0];
+  reinterpret_cast<uint32_t*>(quot_len)[tg] = lens[1];
+  reinterpret_cast<uint32_t*>(rem_len)[tg] = lens[2];
+  reinterpret_cast<uint32_t*>(interp_len)[tg] = lens[3];
+#ifndef PB_PF4_DIRECT
+#define PB_PF4_DIRECT 0
+#endif
+#if PB_PF4_DIRECT
+  // word stores straight to global memory: a warp's 11 (7) store instructions together cover its contiguous 1408 (896) bytes
+  (void)sp; (void)sq;
+#pragma unroll
+  for (int k = 0; k < 11; k++) reinterpret_cast<uint32_t*>(prod)[tg * 11 + k] = pw[k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) reinterpret_cast<uint32_t*>(quot)[tg * 7 + k] = qw[k];
+#else
+#pragma unroll
+  for (int k = 0; k < 11; k++) sp[tid * 11 + k] = pw[k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) sq[tid * 7 + k] = qw[k];
+  __syncthreads();
+  store_slice4<11>(prod, sp, blockIdx.x);
+  store_slice4<7>(quot, sq, blockIdx.x);
+#endif
+}
+
 }  // namespace pb

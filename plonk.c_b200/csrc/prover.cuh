@@ -215,7 +215,32 @@ PB_HD G1 commit(const ProverWideTables& tb, const uint32_t (&c)[N], uint32_t /*l
   return acc;
 }
 
+// The wide tables' commitment split in two: the gathers (issue) and unpack + addition (finish).  prove_one can hand the
+// LAST commitment, [W_z], back unfinished (DEFER_WZ): its status byte does not depend on the point, so the kernel issues
+// the dense-list atomic and writes the rest of the record while the two gathers are in flight (they were 5.6 % of the
+// kernel's stall samples when unpacked on the spot, profiles/r2/NOTES.md).
+struct WzPending { uint32_t lo, hi; };
+PB_HD WzPending wz_issue(const ProverWideTables& tb, const uint32_t (&c)[9]) {
+  uint32_t idx = c[5], hi = c[8];
+#pragma unroll
+  for (int i = 4; i >= 0; i--) idx = idx * 17u + c[i];
+#pragma unroll
+  for (int i = 7; i >= 6; i--) hi = hi * 17u + c[i];
+  return WzPending{wide_load(tb.T6, idx), wide_load(tb.T3, hi)};
+}
+PB_HD WzPending z_issue(const ProverWideTables& tb, const uint32_t (&c)[7]) {
+  uint32_t idx = c[5];
+#pragma unroll
+  for (int i = 4; i >= 0; i--) idx = idx * 17u + c[i];
+  return WzPending{wide_load(tb.T6, idx), wide_load(tb.T3, c[6])};
+}
+#ifndef PB_PROVE_DEFER_Z
+#define PB_PROVE_DEFER_Z 1     // 1: finish [z] after round 3; 2: at the end of prove_one (explicit-challenge mode, wide tables); 0: on the spot
+#endif
+PB_HD G1 wz_finish(const ProverWideTables& tb, const WzPending& q) { return g1_add_c(tb.ft, unpack_g1_16(q.lo), unpack_g1_16(q.hi)); }
+
 struct ProofOut {
+  WzPending wz;     // DEFER_WZ only: pts[7] = wz_finish(tb, wz) is left to the caller
   G1 pts[9];        // a b c z t_lo t_mid t_hi W_z W_zw   (PROOF field order, plonk.h:24-41)
   uint32_t sc[7];   // a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z
   uint32_t status;  // SURVEY.md Appendix B row of the first exit that fires, 0 = completed
@@ -224,7 +249,7 @@ struct ProofOut {
 
 // FS = false: the reference's interface, challenges given by the caller (plonk.h:227).
 // FS = true: the five challenge arguments are ignored and drawn from the transcript (transcript.cuh).
-template <bool FS = false, typename Tables>
+template <bool FS = false, bool DEFER_WZ = false, typename Tables>
 PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
                     const uint32_t (&wa)[4], const uint32_t (&wb)[4], const uint32_t (&wc)[4],
                     const uint32_t (&rnd)[9], uint32_t alpha, uint32_t beta, uint32_t gamma,
@@ -285,7 +310,10 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   uint32_t Z[7] = {sub17(accx[0], rnd[8]), sub17(accx[1], rnd[7]), sub17(accx[2], rnd[6]), accx[3],
                    rnd[8], rnd[7], rnd[6]};
   const uint32_t len_z = canon_len(Z);
-  out.pts[3] = commit(tb, Z, len_z);
+  constexpr bool DEFER_Z = PB_PROVE_DEFER_Z != 0 && DEFER_WZ;
+  WzPending zq{0u, 0u};
+  if constexpr (DEFER_Z) zq = z_issue(tb, Z);
+  else out.pts[3] = commit(tb, Z, len_z);
   if constexpr (FS) tr.round2(out.pts[3], alpha);
 
   // ---- round 3 (plonk.h:385-511): t_numer = t1 + t2 - t3 + t4, all raw, one reduction at the end
@@ -402,6 +430,7 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
     open_zw();
   }
 
+  if constexpr (DEFER_Z && PB_PROVE_DEFER_Z == 1) out.pts[3] = wz_finish(tb, zq);
   // ---- round 4 (plonk.h:527-574): openings at z and the (non-standard) linearisation r(x)
   uint32_t zp[18];
 #pragma unroll
@@ -461,12 +490,14 @@ PB_HD void prove_one(const CircuitConst& cc, const Tables& tb,
   const bool bad_rem1 = rs(wn[0] + z * Wz[0]) != 0u;
   const uint32_t len_wz = canon_len(Wz);
   const uint32_t len_w = umax(len_wz, len_wzw);
-  out.pts[7] = commit(tb, Wz, len_wz);
+  if constexpr (DEFER_WZ) out.wz = wz_issue(tb, Wz);
+  else out.pts[7] = commit(tb, Wz, len_wz);
   if constexpr (FS) {
     out.ch[0] = alpha; out.ch[1] = beta; out.ch[2] = gamma; out.ch[3] = z; out.ch[4] = v;
     tr.round5(out.pts[7], out.pts[8], out.ch[5]);
   }
 
+  if constexpr (DEFER_Z && PB_PROVE_DEFER_Z == 2) out.pts[3] = wz_finish(tb, zq);
   out.sc[0] = a_z; out.sc[1] = b_z; out.sc[2] = c_z; out.sc[3] = s1_z; out.sc[4] = s2_z;
   out.sc[5] = r_z; out.sc[6] = zw_z;
 

@@ -3,6 +3,7 @@
 // can be diffed against the oracle in this GPU-less container.  Never linked into the product library and
 // never used as a fallback: libplonk_b200.so has no host execution path.
 #include <vector>
+#include <type_traits>
 #include <cstdint>
 #include <cstring>
 #include "../../plonk.c_b200/csrc/prover.cuh"
@@ -33,7 +34,12 @@ static void prove_batch(const CircuitConst& cc, const Tables& tb, const uint8_t*
     ProofOut o;
     if (chal) {
       const uint8_t* ch = chal + 5 * i;
-      prove_one<false>(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+      if constexpr (std::is_same<Tables, ProverWideTables>::value) {   // as prove_kernel runs it: [W_z] handed back unfinished
+        prove_one<false, true>(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+        o.pts[7] = wz_finish(tb, o.wz);
+      } else {
+        prove_one<false>(cc, tb, wa, wb, wc, r, ch[0], ch[1], ch[2], ch[3], ch[4], o);
+      }
     } else {
       prove_one<true>(cc, tb, wa, wb, wc, r, 0u, 0u, 0u, 0u, 0u, o);
       if (chal_out) {
