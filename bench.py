@@ -634,6 +634,32 @@ def run_config(args):
         fn()
         return m / (time.perf_counter() - t0)
 
+    def pinned(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
+
+    def HP(x):
+        return x.ctypes.data_as(C.c_void_p)
+
+    def e2e_of(fn, items, h2d, d2h, api, unit):
+        """the same metric through the host-pointer entry point: pinned host buffers in and out, copies inside the timed region"""
+        steps = min(args.steps, 10)
+        for _ in range(2):
+            fn()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return {"value": items * world * steps / (ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms / steps, "steps": steps, "api": api}
+
     peaks, peak_src = measured_peaks()
     if args.workload == "poly":
         n = 1 << 22
@@ -675,6 +701,13 @@ def run_config(args):
                          "per_kernel_gbs": {k: parts[k][1] * n / (ms[k] * 1e-3) / 1e9 for k in ms}},
             "cpu_baseline": {"value": cpu_rate, "unit": "items/s", "cores": 1, "kind": okind, "sample": f"first {m} items, single thread"}}
         line["roofline"]["frac"] = line["roofline"]["achieved"] / peaks["hbm_gbs"]
+        h_in = [pinned(v) for v in (a, b, x, vals)]
+        h_out = tuple(pinned(np.empty(sh, np.uint8)) for sh in ((n, 11), (n,), (n, 7), (n,), (n, 4), (n,), (n,), (n, 4), (n,)))
+        line["e2e"] = e2e_of(lambda: ctx.config2_items_into(*h_in, h_out), n, 17 * n, 31 * n,
+                             "pb_config2_items (host pointers, pinned; generic chunked pipeline)", "items/s")
+        dev_out = ctx.config2_items(A, B, X, V)
+        if not all(np.array_equal(h, d.cpu().numpy()) for h, d in zip(h_out, dev_out)):
+            raise SystemExit("bench.py: config-2 host path and device path disagree")
         gpu_launches = 5 * args.steps
     elif args.workload == "g1_mul":
         n = 1 << 24
@@ -693,6 +726,11 @@ def run_config(args):
                          "algorithmic_int_ops_per_item": int_ops, "traffic": None,
                          "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
             "cpu_baseline": {"value": cpu_rate, "unit": "smul/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
+        hp, hs, ho = pinned(g1s[ai % 10]), pinned(sc), pinned(np.empty((n, 3), np.uint8))
+        line["e2e"] = e2e_of(lambda: host._check(lib.pb_g1_mul_u8(HP(hp), HP(hs), HP(ho), C.c_size_t(n))), n, 4 * n, 3 * n,
+                             "pb_g1_mul_u8 (host pointers, pinned; generic chunked pipeline)", "smul/s")
+        if not np.array_equal(ho, out.cpu().numpy()):
+            raise SystemExit("bench.py: g1_mul host path and device path disagree")
         gpu_launches = args.steps
     elif args.workload == "pairing":
         n = 1 << 22
@@ -713,6 +751,11 @@ def run_config(args):
             "roofline": {"bound": "int32", "kernel": "pairing_kernel", "unit": "TIOP/s", "achieved": int_ops * n / (ms * 1e-3) / 1e12,
                          "algorithmic_int_ops_per_item": int_ops, "traffic": None, "hbm_gbs": 7 * n / (ms * 1e-3) / 1e9},
             "cpu_baseline": {"value": cpu_rate, "unit": "pairings/s", "cores": cores, "kind": okind, "sample": f"first {m} items, {cores} threads"}}
+        hp, hq, ho = pinned(Pn), pinned(Q.cpu().numpy()), pinned(np.empty((n, 2), np.uint8))
+        line["e2e"] = e2e_of(lambda: host._check(lib.pb_pairing(HP(hp), HP(hq), HP(ho), C.c_size_t(n))), n, 5 * n, 2 * n,
+                             "pb_pairing (host pointers, pinned; generic chunked pipeline)", "pairings/s")
+        if not np.array_equal(ho, out.cpu().numpy()):
+            raise SystemExit("bench.py: pairing host path and device path disagree")
         gpu_launches = args.steps
     elif args.workload == "field":
         # kernel family (1): hf.h / gf.h element-wise over 2^27 elements (HBM-bound: 3 B per element, 2 for unary ops), plus

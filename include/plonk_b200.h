@@ -145,10 +145,13 @@ int pb_interpolate_at_h_dev(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out
 int pb_interpolate_at_h(const pb_ctx *ctx, const uint8_t *vals, uint8_t *out, uint8_t *olen, size_t n);
 /* BASELINE config 2 in one launch (SURVEY.md section 8(d) "config 2 unit"): per item a[6], b[6], x, vals[4] ->
  * prod = poly_mul(a, b) [11]+len, (quot [7]+len, rem [4]+len) = poly_divide(prod, Z_H of the context), evals = poly_eval(a, x),
- * interp [4]+len = interpolate_at_h(vals).  Byte-identical to the four separate entry points.  Device pointers only. */
+ * interp [4]+len = interpolate_at_h(vals).  Byte-identical to the four separate entry points. */
 int pb_config2_items_dev(const pb_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *x, const uint8_t *vals,
                          uint8_t *prod, uint8_t *prod_len, uint8_t *quot, uint8_t *quot_len, uint8_t *rem, uint8_t *rem_len,
                          uint8_t *evals, uint8_t *interp, uint8_t *interp_len, size_t n, void *stream);
+int pb_config2_items(const pb_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *x, const uint8_t *vals,
+                     uint8_t *prod, uint8_t *prod_len, uint8_t *quot, uint8_t *quot_len, uint8_t *rem, uint8_t *rem_len,
+                     uint8_t *evals, uint8_t *interp, uint8_t *interp_len, size_t n);
 /* matrix_mul (matrix.h:81-98): out[i] = a[i] (m x k) times b[i] (k x c), row-major, m,k,c <= 8 */
 int pb_matrix_mul_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n, void *stream);
 int pb_matrix_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, uint32_t m, uint32_t k, uint32_t c, size_t n);
@@ -186,6 +189,15 @@ int pb_srs_eval_at_s_dev(const pb_ctx *ctx, const uint8_t *polys, const uint8_t 
 int pb_srs_eval_at_s(const pb_ctx *ctx, const uint8_t *polys, const uint8_t *plen, size_t sp, uint8_t *out,
                      uint8_t *status, size_t n);
 
+/* the same against an SRS handed over per call (no context): srs_g1s[srs_len][3]; the reference's loop as written, g1_mul
+ * per term by double-and-add.  trim = 1: rows pass through poly_new first (as everywhere in this ABI); trim = 0: the loop runs
+ * over plen[i] terms as given, like the reference's over POLY.len (a trailing zero term is not always a no-op, g1.h:60).
+ * What the drop-in srs_eval_at_s calls: one launch per commitment instead of one per term. */
+int pb_srs_eval_at_s_raw_dev(const uint8_t *srs_g1s, uint32_t srs_len, const uint8_t *polys, const uint8_t *plen, size_t sp,
+                             int trim, uint8_t *out, uint8_t *status, size_t n, void *stream);
+int pb_srs_eval_at_s_raw(const uint8_t *srs_g1s, uint32_t srs_len, const uint8_t *polys, const uint8_t *plen, size_t sp,
+                         int trim, uint8_t *out, uint8_t *status, size_t n);
+
 /* ---- kernel family (4): gt.h, pairing.h */
 int pb_gtp_mul_dev(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n, void *stream); /* gt.h:23-28 */
 int pb_gtp_mul(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
@@ -204,6 +216,12 @@ int pb_pairing_f(uint64_t r, const uint8_t *p, const uint8_t *q, uint8_t *out, s
 /* constraints_satisfy (constraints.h:145-171): out[i] in {0,1} */
 int pb_constraints_satisfy_dev(const pb_ctx *ctx, const uint8_t *witness, uint8_t *out, size_t n, void *stream);
 int pb_constraints_satisfy(const pb_ctx *ctx, const uint8_t *witness, uint8_t *out, size_t n);
+/* constraints_satisfy for a gate list of any length (no context): selectors[5][rows] = q_l q_r q_o q_m q_c rows, a / b / c
+ * [n][rows]; first_bad[i] = index of the first row whose gate equation fails (the row the reference prints), -1 if none */
+int pb_constraints_satisfy_rows_dev(const uint8_t *selectors, uint32_t rows, const uint8_t *a, const uint8_t *b,
+                                    const uint8_t *c, int32_t *first_bad, size_t n, void *stream);
+int pb_constraints_satisfy_rows(const uint8_t *selectors, uint32_t rows, const uint8_t *a, const uint8_t *b, const uint8_t *c,
+                                int32_t *first_bad, size_t n);
 /* plonk_prove (plonk.h:223-656) over a batch: witness[n][12], rnd[n][9], chal[n][5] -> proofs[n][34], status[n] */
 int pb_plonk_prove_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                        uint8_t *proofs, uint8_t *status, size_t n, void *stream);

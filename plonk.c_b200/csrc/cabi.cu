@@ -62,9 +62,6 @@ struct Dev {
   ~Dev() { if (p) cudaFree(p); }
   template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
-#define DEV(name, bytes) Dev name(bytes); if (name.err != cudaSuccess) return cuda_fail(name.err, "cudaMalloc")
-#define H2D(dev, host, bytes) CU(cudaMemcpy((dev).p, host, bytes, cudaMemcpyHostToDevice))
-#define D2H(host, dev, bytes) CU(cudaMemcpy(host, (dev).p, bytes, cudaMemcpyDeviceToHost))
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
 constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // largest chunk of the host-pointer pipelines
@@ -196,6 +193,111 @@ int pipe_init(pb_ctx* c, size_t cap) {
   return PB_OK;
 }
 
+
+// ------------------------------------------------------------------ host-pointer wrappers: one chunked pipeline for all
+// Every host-pointer entry point of families (1)-(4) -- and the drop-in headers behind them -- runs through this: per
+// device, three streams (H2D engine, SMs, D2H engine) over a ring of four buffer sets that are owned by the library and
+// grown on demand, so a call allocates nothing once warm and a large batch overlaps its copies with its kernels.  Round 1
+// paid cudaMalloc + cudaFree + blocking copies + a device-wide synchronise per call.
+struct HArr { const void* in; void* out; size_t item; };           // one host array: `item` bytes per batch item; in XOR out
+struct GenericPipe {
+  std::mutex mu;
+  int device = 0;
+  bool ready = false;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  static constexpr int SLOTS = 4;
+  struct Slot { uint8_t* buf = nullptr; size_t cap = 0; cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr; } slots[SLOTS];
+};
+GenericPipe* pipe_for_device(int dev) {
+  static std::mutex mu;
+  static std::map<int, GenericPipe*> pipes;
+  std::lock_guard<std::mutex> lock(mu);
+  auto& p = pipes[dev];
+  if (!p) { p = new GenericPipe(); p->device = dev; }
+  return p;
+}
+constexpr size_t GP_CHUNK_BYTES = 8u << 20;    // per chunk, the larger of the two directions: well above the ~1 MB PCIe knee
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// launch(din, dout, m, stream): enqueue the kernels for m items whose inputs are at din[k] and outputs go to dout[k]
+template <typename F>
+int piped(int device, std::initializer_list<HArr> arrs, size_t n, F&& launch) {
+  if (n == 0) return PB_OK;
+  int rc = require_device();
+  if (rc) return rc;
+  if (device < 0) CU(cudaGetDevice(&device));
+  DeviceGuard g(device);
+  if (!g.ok) return fail(PB_ERR_CUDA, "plonk_b200: cudaSetDevice failed");
+  GenericPipe* gp = pipe_for_device(device);
+  std::lock_guard<std::mutex> lock(gp->mu);
+  if (!gp->ready) {
+    if (!gp->s_in) CU(cudaStreamCreateWithFlags(&gp->s_in, cudaStreamNonBlocking));
+    if (!gp->s_k) CU(cudaStreamCreateWithFlags(&gp->s_k, cudaStreamNonBlocking));
+    if (!gp->s_out) CU(cudaStreamCreateWithFlags(&gp->s_out, cudaStreamNonBlocking));
+    for (auto& s : gp->slots) {
+      if (!s.ev_in) CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+      if (!s.ev_k) CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+      if (!s.ev_out) CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    gp->ready = true;
+  }
+  std::vector<HArr> a(arrs);
+  size_t in_item = 0, out_item = 0;
+  for (auto& x : a) { (x.in ? in_item : out_item) += x.item; }
+  const size_t per = in_item > out_item ? in_item : out_item;
+  size_t chunk = GP_CHUNK_BYTES / (per ? per : 1);
+  chunk = chunk < 4096 ? 4096 : (chunk & ~(size_t)4095);           // a multiple of 4096 items: every array's chunk offset stays 16-byte aligned
+  if (chunk > n) chunk = n;
+  size_t need = 0;
+  std::vector<size_t> off(a.size());
+  for (size_t k = 0; k < a.size(); k++) { off[k] = need; need += up256(chunk * a[k].item); }
+  const size_t nchunks = (n + chunk - 1) / chunk;
+  const int used = nchunks < (size_t)GenericPipe::SLOTS ? (int)nchunks : GenericPipe::SLOTS;
+  for (int k = 0; k < used; k++) {
+    auto& s = gp->slots[k];
+    if (s.cap < need) {
+      CU(cudaStreamSynchronize(gp->s_in)); CU(cudaStreamSynchronize(gp->s_k)); CU(cudaStreamSynchronize(gp->s_out));
+      if (s.buf) CU(cudaFree(s.buf));
+      s.buf = nullptr; s.cap = 0;
+      const size_t cap = need < (1u << 16) ? (1u << 16) : need;
+      CU(cudaMalloc(&s.buf, cap));
+      s.cap = cap;
+    }
+  }
+  std::vector<uint8_t*> din, dout;
+  size_t done = 0;
+  for (size_t c = 0; c < nchunks; c++) {
+    auto& s = gp->slots[c % GenericPipe::SLOTS];
+    const size_t m = n - done < chunk ? n - done : chunk;
+    const bool reuse = c >= (size_t)GenericPipe::SLOTS;
+    if (reuse) { CU(cudaStreamWaitEvent(gp->s_in, s.ev_k, 0)); CU(cudaStreamWaitEvent(gp->s_in, s.ev_out, 0)); }
+    din.clear(); dout.clear();
+    for (size_t k = 0; k < a.size(); k++) {
+      if (a[k].in) {
+        din.push_back(s.buf + off[k]);
+        CU(cudaMemcpyAsync(s.buf + off[k], static_cast<const uint8_t*>(a[k].in) + done * a[k].item, m * a[k].item, cudaMemcpyHostToDevice, gp->s_in));
+      } else {
+        dout.push_back(s.buf + off[k]);
+      }
+    }
+    CU(cudaEventRecord(s.ev_in, gp->s_in));
+    CU(cudaStreamWaitEvent(gp->s_k, s.ev_in, 0));
+    if ((rc = launch(din.data(), dout.data(), m, gp->s_k))) return rc;
+    CU(cudaEventRecord(s.ev_k, gp->s_k));
+    CU(cudaStreamWaitEvent(gp->s_out, s.ev_k, 0));
+    for (size_t k = 0; k < a.size(); k++)
+      if (!a[k].in) CU(cudaMemcpyAsync(static_cast<uint8_t*>(a[k].out) + done * a[k].item, s.buf + off[k], m * a[k].item, cudaMemcpyDeviceToHost, gp->s_out));
+    CU(cudaEventRecord(s.ev_out, gp->s_out));
+    done += m;
+  }
+  CU(cudaStreamSynchronize(gp->s_out));
+  CU(cudaStreamSynchronize(gp->s_k));
+  CU(cudaStreamSynchronize(gp->s_in));
+  return PB_OK;
+}
+#define HIN(p, item) HArr{(p), nullptr, (size_t)(item)}
+#define HOUT(p, item) HArr{nullptr, (p), (size_t)(item)}
+
 }  // namespace
 
 extern "C" {
@@ -245,17 +347,12 @@ int pb_field_op_dev(int field, int op, const uint8_t* a, const uint8_t* b, uint8
 }
 int pb_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(a && out);
-  DEV(da, n); DEV(db, n); DEV(dout, n);
-  H2D(da, a, n);
-  if (b) H2D(db, b, n);
-  rc = pb_field_op_dev(field, op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n);
-  return PB_OK;
+  ARG(b || op == PB_OP_NEG || op == PB_OP_INV);
+  if (b) return piped(-1, {HIN(a, 1), HIN(b, 1), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_field_op_dev(field, op, di[0], di[1], dq[0], m, st); });
+  return piped(-1, {HIN(a, 1), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_field_op_dev(field, op, di[0], nullptr, dq[0], m, st); });
 }
 
 int pb_field_new_dev(int field, const int64_t* v, uint8_t* out, size_t n, void* stream) {
@@ -270,16 +367,9 @@ int pb_field_new_dev(int field, const int64_t* v, uint8_t* out, size_t n, void* 
 }
 int pb_field_new(int field, const int64_t* v, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;
-  int rc = require_device();
-  if (rc) return rc;
   ARG(v && out);
-  DEV(dv, n * 8); DEV(dout, n);
-  H2D(dv, v, n * 8);
-  rc = pb_field_new_dev(field, dv.as<int64_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n);
-  return PB_OK;
+  return piped(-1, {HIN(v, 8), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_field_new_dev(field, reinterpret_cast<const int64_t*>(di[0]), dq[0], m, st); });
 }
 
 // ------------------------------------------------------------------ family (2)
@@ -310,17 +400,10 @@ int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, 
 int pb_poly_binop(int op, const uint8_t* a, const uint8_t* alen, size_t sa, const uint8_t* b, const uint8_t* blen, size_t sb,
                   uint8_t* out, uint8_t* olen, size_t so, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(a && alen && b && blen && out && olen);
-  DEV(da, n * sa); DEV(dal, n); DEV(db, n * sb); DEV(dbl, n); DEV(dout, n * so); DEV(dol, n);
-  H2D(da, a, n * sa); H2D(dal, alen, n); H2D(db, b, n * sb); H2D(dbl, blen, n);
-  rc = pb_poly_binop_dev(op, da.as<uint8_t>(), dal.as<uint8_t>(), sa, db.as<uint8_t>(), dbl.as<uint8_t>(), sb,
-                         dout.as<uint8_t>(), dol.as<uint8_t>(), so, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * so); D2H(olen, dol, n);
-  return PB_OK;
+  return piped(-1, {HIN(a, sa), HIN(alen, 1), HIN(b, sb), HIN(blen, 1), HOUT(out, so), HOUT(olen, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_poly_binop_dev(op, di[0], di[1], sa, di[2], di[3], sb, dq[0], dq[1], so, m, st); });
 }
 
 int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
@@ -349,17 +432,10 @@ int pb_poly_divide_dev(const uint8_t* num, const uint8_t* nlen, size_t sn, const
 int pb_poly_divide(const uint8_t* num, const uint8_t* nlen, size_t sn, const uint8_t* den, const uint8_t* dlen, size_t sd,
                    uint8_t* quot, uint8_t* qlen, size_t sq, uint8_t* rem, uint8_t* rlen, size_t sr, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(num && nlen && den && dlen && quot && qlen && rem && rlen && status);
-  DEV(dn, n * sn); DEV(dnl, n); DEV(dd, n * sd); DEV(ddl, n); DEV(dq, n * sq); DEV(dql, n); DEV(dr, n * sr); DEV(drl, n); DEV(dst, n);
-  H2D(dn, num, n * sn); H2D(dnl, nlen, n); H2D(dd, den, n * sd); H2D(ddl, dlen, n);
-  rc = pb_poly_divide_dev(dn.as<uint8_t>(), dnl.as<uint8_t>(), sn, dd.as<uint8_t>(), ddl.as<uint8_t>(), sd, dq.as<uint8_t>(),
-                          dql.as<uint8_t>(), sq, dr.as<uint8_t>(), drl.as<uint8_t>(), sr, dst.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(quot, dq, n * sq); D2H(qlen, dql, n); D2H(rem, dr, n * sr); D2H(rlen, drl, n); D2H(status, dst, n);
-  return PB_OK;
+  return piped(-1, {HIN(num, sn), HIN(nlen, 1), HIN(den, sd), HIN(dlen, 1), HOUT(quot, sq), HOUT(qlen, 1), HOUT(rem, sr), HOUT(rlen, 1), HOUT(status, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_poly_divide_dev(di[0], di[1], sn, di[2], di[3], sd, dq[0], dq[1], sq, dq[2], dq[3], sr, dq[4], m, st); });
 }
 
 int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n, void* stream) {
@@ -382,16 +458,9 @@ int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uin
 }
 int pb_poly_eval(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(p && plen && x && out);
-  DEV(dp, n * sp); DEV(dl, n); DEV(dx, n); DEV(dout, n);
-  H2D(dp, p, n * sp); H2D(dl, plen, n); H2D(dx, x, n);
-  rc = pb_poly_eval_dev(dp.as<uint8_t>(), dl.as<uint8_t>(), sp, dx.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n);
-  return PB_OK;
+  return piped(-1, {HIN(p, sp), HIN(plen, 1), HIN(x, 1), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_poly_eval_dev(di[0], di[1], sp, di[2], dq[0], m, st); });
 }
 
 int pb_poly_unop_dev(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen,
@@ -407,17 +476,11 @@ int pb_poly_unop_dev(int op, const uint8_t* p, const uint8_t* plen, size_t sp, c
 }
 int pb_poly_unop(int op, const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* k, uint8_t* out, uint8_t* olen, size_t so, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(p && plen && out && olen);
-  DEV(dp, n * sp); DEV(dl, n); DEV(dk, n); DEV(dout, n * so); DEV(dol, n);
-  H2D(dp, p, n * sp); H2D(dl, plen, n);
-  if (k) H2D(dk, k, n);
-  rc = pb_poly_unop_dev(op, dp.as<uint8_t>(), dl.as<uint8_t>(), sp, k ? dk.as<uint8_t>() : nullptr, dout.as<uint8_t>(), dol.as<uint8_t>(), so, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * so); D2H(olen, dol, n);
-  return PB_OK;
+  if (k) return piped(-1, {HIN(p, sp), HIN(plen, 1), HIN(k, 1), HOUT(out, so), HOUT(olen, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_poly_unop_dev(op, di[0], di[1], sp, di[2], dq[0], dq[1], so, m, st); });
+  return piped(-1, {HIN(p, sp), HIN(plen, 1), HOUT(out, so), HOUT(olen, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_poly_unop_dev(op, di[0], di[1], sp, nullptr, dq[0], dq[1], so, m, st); });
 }
 
 int pb_poly_slice_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
@@ -432,17 +495,10 @@ int pb_poly_slice_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const ui
 int pb_poly_slice(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* start, const uint8_t* end, uint8_t* out,
                   uint8_t* olen, size_t so, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(p && plen && start && end && out && olen && status);
-  DEV(dp, n * sp); DEV(dl, n); DEV(ds, n); DEV(de, n); DEV(dout, n * so); DEV(dol, n); DEV(dst, n);
-  H2D(dp, p, n * sp); H2D(dl, plen, n); H2D(ds, start, n); H2D(de, end, n);
-  rc = pb_poly_slice_dev(dp.as<uint8_t>(), dl.as<uint8_t>(), sp, ds.as<uint8_t>(), de.as<uint8_t>(), dout.as<uint8_t>(), dol.as<uint8_t>(), so,
-                         dst.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * so); D2H(olen, dol, n); D2H(status, dst, n);
-  return PB_OK;
+  return piped(-1, {HIN(p, sp), HIN(plen, 1), HIN(start, 1), HIN(end, 1), HOUT(out, so), HOUT(olen, 1), HOUT(status, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_poly_slice_dev(di[0], di[1], sp, di[2], di[3], dq[0], dq[1], so, dq[2], m, st); });
 }
 
 int pb_poly_lagrange_dev(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status,
@@ -456,16 +512,10 @@ int pb_poly_lagrange_dev(const uint8_t* xs, const uint8_t* ys, size_t len, uint8
 }
 int pb_poly_lagrange(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* out, uint8_t* olen, size_t so, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(xs && ys && out && olen && status);
-  DEV(dx, n * len); DEV(dy, n * len); DEV(dout, n * so); DEV(dol, n); DEV(dst, n);
-  H2D(dx, xs, n * len); H2D(dy, ys, n * len);
-  rc = pb_poly_lagrange_dev(dx.as<uint8_t>(), dy.as<uint8_t>(), len, dout.as<uint8_t>(), dol.as<uint8_t>(), so, dst.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * so); D2H(olen, dol, n); D2H(status, dst, n);
-  return PB_OK;
+  return piped(-1, {HIN(xs, len), HIN(ys, len), HOUT(out, so), HOUT(olen, 1), HOUT(status, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_poly_lagrange_dev(di[0], di[1], len, dq[0], dq[1], so, dq[2], m, st); });
 }
 
 int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n, void* stream) {
@@ -480,14 +530,8 @@ int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out
 int pb_interpolate_at_h(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && vals && out && olen);
-  DeviceGuard g(ctx->device);
-  DEV(dv, n * 4); DEV(dout, n * 4); DEV(dol, n);
-  H2D(dv, vals, n * 4);
-  int rc = pb_interpolate_at_h_dev(ctx, dv.as<uint8_t>(), dout.as<uint8_t>(), dol.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 4); D2H(olen, dol, n);
-  return PB_OK;
+  return piped(ctx->device, {HIN(vals, 4), HOUT(out, 4), HOUT(olen, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_interpolate_at_h_dev(ctx, di[0], dq[0], dq[1], m, st); });
 }
 
 int pb_config2_items_dev(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, const uint8_t* x, const uint8_t* vals, uint8_t* prod,
@@ -514,6 +558,16 @@ int pb_config2_items_dev(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, 
   return PB_OK;
 }
 
+int pb_config2_items(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, const uint8_t* x, const uint8_t* vals, uint8_t* prod, uint8_t* prod_len,
+                     uint8_t* quot, uint8_t* quot_len, uint8_t* rem, uint8_t* rem_len, uint8_t* evals, uint8_t* interp, uint8_t* interp_len, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && a && b && x && vals && prod && prod_len && quot && quot_len && rem && rem_len && evals && interp && interp_len);
+  return piped(ctx->device, {HIN(a, 6), HIN(b, 6), HIN(x, 1), HIN(vals, 4), HOUT(prod, 11), HOUT(prod_len, 1), HOUT(quot, 7), HOUT(quot_len, 1), HOUT(rem, 4),
+                             HOUT(rem_len, 1), HOUT(evals, 1), HOUT(interp, 4), HOUT(interp_len, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_config2_items_dev(ctx, di[0], di[1], di[2], di[3], dq[0], dq[1], dq[2], dq[3], dq[4], dq[5], dq[6], dq[7], dq[8], m, st); });
+}
+
 int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(a && b && out && m >= 1 && k >= 1 && c >= 1 && m <= 8 && k <= 8 && c <= 8);
@@ -524,16 +578,9 @@ int pb_matrix_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t
 }
 int pb_matrix_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t m, uint32_t k, uint32_t c, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
-  ARG(a && b && out);
-  DEV(da, n * m * k); DEV(db, n * k * c); DEV(dout, n * m * c);
-  H2D(da, a, n * m * k); H2D(db, b, n * k * c);
-  rc = pb_matrix_mul_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), m, k, c, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * m * c);
-  return PB_OK;
+  ARG(a && b && out && m >= 1 && k >= 1 && c >= 1 && m <= 8 && k <= 8 && c <= 8);
+  return piped(-1, {HIN(a, m * k), HIN(b, k * c), HOUT(out, m * c)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t cnt, cudaStream_t st) {
+    return pb_matrix_mul_dev(di[0], di[1], dq[0], m, k, c, cnt, st); });
 }
 int pb_matrix_inv_dev(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -545,16 +592,9 @@ int pb_matrix_inv_dev(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n, vo
 }
 int pb_matrix_inv(const uint8_t* a, uint8_t* out, uint32_t dim, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
-  ARG(a && out);
-  DEV(da, n * dim * dim); DEV(dout, n * dim * dim);
-  H2D(da, a, n * dim * dim);
-  rc = pb_matrix_inv_dev(da.as<uint8_t>(), dout.as<uint8_t>(), dim, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * dim * dim);
-  return PB_OK;
+  ARG(a && out && dim >= 1 && dim <= 8);
+  return piped(-1, {HIN(a, dim * dim), HOUT(out, dim * dim)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_matrix_inv_dev(di[0], dq[0], dim, m, st); });
 }
 
 int pb_matrix_gauss_jordan_dev(uint8_t* a, uint32_t rows, uint32_t cols, size_t n, void* stream) {
@@ -566,16 +606,10 @@ int pb_matrix_gauss_jordan_dev(uint8_t* a, uint32_t rows, uint32_t cols, size_t 
 }
 int pb_matrix_gauss_jordan(uint8_t* a, uint32_t rows, uint32_t cols, size_t n) {
   if (n == 0) return PB_OK;
-  int rc = require_device();
-  if (rc) return rc;
-  ARG(a);
-  DEV(da, n * rows * cols);
-  H2D(da, a, n * rows * cols);
-  rc = pb_matrix_gauss_jordan_dev(da.as<uint8_t>(), rows, cols, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(a, da, n * rows * cols);
-  return PB_OK;
+  ARG(a && rows >= 1 && cols >= 1 && rows <= 8 && cols <= 16);
+  return piped(-1, {HIN(a, rows * cols), HOUT(a, rows * cols)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    CU(cudaMemcpyAsync(dq[0], di[0], m * rows * cols, cudaMemcpyDeviceToDevice, st));     // the kernel reduces in place
+    return pb_matrix_gauss_jordan_dev(dq[0], rows, cols, m, st); });
 }
 
 // ------------------------------------------------------------------ family (3)
@@ -589,17 +623,11 @@ int pb_g1_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_
 }
 int pb_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
-  ARG(a && out);
-  DEV(da, n * 3); DEV(db, n * 3); DEV(dout, n * 3);
-  H2D(da, a, n * 3);
-  if (b) H2D(db, b, n * 3);
-  rc = pb_g1_op_dev(op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 3);
-  return PB_OK;
+  ARG(a && out && (b || op != PB_G_ADD));
+  if (b) return piped(-1, {HIN(a, 3), HIN(b, 3), HOUT(out, 3)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g1_op_dev(op, di[0], di[1], dq[0], m, st); });
+  return piped(-1, {HIN(a, 3), HOUT(out, 3)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g1_op_dev(op, di[0], nullptr, dq[0], m, st); });
 }
 int pb_g1_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -611,16 +639,9 @@ int pb_g1_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, 
 }
 int pb_g1_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(points && scalars && out);
-  DEV(dp, n * 3); DEV(ds, n * 8); DEV(dout, n * 3);
-  H2D(dp, points, n * 3); H2D(ds, scalars, n * 8);
-  rc = pb_g1_mul_dev(dp.as<uint8_t>(), ds.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 3);
-  return PB_OK;
+  return piped(-1, {HIN(points, 3), HIN(scalars, 8), HOUT(out, 3)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g1_mul_dev(di[0], reinterpret_cast<const uint64_t*>(di[1]), dq[0], m, st); });
 }
 int pb_g1_mul_u8_dev(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -632,16 +653,9 @@ int pb_g1_mul_u8_dev(const uint8_t* points, const uint8_t* scalars, uint8_t* out
 }
 int pb_g1_mul_u8(const uint8_t* points, const uint8_t* scalars, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(points && scalars && out);
-  DEV(dp, n * 3); DEV(ds, n); DEV(dout, n * 3);
-  H2D(dp, points, n * 3); H2D(ds, scalars, n);
-  rc = pb_g1_mul_u8_dev(dp.as<uint8_t>(), ds.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 3);
-  return PB_OK;
+  return piped(-1, {HIN(points, 3), HIN(scalars, 1), HOUT(out, 3)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g1_mul_u8_dev(di[0], di[1], dq[0], m, st); });
 }
 int pb_g1_is_on_curve_dev(const uint8_t* points, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -653,16 +667,9 @@ int pb_g1_is_on_curve_dev(const uint8_t* points, uint8_t* out, size_t n, void* s
 }
 int pb_g1_is_on_curve(const uint8_t* points, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(points && out);
-  DEV(dp, n * 3); DEV(dout, n);
-  H2D(dp, points, n * 3);
-  rc = pb_g1_is_on_curve_dev(dp.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n);
-  return PB_OK;
+  return piped(-1, {HIN(points, 3), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g1_is_on_curve_dev(di[0], dq[0], m, st); });
 }
 int pb_g2_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -674,17 +681,11 @@ int pb_g2_op_dev(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_
 }
 int pb_g2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
-  ARG(a && out);
-  DEV(da, n * 2); DEV(db, n * 2); DEV(dout, n * 2);
-  H2D(da, a, n * 2);
-  if (b) H2D(db, b, n * 2);
-  rc = pb_g2_op_dev(op, da.as<uint8_t>(), b ? db.as<uint8_t>() : nullptr, dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  ARG(a && out && (b || op != PB_G_ADD));
+  if (b) return piped(-1, {HIN(a, 2), HIN(b, 2), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g2_op_dev(op, di[0], di[1], dq[0], m, st); });
+  return piped(-1, {HIN(a, 2), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g2_op_dev(op, di[0], nullptr, dq[0], m, st); });
 }
 int pb_g2_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -696,16 +697,9 @@ int pb_g2_mul_dev(const uint8_t* points, const uint64_t* scalars, uint8_t* out, 
 }
 int pb_g2_mul(const uint8_t* points, const uint64_t* scalars, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(points && scalars && out);
-  DEV(dp, n * 2); DEV(ds, n * 8); DEV(dout, n * 2);
-  H2D(dp, points, n * 2); H2D(ds, scalars, n * 8);
-  rc = pb_g2_mul_dev(dp.as<uint8_t>(), ds.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  return piped(-1, {HIN(points, 2), HIN(scalars, 8), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_g2_mul_dev(di[0], reinterpret_cast<const uint64_t*>(di[1]), dq[0], m, st); });
 }
 
 int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status,
@@ -721,14 +715,34 @@ int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t*
 int pb_srs_eval_at_s(const pb_ctx* ctx, const uint8_t* polys, const uint8_t* plen, size_t sp, uint8_t* out, uint8_t* status, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && polys && plen && out && status);
-  DeviceGuard g(ctx->device);
-  DEV(dp, n * sp); DEV(dl, n); DEV(dout, n * 3); DEV(dst, n);
-  H2D(dp, polys, n * sp); H2D(dl, plen, n);
-  int rc = pb_srs_eval_at_s_dev(ctx, dp.as<uint8_t>(), dl.as<uint8_t>(), sp, dout.as<uint8_t>(), dst.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 3); D2H(status, dst, n);
+  return piped(ctx->device, {HIN(polys, sp), HIN(plen, 1), HOUT(out, 3), HOUT(status, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_srs_eval_at_s_dev(ctx, di[0], di[1], sp, dq[0], dq[1], m, st); });
+}
+
+int pb_srs_eval_at_s_raw_dev(const uint8_t* srs_g1s, uint32_t srs_len, const uint8_t* polys, const uint8_t* plen, size_t sp, int trim,
+                             uint8_t* out, uint8_t* status, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(srs_g1s && polys && plen && out && status && sp >= 1 && sp <= PB_POLY_MAX && srs_len >= 1);
+  commit_raw_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(srs_g1s, srs_len, polys, plen, (int)sp, trim, out, status, n);
+  LAUNCH_CHECK("commit_raw_kernel");
   return PB_OK;
+}
+int pb_srs_eval_at_s_raw(const uint8_t* srs_g1s, uint32_t srs_len, const uint8_t* polys, const uint8_t* plen, size_t sp, int trim, uint8_t* out,
+                         uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(srs_g1s && polys && plen && out && status && srs_len >= 1);
+  // the SRS is one shared array, not a per-item one: it rides along as a single "item" of srs_len * 3 bytes per chunk
+  int rc = require_device();
+  if (rc) return rc;
+  void* d_srs = nullptr;
+  CU(cudaMalloc(&d_srs, 3 * (size_t)srs_len));
+  cudaError_t e = cudaMemcpy(d_srs, srs_g1s, 3 * (size_t)srs_len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    rc = piped(-1, {HIN(polys, sp), HIN(plen, 1), HOUT(out, 3), HOUT(status, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+      return pb_srs_eval_at_s_raw_dev(static_cast<const uint8_t*>(d_srs), srs_len, di[0], di[1], sp, trim, dq[0], dq[1], m, st); });
+  cudaFree(d_srs);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return rc;
 }
 
 // ------------------------------------------------------------------ family (4)
@@ -742,16 +756,9 @@ int pb_gtp_mul_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, v
 }
 int pb_gtp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(a && b && out);
-  DEV(da, n * 2); DEV(db, n * 2); DEV(dout, n * 2);
-  H2D(da, a, n * 2); H2D(db, b, n * 2);
-  rc = pb_gtp_mul_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  return piped(-1, {HIN(a, 2), HIN(b, 2), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_gtp_mul_dev(di[0], di[1], dq[0], m, st); });
 }
 int pb_gtp_pow_dev(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -763,16 +770,9 @@ int pb_gtp_pow_dev(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n, 
 }
 int pb_gtp_pow(const uint8_t* a, const uint64_t* e, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(a && e && out);
-  DEV(da, n * 2); DEV(de, n * 8); DEV(dout, n * 2);
-  H2D(da, a, n * 2); H2D(de, e, n * 8);
-  rc = pb_gtp_pow_dev(da.as<uint8_t>(), de.as<uint64_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  return piped(-1, {HIN(a, 2), HIN(e, 8), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_gtp_pow_dev(di[0], reinterpret_cast<const uint64_t*>(di[1]), dq[0], m, st); });
 }
 int pb_line_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -784,16 +784,9 @@ int pb_line_dev(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, void
 }
 int pb_line(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(a && b && out);
-  DEV(da, n * 3); DEV(db, n * 3); DEV(dout, n * 3);
-  H2D(da, a, n * 3); H2D(db, b, n * 3);
-  rc = pb_line_dev(da.as<uint8_t>(), db.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 3);
-  return PB_OK;
+  return piped(-1, {HIN(a, 3), HIN(b, 3), HOUT(out, 3)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_line_dev(di[0], di[1], dq[0], m, st); });
 }
 int pb_pairing_dev(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -805,16 +798,9 @@ int pb_pairing_dev(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, v
 }
 int pb_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(p && q && out);
-  DEV(dp, n * 3); DEV(dq, n * 2); DEV(dout, n * 2);
-  H2D(dp, p, n * 3); H2D(dq, q, n * 2);
-  rc = pb_pairing_dev(dp.as<uint8_t>(), dq.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  return piped(-1, {HIN(p, 3), HIN(q, 2), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_pairing_dev(di[0], di[1], dq[0], m, st); });
 }
 int pb_pairing_f_dev(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
@@ -826,16 +812,9 @@ int pb_pairing_f_dev(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* ou
 }
 int pb_pairing_f(uint64_t r, const uint8_t* p, const uint8_t* q, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
-  int rc = require_device();
-  if (rc) return rc;
   ARG(p && q && out);
-  DEV(dp, n * 3); DEV(dq, n * 2); DEV(dout, n * 2);
-  H2D(dp, p, n * 3); H2D(dq, q, n * 2);
-  rc = pb_pairing_f_dev(r, dp.as<uint8_t>(), dq.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n * 2);
-  return PB_OK;
+  return piped(-1, {HIN(p, 3), HIN(q, 2), HOUT(out, 2)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_pairing_f_dev(r, di[0], di[1], dq[0], m, st); });
 }
 
 // ------------------------------------------------------------------ context
@@ -1095,14 +1074,32 @@ int pb_constraints_satisfy_dev(const pb_ctx* ctx, const uint8_t* witness, uint8_
 int pb_constraints_satisfy(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && out);
-  DeviceGuard g(ctx->device);
-  DEV(dw, n * 12); DEV(dout, n);
-  H2D(dw, witness, n * 12);
-  int rc = pb_constraints_satisfy_dev(ctx, dw.as<uint8_t>(), dout.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(out, dout, n);
+  return piped(ctx->device, {HIN(witness, 12), HOUT(out, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_constraints_satisfy_dev(ctx, di[0], dq[0], m, st); });
+}
+
+int pb_constraints_satisfy_rows_dev(const uint8_t* selectors, uint32_t rows, const uint8_t* a, const uint8_t* b, const uint8_t* c, int32_t* first_bad,
+                                    size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(selectors && a && b && c && first_bad && rows >= 1);
+  satisfy_rows_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(selectors, rows, a, b, c, first_bad, n);
+  LAUNCH_CHECK("satisfy_rows_kernel");
   return PB_OK;
+}
+int pb_constraints_satisfy_rows(const uint8_t* selectors, uint32_t rows, const uint8_t* a, const uint8_t* b, const uint8_t* c, int32_t* first_bad, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(selectors && a && b && c && first_bad && rows >= 1);
+  int rc = require_device();
+  if (rc) return rc;
+  void* d_q = nullptr;
+  CU(cudaMalloc(&d_q, 5 * (size_t)rows));
+  cudaError_t e = cudaMemcpy(d_q, selectors, 5 * (size_t)rows, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    rc = piped(-1, {HIN(a, rows), HIN(b, rows), HIN(c, rows), HOUT(first_bad, 4)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+      return pb_constraints_satisfy_rows_dev(static_cast<const uint8_t*>(d_q), rows, di[0], di[1], di[2], reinterpret_cast<int32_t*>(dq[0]), m, st); });
+  cudaFree(d_q);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return rc;
 }
 
 // prove launch: pair tables when the SRS is canonical, the sequential tables otherwise
@@ -1620,14 +1617,10 @@ int pb_plonk_prove_fs(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* 
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && proofs && status);
   if (!chal_out) return pipeline(ctx, witness, rnd, nullptr, nullptr, proofs, status, nullptr, n, PIPE_PROVE);
-  DeviceGuard g(ctx->device);   // with the challenge read-back: one unchunked launch
-  DEV(dw, n * 12); DEV(dr, n * 9); DEV(dp, n * 34); DEV(ds, n); DEV(dc, n * 6);
-  H2D(dw, witness, n * 12); H2D(dr, rnd, n * 9);
-  int rc = pb_plonk_prove_fs_dev(ctx, dw.as<uint8_t>(), dr.as<uint8_t>(), dp.as<uint8_t>(), ds.as<uint8_t>(), dc.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(proofs, dp, n * 34); D2H(status, ds, n); D2H(chal_out, dc, n * 6);
-  return PB_OK;
+  // with the challenge read-back: the generic chunked pipeline
+  return piped(ctx->device, {HIN(witness, 12), HIN(rnd, 9), HOUT(proofs, 34), HOUT(status, 1), HOUT(chal_out, 6)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_plonk_prove_fs_dev(ctx, di[0], di[1], dq[0], dq[1], dq[2], m, st); });
 }
 int pb_plonk_prove_verify_fs(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status,
                              uint8_t* verdict, size_t n) {
@@ -1639,40 +1632,24 @@ int pb_plonk_prove_verify_fs(const pb_ctx* ctx, const uint8_t* witness, const ui
 int pb_plonk_verify_fs(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* verdict, uint8_t* gt, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && verdict);
-  DeviceGuard g(ctx->device);
-  DEV(dp, n * 34); DEV(dv, n); DEV(dg, n * 4);
-  H2D(dp, proofs, n * 34);
-  int rc = pb_plonk_verify_fs_dev(ctx, dp.as<uint8_t>(), dv.as<uint8_t>(), gt ? dg.as<uint8_t>() : nullptr, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(verdict, dv, n);
-  if (gt) D2H(gt, dg, n * 4);
-  return PB_OK;
+  if (gt) return piped(ctx->device, {HIN(proofs, 34), HOUT(verdict, 1), HOUT(gt, 4)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_plonk_verify_fs_dev(ctx, di[0], dq[0], dq[1], m, st); });
+  return piped(ctx->device, {HIN(proofs, 34), HOUT(verdict, 1)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_plonk_verify_fs_dev(ctx, di[0], dq[0], nullptr, m, st); });
 }
 int pb_fs_challenges(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal6, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal6);
-  DeviceGuard g(ctx->device);
-  DEV(dp, n * 34); DEV(dc, n * 6);
-  H2D(dp, proofs, n * 34);
-  int rc = pb_fs_challenges_dev(ctx, dp.as<uint8_t>(), dc.as<uint8_t>(), n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(chal6, dc, n * 6);
-  return PB_OK;
+  return piped(ctx->device, {HIN(proofs, 34), HOUT(chal6, 6)}, n, [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+    return pb_fs_challenges_dev(ctx, di[0], dq[0], m, st); });
 }
 int pb_plonk_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal && u && verdict);
-  DeviceGuard g(ctx->device);
-  DEV(dp, n * 34); DEV(dc, n * 5); DEV(du, n); DEV(dv, n); DEV(dg, n * 4);
-  H2D(dp, proofs, n * 34); H2D(dc, chal, n * 5); H2D(du, u, n);
-  int rc = pb_plonk_verify_dev(ctx, dp.as<uint8_t>(), dc.as<uint8_t>(), du.as<uint8_t>(), dv.as<uint8_t>(), gt ? dg.as<uint8_t>() : nullptr, n, nullptr);
-  if (rc) return rc;
-  CU(cudaDeviceSynchronize());
-  D2H(verdict, dv, n);
-  if (gt) D2H(gt, dg, n * 4);
-  return PB_OK;
+  if (gt) return piped(ctx->device, {HIN(proofs, 34), HIN(chal, 5), HIN(u, 1), HOUT(verdict, 1), HOUT(gt, 4)}, n,
+                       [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) { return pb_plonk_verify_dev(ctx, di[0], di[1], di[2], dq[0], dq[1], m, st); });
+  return piped(ctx->device, {HIN(proofs, 34), HIN(chal, 5), HIN(u, 1), HOUT(verdict, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) { return pb_plonk_verify_dev(ctx, di[0], di[1], di[2], dq[0], nullptr, m, st); });
 }
 
 // ---- circuit front-end: what eval_expr / gate_list_append produce (constraints.h:227-309) -> the

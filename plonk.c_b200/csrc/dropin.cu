@@ -311,13 +311,14 @@ G1 srs_eval_at_s(const SRS* srs, const POLY* vs) {                              
     fprintf(stderr, "Poynomial degree exceeds SRS size: POLY degree: %zu, SRS supports up to degree: %zu \n", vs->len, vs->len);
     exit(EXIT_FAILURE);
   }
-  // terms = g1_mul(g1s[i], coeff_i) as one batch, then the reference's left-to-right sum
-  std::vector<uint8_t> pts(3 * (vs->len ? vs->len : 1)), terms(3 * (vs->len ? vs->len : 1));
+  // one launch: g1_mul(g1s[i], coeff_i) per term and the reference's left-to-right sum, on the device
+  if (vs->len == 0) return g1_identity();
+  if (vs->len > PB_POLY_MAX) need_len(vs, "srs_eval_at_s");
+  std::vector<uint8_t> pts(3 * vs->len);
   for (size_t i = 0; i < vs->len; i++) g1_bytes(&pts[3 * i], &srs->g1s[i]);
-  gpu(pb_g1_mul_u8(pts.data(), bytes(vs->coeffs), terms.data(), vs->len));
-  G1 acc = g1_identity();
-  for (size_t i = 0; i < vs->len; i++) { G1 t = g1_from(&terms[3 * i]); acc = g1_add(&acc, &t); }
-  return acc;
+  uint8_t out[3], st = 0, len = (uint8_t)vs->len;
+  gpu(pb_srs_eval_at_s_raw(pts.data(), (uint32_t)vs->len, bytes(vs->coeffs), &len, vs->len, /*trim=*/0, out, &st, 1));
+  return g1_from(out);
 }
 
 // ------------------------------------------------------------------ constraints.h (host-side circuit authoring)
@@ -345,13 +346,15 @@ CONSTRAINTS constraints_new(GATE* gates, size_t num_gates, COPY_OF* c_a, COPY_OF
   return k;
 }
 bool constraints_satisfy(const CONSTRAINTS* c, const ASSIGNMENTS* a) {                                                    // src/constraints.h:145-171
-  // rows are checked in order and the first failing row is reported on stdout, like the reference
-  for (size_t i = 0; i < c->num_constraints; i++) {
-    HF ab = hf_mul(a->a[i], a->b[i]);
-    HF lhs = hf_add(hf_add(hf_mul(c->q_l[i], a->a[i]), hf_mul(c->q_r[i], a->b[i])),
-                    hf_add(hf_add(hf_mul(c->q_o[i], a->c[i]), hf_mul(c->q_m[i], ab)), c->q_c[i]));
-    if (lhs.value != 0) { printf("Constraint %zu not satisfied.\n", i); return false; }
-  }
+  // the gate equations are evaluated on the GPU (pb_constraints_satisfy_rows); the first failing row is reported on stdout, like the reference
+  const size_t rows = c->num_constraints;
+  if (rows == 0) return true;
+  std::vector<uint8_t> q(5 * rows);
+  const HF* sel[5] = {c->q_l, c->q_r, c->q_o, c->q_m, c->q_c};
+  for (int s = 0; s < 5; s++) memcpy(&q[s * rows], sel[s], rows);
+  int32_t bad = -1;
+  gpu(pb_constraints_satisfy_rows(q.data(), (uint32_t)rows, bytes(a->a), bytes(a->b), bytes(a->c), &bad, 1));
+  if (bad >= 0) { printf("Constraint %zu not satisfied.\n", (size_t)bad); return false; }
   return true;
 }
 void constraints_free(CONSTRAINTS* k) {                                                                                   // src/constraints.h:173-183

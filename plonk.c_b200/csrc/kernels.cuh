@@ -545,6 +545,34 @@ __global__ void __launch_bounds__(BLOCK) commit_kernel(const uint32_t* __restric
   store_g1(out + 3 * i, acc);
 }
 
+// srs_eval_at_s (srs.h:53-68) against an SRS handed over per call (no context, no table): the reference's loop as written --
+// g1_mul(g1s[i], coeff_i) by double-and-add, summed left to right.  For callers that hold an SRS struct and a handful of
+// polynomials (the drop-in srs_eval_at_s): one launch instead of one per term.
+__global__ void __launch_bounds__(BLOCK_LIGHT) commit_raw_kernel(const uint8_t* __restrict__ g1s, uint32_t srs_len, const uint8_t* __restrict__ polys,
+                                                                 const uint8_t* __restrict__ plen, int sp, int trim, uint8_t* __restrict__ out,
+                                                                 uint8_t* __restrict__ status, size_t n) {
+  __shared__ FieldTables ft;
+  build_field_tables(ft);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* row = polys + i * sp;
+  int len = plen[i] > sp ? sp : plen[i];
+  // trim: the row is passed through poly_new first, as in the other batch entry points; otherwise len is used as given -- the
+  // reference's loop runs over POLY.len terms, and a trailing zero term is NOT a no-op when the accumulator is an "identity with
+  // coordinates" (g1_add returns *b when a is infinite, g1.h:60)
+  while (trim && len > 1 && row[len - 1] == 0) len--;
+  if ((uint32_t)len > srs_len) {                                 // "exceeds SRS size", srs.h:54-57
+    status[i] = 1;
+    out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0;
+    return;
+  }
+  status[i] = 0;
+  G1 acc = g1_identity();
+  for (int k = 0; k < len; k++) acc = g1_add(ft, acc, g1_mul(ft, load_g1(g1s + 3 * k), (uint64_t)row[k]));
+  store_g1(out + 3 * i, acc);
+}
+
 // ------------------------------------------------------------------ family (4)
 __global__ void __launch_bounds__(BLOCK_LIGHT) gtp_mul_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,6 +624,22 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) satisfy_kernel(const __grid_const
     ok &= red17(cc.qv[0][g] * a + cc.qv[1][g] * b + cc.qv[2][g] * c + cc.qv[3][g] * (a * b) + cc.qv[4][g]) == 0u;
   }
   out[i] = ok ? 1 : 0;
+}
+
+// constraints_satisfy (constraints.h:145-171) for a gate list of any length: q[5][rows] selectors (q_l q_r q_o q_m q_c),
+// a / b / c [n][rows]; first_bad[i] = the first row whose gate equation fails, -1 if all hold (the reference prints that row)
+__global__ void __launch_bounds__(BLOCK_LIGHT) satisfy_rows_kernel(const uint8_t* __restrict__ q, uint32_t rows, const uint8_t* __restrict__ a,
+                                                                   const uint8_t* __restrict__ b, const uint8_t* __restrict__ c,
+                                                                   int32_t* __restrict__ first_bad, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t bad = -1;
+  for (uint32_t g = rows; g-- > 0;) {
+    const uint32_t av = a[i * rows + g], bv = b[i * rows + g], cv = c[i * rows + g];
+    const uint32_t lhs = q[g] * av + q[rows + g] * bv + q[2 * rows + g] * cv + q[3 * rows + g] * (av * bv) + q[4 * rows + g];
+    if (red17(lhs) != 0u) bad = (int32_t)g;
+  }
+  first_bad[i] = bad;
 }
 
 // plonk_prove over a batch.  Shared memory: the per-lane-indexed tables, and a staging area through

@@ -417,9 +417,24 @@ class Plonk:
         c.run(self._h, c.inp(vals), po, pl, C.c_size_t(n))
         return out, olen
 
+    def config2_items_into(self, a, b, x, vals, outs):
+        """Host path with caller-owned (pinned) numpy buffers: outs = (prod[n][11], prod_len[n], quot[n][7], quot_len[n],
+        rem[n][4], rem_len[n], evals[n], interp[n][4], interp_len[n])."""
+        n = _n(a)
+        shapes = ((n, 11), (n,), (n, 7), (n,), (n, 4), (n,), (n,), (n, 4), (n,))
+        c = _Call("pb_config2_items", a, b, x, vals)
+        assert not c.dev
+        c.run(self._h, c.inp(a), c.inp(b), c.inp(x), c.inp(vals), *(c.outbuf(o, sh) for o, sh in zip(outs, shapes)), C.c_size_t(n))
+
     def config2_items(self, a, b, x, vals):
-        """BASELINE config 2 in one launch (torch CUDA tensors): returns (prod, prod_len, quot, quot_len, rem, rem_len, evals,
-        interp, interp_len), byte-identical to poly_mul / poly_divide(., Z_H) / poly_eval / interpolate_at_h."""
+        """BASELINE config 2 in one launch: returns (prod, prod_len, quot, quot_len, rem, rem_len, evals, interp, interp_len),
+        byte-identical to poly_mul / poly_divide(., Z_H) / poly_eval / interpolate_at_h.  torch CUDA tensors -> device path;
+        numpy arrays -> the pipelined host path."""
+        if not _is_torch(a):
+            n = _n(a)
+            outs = tuple(np.empty(sh, np.uint8) for sh in ((n, 11), (n,), (n, 7), (n,), (n, 4), (n,), (n,), (n, 4), (n,)))
+            self.config2_items_into(a, b, x, vals, outs)
+            return outs
         import torch
         n = _n(a)
         dev = a.device
@@ -680,6 +695,34 @@ def wire_split_sv(sv):
     st, vd = np.empty_like(sv), np.empty_like(sv)
     _check(lib().pb_wire_split_sv(sv.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), vd.ctypes.data_as(C.c_void_p), C.c_size_t(sv.shape[0])))
     return st, vd
+
+
+def srs_eval_at_s_raw(srs_g1s, polys, plen, trim=True):
+    """srs_eval_at_s against an SRS passed per call (no context): -> (points[n][3], status[n])"""
+    g = np.ascontiguousarray(srs_g1s, np.uint8)
+    c = _Call("pb_srs_eval_at_s_raw", polys)
+    n = _n(polys)
+    out, po = c.out((n, 3))
+    status, ps = c.out((n,))
+    if c.dev:
+        g = c.torch.as_tensor(g, device=c.device)
+        c.keep.append(g)
+        pg = C.c_void_p(g.data_ptr())
+    else:
+        pg = g.ctypes.data_as(C.c_void_p)
+    c.run(pg, C.c_uint32(g.shape[0]), c.inp(polys), c.inp(plen), C.c_size_t(int(polys.shape[1])), C.c_int(1 if trim else 0), po, ps, C.c_size_t(n))
+    return out, status
+
+
+def constraints_satisfy_rows(selectors, a, b, c_):
+    """selectors[5][rows], a / b / c [n][rows] (numpy) -> first failing row per item (int32, -1 = satisfied)"""
+    q = np.ascontiguousarray(selectors, np.uint8)
+    a, b, c_ = (np.ascontiguousarray(v, np.uint8) for v in (a, b, c_))
+    n, rows = a.shape
+    out = np.empty(n, np.int32)
+    _check(lib().pb_constraints_satisfy_rows(q.ctypes.data_as(C.c_void_p), C.c_uint32(rows), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                             c_.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+    return out
 
 
 def tally(proofs, status, verdict, counts):

@@ -462,3 +462,55 @@ def test_compact_and_packed_many_chunks(host, W):
     pk.prove_verify_compact(wit[:1000], rnd[:1000], chal[:1000], u[:1000])
     dense3, s3, v3 = pk.prove_verify_compact(wit, rnd, chal, u)
     ps.eq("compact, second call", (dense3, s3, v3), (dense, s2, v2))
+
+
+def test_srs_eval_raw_and_satisfy_rows(host, oracle, W):
+    """The context-free entry points behind the drop-in srs_eval_at_s / constraints_satisfy: one launch each, exactly the
+    reference's loops -- including an untrimmed polynomial over a garbage SRS, where a trailing zero term changes the result."""
+    import torch
+    import util
+    rng = np.random.default_rng(21)
+    n = 20000
+    for g1s, _ in (W.generator_srs(9), util.garbage_srs(10)):
+        polys = rng.integers(0, 17, (n, 8), dtype=np.uint8)
+        polys[rng.random((n, 8)) < 0.3] = 0
+        plen = rng.integers(1, 9, n).astype(np.uint8)
+        pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, np.array([36, 31, 90, 82], np.uint8))
+        want = pk.srs_eval_at_s(polys, plen)                               # the table-based kernel, checked against the oracle elsewhere
+        ps.eq("raw == context", host.srs_eval_at_s_raw(g1s, polys, plen), want)
+        ps.eq("raw == context (device)", tuple(t.cpu().numpy() for t in host.srs_eval_at_s_raw(g1s, torch.from_numpy(polys).cuda(), torch.from_numpy(plen).cuda())), want)
+        # untrimmed: the reference's loop over POLY.len terms = the oracle's term-by-term sum
+        pts = np.zeros((n, 3), np.uint8); pts[:, 2] = 1
+        for k in range(8):
+            term = oracle.g1_mul(np.tile(g1s[k:k + 1], (n, 1)), polys[:, k].astype(np.uint64))
+            nxt = oracle.g1_op(0, pts, term)
+            live = plen > k
+            pts[live] = nxt[live]
+        got, st = host.srs_eval_at_s_raw(g1s, polys, plen, trim=False)
+        assert not st.any()
+        ps.eq("untrimmed loop", got, pts)
+    q = rng.integers(0, 17, (5, 7), dtype=np.uint8)
+    q[2] = 16                                                            # q_o = -1: a row holds iff c = q_l a + q_r b + q_m a b + q_c
+    a, b, c = (rng.integers(0, 17, (n, 7), dtype=np.uint8) for _ in range(3))
+    rhs = (q[0] * a.astype(np.int64) + q[1] * b + q[3] * (a.astype(np.int64) * b) + q[4]) % 17
+    c[::3] = rhs[::3]                                                    # every third item satisfies all seven rows
+    c[1::3, :4] = rhs[1::3, :4]                                          # another third fails first at row 4 or later
+    lhs = (rhs + 16 * c.astype(np.int64)) % 17
+    want = np.where((lhs != 0).any(axis=1), (lhs != 0).argmax(axis=1), -1).astype(np.int32)
+    ps.eq("constraints_satisfy_rows", host.constraints_satisfy_rows(q, a, b, c), want)
+    assert (want == -1).sum() > 1000 and (want >= 0).sum() > 1000
+
+
+def test_config2_host_path(host, W):
+    """pb_config2_items with host pointers (the generic chunked pipeline, several chunks) == the device path."""
+    import torch
+    n = (1 << 20) + 12345
+    a, b, x, vals = W.make_poly_items(6, 0, n)
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
+    dev = [g.cpu().numpy() for g in pk.config2_items(*[torch.from_numpy(v).cuda() for v in (a, b, x, vals)])]
+    ps.eq("config2 host path", tuple(pk.config2_items(a, b, x, vals)), tuple(dev))
+    # and the other families through the same pipeline at a size that spans chunks: g1_mul, pairing
+    ai, bi, sc = W.make_group_items(3, 0, 3 * (1 << 20) + 77)
+    P = W.g1_subgroup_table()[ai]
+    want = host.g1_mul(torch.from_numpy(P).cuda(), torch.from_numpy(sc).cuda()).cpu().numpy()
+    ps.eq("g1_mul host path", host.g1_mul(P, sc), want)
