@@ -22,6 +22,17 @@
  *    PB_ERR_NO_DEVICE.
  *  - where the reference would exit() or abort() on an item, the batch entry point writes a per-item
  *    status byte instead (SURVEY.md Appendix B numbering for plonk_prove) and zero-fills the item.
+ *  - per-item bytes are validated on the device.  A polynomial row whose length byte exceeds its stride, a
+ *    coefficient / value / scalar byte above 16 where a field element of F17 is expected, a shift that does not
+ *    fit the output row: none of these is a value any reference path produces (HF is "always kept in range",
+ *    hf.h:11-14; poly_new exits on a bad length, poly.h:29-32).  Such an item is REPORTED and never computed on:
+ *    status[i] = 2 where the entry point has a status array, olen[i] = 0 with a zero row where the result has a
+ *    length (every valid result has len >= 1 there), 0xFF from poly_eval, PB_PROVE_BAD_INPUT from the prover.
+ *    The other items of the batch are unaffected.  (pb_config2_items, the fused fixed-shape entry point, and the
+ *    group / field element-wise kernels do not validate: any byte is memory-safe there and yields a
+ *    deterministic, unspecified value.)
+ *  - `*_dev` entry points that take a context must be called with the context's device current
+ *    (cudaSetDevice); otherwise PB_ERR_ARG.
  */
 #ifndef PLONK_B200_H
 #define PLONK_B200_H

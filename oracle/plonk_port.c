@@ -6,7 +6,7 @@
  * of malloc'd ones, status codes instead of exit()/assert().  Each function cites the reference
  * file:line whose behaviour it restates (paths relative to /root/reference/).
  *
- * Pinning: tests/test_oracle_pinning.py checks this file against (a) every golden vector the
+ * Pinning: tests/test_oracle.py (and the CPU halves of tests/parity_suite.py) check this file against (a) every golden vector the
  * reference's own tests hold, (b) the golden transcript of SURVEY.md
  * Appendix A, and (c) oracle/_ref (the unmodified reference compiled here) on seeded random
  * batches, including the per-item exit paths of Appendix B.  The verifier part is

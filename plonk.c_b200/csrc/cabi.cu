@@ -139,6 +139,17 @@ struct DeviceGuard {
   ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
 };
 
+// `_dev` entry points that take a context launch on the CALLER's current device: it must be the context's (tables, keys and
+// scratch live there); anything else would be a peer access or a fault
+int on_ctx_device(const pb_ctx* ctx) {
+  int cur = -1;
+  CU(cudaGetDevice(&cur));
+  if (cur != ctx->device)
+    return fail(PB_ERR_ARG, "plonk_b200: the context lives on device " + std::to_string(ctx->device) + " but the current device is " + std::to_string(cur) +
+                                " (call cudaSetDevice before a *_dev entry point)");
+  return PB_OK;
+}
+
 // device scratch of (n + 4) words for `stream`: [0] = counter, [4..] = list
 int scratch_for(const pb_ctx* cctx, cudaStream_t st, size_t n, uint32_t** out) {
   pb_ctx* c = const_cast<pb_ctx*>(cctx);
@@ -521,6 +532,7 @@ int pb_poly_lagrange(const uint8_t* xs, const uint8_t* ys, size_t len, uint8_t* 
 int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out, uint8_t* olen, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && vals && out && olen);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(aligned16(vals) && aligned16(out));
   if (n == 0) return PB_OK;
   interpolate_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, vals, out, olen, n);
@@ -539,6 +551,7 @@ int pb_config2_items_dev(const pb_ctx* ctx, const uint8_t* a, const uint8_t* b, 
                          uint8_t* interp_len, size_t n, void* stream) {
   if (n == 0) return PB_OK;
   ARG(ctx && a && b && x && vals && prod && prod_len && quot && quot_len && rem && rem_len && evals && interp && interp_len);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(aligned16(a) && aligned16(b) && aligned16(vals) && aligned16(prod) && aligned16(quot) && aligned16(rem) && aligned16(interp));
   // full groups of PF4_ITEMS items: four items per thread, whole-word accesses (poly_fast.cuh); the ragged tail: one item per thread
   const size_t blocks4 = (aligned16(x) && aligned16(prod_len) && aligned16(quot_len) && aligned16(rem_len) && aligned16(evals) && aligned16(interp_len))
@@ -706,6 +719,7 @@ int pb_srs_eval_at_s_dev(const pb_ctx* ctx, const uint8_t* polys, const uint8_t*
                          size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && polys && plen && out && status && sp >= 1 && sp <= PB_POLY_MAX);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   if (n == 0) return PB_OK;
   commit_kernel<<<blocks_for(n, BLOCK), BLOCK, ctx->srs_len * 17 * sizeof(uint32_t), S(stream)>>>(ctx->d_srs_table, ctx->srs_len, polys, plen,
                                                                                                  (int)sp, out, status, n);
@@ -1066,6 +1080,7 @@ int pb_ctx_srs_table(const pb_ctx* ctx, uint8_t* out) { ARG(ctx && out); memcpy(
 int pb_constraints_satisfy_dev(const pb_ctx* ctx, const uint8_t* witness, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && out);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   if (n == 0) return PB_OK;
   satisfy_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, witness, out, n);
   LAUNCH_CHECK("satisfy_kernel");
@@ -1147,6 +1162,7 @@ int pb_plonk_prove_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t*
                        uint8_t* status, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && chal && proofs && status);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status));
   if (n == 0) return PB_OK;
   return launch_prove(ctx, witness, rnd, chal, proofs, status, n, S(stream), nullptr, nullptr, nullptr);
@@ -1155,6 +1171,7 @@ int pb_plonk_verify_dev(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t*
                         size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal && u && verdict);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && aligned16(chal) && (!gt || aligned16(gt)));
   if (n == 0) return PB_OK;
@@ -1164,6 +1181,7 @@ int pb_plonk_verify_completed_dev(const pb_ctx* ctx, const uint8_t* proofs, cons
                                   uint8_t* verdict, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal && u && status && verdict);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && aligned16(chal));
   ARG(n < 0xFFFFFFFFull);
@@ -1186,6 +1204,7 @@ static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uin
                             const uint8_t* packed = nullptr) {
   ARG(verdict);
   ARG(ctx && ctx->vk_valid);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG((packed || (witness && rnd)) && proofs && status);
   ARG((chal == nullptr) == (u == nullptr));
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(chal) && aligned16(proofs) && aligned16(status) && aligned16(packed));
@@ -1215,12 +1234,14 @@ int pb_plonk_prove_fs_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8
                           uint8_t* chal_out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && witness && rnd && proofs && status);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(aligned16(witness) && aligned16(rnd) && aligned16(proofs) && aligned16(status));
   return launch_prove(ctx, witness, rnd, nullptr, proofs, status, n, S(stream), nullptr, nullptr, nullptr, chal_out);
 }
 int pb_plonk_verify_fs_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* verdict, uint8_t* gt, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && verdict);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(ctx->vk_valid);
   ARG(aligned16(proofs) && (!gt || aligned16(gt)));
   return launch_verify(ctx, proofs, nullptr, nullptr, nullptr, nullptr, nullptr, verdict, gt, n, S(stream));
@@ -1233,6 +1254,7 @@ int pb_plonk_prove_verify_fs_dev(const pb_ctx* ctx, const uint8_t* witness, cons
 int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal6, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(ctx && proofs && chal6);
+  { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   fs_challenges_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc.fs_seed, proofs, chal6, n);
   LAUNCH_CHECK("fs_challenges_kernel");
   return PB_OK;

@@ -77,9 +77,15 @@ pb_ctx* ctx_for(const uint8_t circuit[PB_CIRCUIT_BYTES], const SRS* srs) {
   uint8_t g2[4] = {srs->g2_1.x.value, srs->g2_1.y.value, srs->g2_s.x.value, srs->g2_s.y.value};
   key.append(reinterpret_cast<const char*>(g1s.data()), g1s.size());
   key.append(reinterpret_cast<const char*>(g2), 4);
-  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  // the caller holds g_ctx_mu (for the whole plonk_prove call: the context must not be evicted under it)
   auto it = g_ctx.find(key);
   if (it != g_ctx.end()) return it->second;
+  // bounded: a program that proves against many (circuit, SRS) pairs does not accumulate contexts (each holds ~50 MB of
+  // tables); drop-in proofs are serialised by g_ctx_mu, so no context is in use when the cache is emptied
+  if (g_ctx.size() >= 8) {
+    for (auto& kv : g_ctx) pb_ctx_destroy(kv.second);
+    g_ctx.clear();
+  }
   pb_ctx* c = nullptr;
   int dev = 0;
   gpu(pb_ctx_create(&c, dev, circuit, g1s.data(), (uint32_t)srs->len, g2));
@@ -491,6 +497,7 @@ PROOF plonk_prove(PLONK* pk, CONSTRAINTS* cs, ASSIGNMENTS* as, CHALLENGE* ch, HF
   for (int s = 0; s < 5; s++) for (int i = 0; i < 4; i++) circuit[4 * s + i] = sel[s][i].value;
   const COPY_OF* cp[3] = {cs->c_a, cs->c_b, cs->c_c};
   for (int s = 0; s < 3; s++) for (int i = 0; i < 4; i++) { circuit[20 + 8 * s + i] = (uint8_t)cp[s][i].type; circuit[24 + 8 * s + i] = (uint8_t)cp[s][i].index; }
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
   pb_ctx* ctx = ctx_for(circuit, &pk->srs);
   uint8_t wit[12], proof[PB_PROOF_BYTES], status = 0;
   for (int i = 0; i < 4; i++) { wit[i] = as->a[i].value; wit[4 + i] = as->b[i].value; wit[8 + i] = as->c[i].value; }

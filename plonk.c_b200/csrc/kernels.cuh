@@ -93,9 +93,9 @@ PB_D uint32_t field_apply(const FieldTables& ft, int op, uint32_t a, uint32_t b)
       case 0: return add17(a, b);
       case 1: return sub17(a, b);
       case 2: return mul17(a, b);
-      case 3: return mul17(a, inv17(ft, b));
+      case 3: return mul17(a, inv17(ft, b & 31u));   // bytes outside [0,17) are not field elements: the index is kept inside the table
       case 4: return neg17(a);
-      case 5: return inv17(ft, a);
+      case 5: return inv17(ft, a & 31u);
       default: return pow17(a, b);
     }
   } else {
@@ -186,17 +186,30 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_new_kernel(const long long*
 
 // ------------------------------------------------------------------ family (2), generic shapes
 // Polynomials in per-thread local arrays; dynamic lengths.  (Fixed-shape fast paths: poly_fast.cuh.)
+// Inputs are validated per item: a length above the row stride, a coefficient byte above 16, a shift that does not fit the
+// output row are not values any reference path produces (HF is "always kept in range", hf.h:11-14; poly_new exits on a bad
+// length, poly.h:29-32).  Such an item is REPORTED, never computed on: olen[i] = 0 with a zero row where the result has a
+// length (every valid result has len >= 1 there), status[i] = 2 where a status array exists, 0xFF for poly_eval.
+constexpr uint8_t ITEM_INVALID = 2;
 struct LPoly { uint8_t c[2 * POLY_MAX]; int len; };
 
-PB_D void lp_load(LPoly& p, const uint8_t* row, int len) {      // poly_new: trim while len > 1 (poly.h:20-24)
-  while (len > 1 && row[len - 1] == 0) len--;
+// poly_new: trim while len > 1 (poly.h:20-24).  false = the row is not a polynomial over F17 of at most `stride` coefficients
+PB_D bool lp_load(LPoly& p, const uint8_t* row, int len, int stride) {
+  if (len > stride) { p.len = 0; return false; }
+  bool ok = true;
+  for (int i = 0; i < len; i++) { p.c[i] = row[i]; ok &= row[i] <= 16; }
+  while (len > 1 && p.c[len - 1] == 0) len--;
   p.len = len;
-  for (int i = 0; i < len; i++) p.c[i] = row[i];
+  return ok;
 }
 PB_D void lp_trim(LPoly& p) { while (p.len > 1 && p.c[p.len - 1] == 0) p.len--; }
 PB_D void lp_store(const LPoly& p, uint8_t* row, int stride, uint8_t* len) {
   for (int i = 0; i < stride; i++) row[i] = i < p.len ? p.c[i] : 0;
   *len = (uint8_t)p.len;
+}
+PB_D void lp_invalid(uint8_t* row, int stride, uint8_t* len) {
+  for (int i = 0; i < stride; i++) row[i] = 0;
+  *len = 0;
 }
 
 __global__ void __launch_bounds__(BLOCK_LIGHT) poly_binop_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ alen, int sa,
@@ -205,8 +218,9 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_binop_kernel(int op, const u
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   LPoly pa, pb, r;
-  lp_load(pa, a + i * sa, alen[i]);
-  lp_load(pb, b + i * sb, blen[i]);
+  bool ok = lp_load(pa, a + i * sa, alen[i], sa);
+  ok &= lp_load(pb, b + i * sb, blen[i], sb);
+  if (!ok || pa.len == 0 || pb.len == 0) { lp_invalid(out + i * so, so, olen + i); return; }
   if (op == 2) {                                                 // poly_mul, poly.h:106-122
     r.len = pa.len + pb.len - 1;
     for (int k = 0; k < r.len; k++) {
@@ -237,12 +251,15 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_divide_kernel(const uint8_t*
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   LPoly pn, pd, q;
-  lp_load(pn, num + i * sn, nlen[i]);
-  lp_load(pd, den + i * sd, dlen[i]);
+  bool ok = lp_load(pn, num + i * sn, nlen[i], sn);
+  ok &= lp_load(pd, den + i * sd, dlen[i], sd);
   bool zero_den = true;                                          // poly_is_zero, poly.h:55-64
   for (int k = 0; k < pd.len; k++) zero_den &= pd.c[k] == 0;
-  if (zero_den) {                                                // "Division by zero polynomial", poly.h:125-128
-    status[i] = 1;
+  // the quotient / remainder rows must hold what the division produces (the natural strides sn - sd + 1 and sd - 1 always do)
+  const int need_q = pn.len >= pd.len ? pn.len - pd.len + 1 : 1, need_r = pd.len - 1 < pn.len ? pd.len - 1 : pn.len;
+  if (ok && !zero_den && (need_q > sq || need_r > sr)) ok = false;
+  if (!ok || zero_den) {                                         // "Division by zero polynomial", poly.h:125-128 -> 1; not a polynomial -> 2
+    status[i] = ok ? 1 : ITEM_INVALID;
     for (int k = 0; k < sq; k++) quot[i * sq + k] = 0;
     for (int k = 0; k < sr; k++) rem[i * sr + k] = 0;
     qlen[i] = 0; rlen[i] = 0;
@@ -274,8 +291,10 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_eval_kernel(const uint8_t* _
   if (i >= n) return;
   const uint8_t* row = p + i * sp;
   uint32_t y = 0, xv = x[i];
-  for (int k = (int)plen[i] - 1; k >= 0; k--) y = red17(y * xv + row[k]);   // Horner, poly.h:265-272
-  out[i] = (uint8_t)y;
+  const int len = plen[i];
+  bool ok = len <= sp && xv <= 16u;
+  for (int k = (ok ? len : 0) - 1; k >= 0; k--) { ok &= row[k] <= 16; y = red17(y * xv + (row[k] & 31u)); }   // Horner, poly.h:265-272
+  out[i] = ok ? (uint8_t)y : 0xFF;
 }
 
 __global__ void __launch_bounds__(BLOCK_LIGHT) poly_unop_kernel(int op, const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen, int sp,
@@ -284,8 +303,13 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_unop_kernel(int op, const ui
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   LPoly a, r;
-  lp_load(a, p + i * sp, plen[i]);
+  bool ok = lp_load(a, p + i * sp, plen[i], sp) && a.len >= 1;
   uint32_t kv = k ? k[i] : 0u;
+  if ((op == 0 || op == 3) && kv > 16u) ok = false;             // the scalar of poly_scale / poly_add_hf is a field element
+  bool z = true;
+  for (int j = 0; j < a.len; j++) z &= a.c[j] == 0;
+  if (op == 2 && !z && a.len + (int)kv > so) ok = false;        // the shifted polynomial must fit the output row
+  if (!ok) { lp_invalid(out + i * so, so, olen + i); return; }
   if (op == 0) {                                                 // poly_scale, poly.h:179-197: scalar 0 -> [0]
     if (kv == 0) { r.len = 1; r.c[0] = 0; }
     else { r.len = a.len; for (int j = 0; j < a.len; j++) r.c[j] = (uint8_t)mul17(a.c[j], kv); lp_trim(r); }
@@ -294,8 +318,6 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_unop_kernel(int op, const ui
     for (int j = 0; j < a.len; j++) r.c[j] = (uint8_t)neg17(a.c[j]);
     lp_trim(r);
   } else if (op == 2) {                                          // poly_shift, poly.h:199-216: zero stays [0]
-    bool z = true;
-    for (int j = 0; j < a.len; j++) z &= a.c[j] == 0;
     if (z) { r.len = 1; r.c[0] = 0; }
     else {
       r.len = a.len + (int)kv;
@@ -316,10 +338,10 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_slice_kernel(const uint8_t* 
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   LPoly a, r;
-  lp_load(a, p + i * sp, plen[i]);
+  const bool ok = lp_load(a, p + i * sp, plen[i], sp);
   int s = start[i], e = end[i];
-  if (s >= e || e > a.len) {                                     // "Invalid slice indices", poly.h:219-222
-    status[i] = 1; olen[i] = 0;
+  if (!ok || s >= e || e > a.len) {                              // "Invalid slice indices", poly.h:219-222 -> 1; not a polynomial -> 2
+    status[i] = ok ? 1 : ITEM_INVALID; olen[i] = 0;
     for (int j = 0; j < so; j++) out[i * so + j] = 0;
     return;
   }
@@ -343,6 +365,13 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) poly_lagrange_kernel(const uint8_
   const uint8_t* y = ys + i * len;
   uint8_t l[17], lj[17], t[17];
   for (int k = 0; k <= len; k++) l[k] = 0;
+  bool bytes_ok = true;
+  for (int k = 0; k < len; k++) bytes_ok &= x[k] <= 16 && y[k] <= 16;
+  if (!bytes_ok) {                                               // not field elements: reported, not computed on
+    status[i] = ITEM_INVALID; olen[i] = 0;
+    for (int k = 0; k < so; k++) out[i * so + k] = 0;
+    return;
+  }
   bool dup = false;
   for (int j = 0; j < len && !dup; j++) {
     int ljn = 1;
@@ -381,9 +410,10 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) interpolate_kernel(const __grid_c
   if (i >= n) return;
   uint32_t w = reinterpret_cast<const uint32_t*>(vals)[i];
   uint32_t v[4] = {w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24}, r[4];
+  const bool ok = v[0] <= 16u && v[1] <= 16u && v[2] <= 16u && v[3] <= 16u;
   interpolate(cc, v, r);
-  reinterpret_cast<uint32_t*>(out)[i] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
-  olen[i] = (uint8_t)canon_len(r);
+  reinterpret_cast<uint32_t*>(out)[i] = ok ? r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24) : 0u;
+  olen[i] = ok ? (uint8_t)canon_len(r) : 0;                      // a value byte above 16 is not a field element: reported as length 0
 }
 
 // matrix_mul, matrix.h:81-98; dims <= 8
@@ -433,7 +463,7 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) matrix_rref_kernel(uint8_t* __res
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint8_t M[8 * 16];
-  for (int k = 0; k < rows * cols; k++) M[k] = a[i * rows * cols + k];
+  for (int k = 0; k < rows * cols; k++) M[k] = (uint8_t)red17(a[i * rows * cols + k]);   // entries are reduced on load: table indices stay in range
   rref(ft, M, rows, cols);
   for (int k = 0; k < rows * cols; k++) a[i * rows * cols + k] = M[k];
 }
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) matrix_inv_kernel(const uint8_t* 
   uint8_t M[8 * 16];
   const int rows = dim, cols = 2 * dim;
   for (int r = 0; r < rows; r++)
-    for (int c = 0; c < cols; c++) M[r * cols + c] = c < dim ? a[i * dim * dim + r * dim + c] : (c - dim == r ? 1 : 0);
+    for (int c = 0; c < cols; c++) M[r * cols + c] = c < dim ? (uint8_t)red17(a[i * dim * dim + r * dim + c]) : (c - dim == r ? 1 : 0);
   rref(ft, M, rows, cols);
   for (int r = 0; r < rows; r++)
     for (int c = 0; c < dim; c++) out[i * dim * dim + r * dim + c] = M[r * cols + dim + c];
@@ -533,6 +563,13 @@ __global__ void __launch_bounds__(BLOCK) commit_kernel(const uint32_t* __restric
   if (i >= n) return;
   const uint8_t* row = polys + i * sp;
   int len = plen[i];
+  bool ok = len <= sp;
+  for (int k = 0; k < (ok ? len : 0); k++) ok &= row[k] <= 16;   // a coefficient byte above 16 would index past its table row
+  if (!ok) {
+    status[i] = ITEM_INVALID;
+    out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0;
+    return;
+  }
   while (len > 1 && row[len - 1] == 0) len--;                   // poly_new trims first
   if ((uint32_t)len > srs_len) {                                 // "exceeds SRS size", srs.h:54-57
     status[i] = 1;
@@ -557,7 +594,14 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) commit_raw_kernel(const uint8_t* 
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* row = polys + i * sp;
-  int len = plen[i] > sp ? sp : plen[i];
+  int len = plen[i];
+  bool ok = len <= sp;
+  for (int k = 0; k < (ok ? len : 0); k++) ok &= row[k] <= 16;
+  if (!ok) {                                                     // not a polynomial over F17: reported, not computed on
+    status[i] = ITEM_INVALID;
+    out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0;
+    return;
+  }
   // trim: the row is passed through poly_new first, as in the other batch entry points; otherwise len is used as given -- the
   // reference's loop runs over POLY.len terms, and a trailing zero term is NOT a no-op when the accumulator is an "identity with
   // coordinates" (g1_add returns *b when a is infinite, g1.h:60)

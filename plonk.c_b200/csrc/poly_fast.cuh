@@ -33,10 +33,23 @@ PB_D void load_record(uint32_t (&w)[(ITEM + 3) / 4], const uint8_t* __restrict__
 #pragma unroll
   for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
 }
+// The first `len` coefficient bytes of an N-byte record: the words are masked by length (bytes at positions >= len become 0,
+// as zero padding), tested for bytes above 16 -- b > 16  <=>  bit 7 of ((b & 0x7F) + 0x6F) | b -- and unpacked.  Returns
+// false when the row is not a polynomial over F17 of at most N coefficients (same rule as the generic kernels' lp_load).
 template <int N>
-PB_D void unpack_masked(uint32_t (&r)[N], const uint32_t (&w)[(N + 3) / 4], uint32_t len) {
+PB_D bool unpack_masked(uint32_t (&r)[N], const uint32_t (&w)[(N + 3) / 4], uint32_t len) {
+  constexpr int NW = (N + 3) / 4;
+  uint32_t bad = 0u, m[NW];
 #pragma unroll
-  for (int i = 0; i < N; i++) r[i] = (uint32_t)i < len ? ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) : 0u;
+  for (int k = 0; k < NW; k++) {
+    const int left = (int)len - 4 * k;                                      // valid bytes in this word
+    const uint32_t mask = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : (1u << (8 * left)) - 1u;
+    m[k] = w[k] & mask;
+    bad |= (((m[k] & 0x7F7F7F7Fu) + 0x6F6F6F6Fu) | m[k]) & 0x80808080u;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = (m[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+  return bad == 0u && len <= (uint32_t)N;
 }
 // the block's slice of an output array with ITEM bytes per record: shared memory -> global, 128-bit stores
 template <int ITEM>
@@ -73,15 +86,18 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_mul_fast_kernel(const uint8_t* 
     uint32_t wa[(SA + 3) / 4], wb[(SB + 3) / 4], ra[SA], rb[SB], ro[SO];
     load_record<SA>(wa, a, t, n);
     load_record<SB>(wb, b, t, n);
-    unpack_masked(ra, wa, alen[t]);
-    unpack_masked(rb, wb, blen[t]);
+    const uint32_t la = alen[t], lb = blen[t];
+    bool ok = unpack_masked(ra, wa, la);
+    ok &= unpack_masked(rb, wb, lb);
+    ok &= la != 0u && lb != 0u;
 #pragma unroll
     for (int k = 0; k < SO; k++) ro[k] = 0u;
     mul_acc<SA, SB>(ro, ra, rb);            // raw < min(SA,SB) * 2^8
 #pragma unroll
-    for (int k = 0; k < SO; k++) { ro[k] = red17(ro[k]); so[tid * SO + k] = (uint8_t)ro[k]; }
-    // F17[x] has no zero divisors: trimming the product gives its canonical length (1 for a zero product)
-    olen[t] = (uint8_t)canon_len(ro);
+    for (int k = 0; k < SO; k++) { ro[k] = red17(ro[k]); so[tid * SO + k] = ok ? (uint8_t)ro[k] : 0; }
+    // F17[x] has no zero divisors: trimming the product gives its canonical length (1 for a zero product);
+    // an invalid row (kernels.cuh: ITEM_INVALID rule) is reported as length 0
+    olen[t] = ok ? (uint8_t)canon_len(ro) : 0;
   }
   __syncthreads();
   store_slice<SO>(out, so, first, n);
@@ -107,13 +123,18 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
     load_record<SN>(wn, num, t, n);
     load_record<SD>(wd, den, t, n);
     const uint32_t nlen0 = nlen[t], dlen0 = dlen[t];
-    unpack_masked(r, wn, nlen0);
-    unpack_masked(d, wd, dlen0);
+    bool ok = unpack_masked(r, wn, nlen0);
+    ok &= unpack_masked(d, wd, dlen0);
     const uint32_t nl = nlen0 == 0 ? 0u : canon_len(r);      // poly_new trims the inputs first
     const uint32_t dl = dlen0 == 0 ? 0u : canon_len(d);
     bool zero_den = true;
 #pragma unroll
     for (int j = 0; j < SD; j++) zero_den &= d[j] == 0u;
+    zero_den |= !ok;                                             // an invalid row takes the zero-output path; its status is ITEM_INVALID
+    if (!ok) {
+#pragma unroll
+      for (int j = 0; j < SD; j++) d[j] = 0u;                    // keep the inverse-table index in range
+    }
     // top-aligned divisor: dt[j] = d[dl-1-j] (dt[0] is the leading coefficient)
     uint32_t dt[SD];
 #pragma unroll
@@ -162,7 +183,7 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
     for (int k = 0; k < SR; k++) sr[tid * SR + k] = (!zero_den && (uint32_t)k < rl) ? (uint8_t)r[k] : 0;
     qlen[t] = zero_den ? 0 : (uint8_t)ql;
     rlen[t] = zero_den ? 0 : (uint8_t)rl;
-    status[t] = zero_den ? 1 : 0;                                // "Division by zero polynomial", poly.h:125-128
+    status[t] = !ok ? ITEM_INVALID : zero_den ? 1 : 0;            // "Division by zero polynomial", poly.h:125-128
   }
   __syncthreads();
   store_slice<SQ>(quot, sq, first, n);
@@ -178,11 +199,11 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_eval_fast_kernel(const uint8_t*
   uint32_t w[(SP + 3) / 4], c[SP];
   load_record<SP>(w, p, t, n);
   const uint32_t len = plen[t], xv = x[t];
-  unpack_masked(c, w, len);
+  const bool ok = unpack_masked(c, w, len) && xv <= 16u;
   uint32_t y = 0u;
 #pragma unroll
-  for (int k = SP - 1; k >= 0; k--) y = red17(y * xv + c[k]);    // Horner from the top; masked coefficients are 0 and y stays 0 above len
-  out[t] = (uint8_t)y;
+  for (int k = SP - 1; k >= 0; k--) y = red17(y * (xv & 31u) + c[k]);   // Horner from the top; masked coefficients are 0 and y stays 0 above len
+  out[t] = ok ? (uint8_t)y : 0xFF;
 }
 
 // BASELINE config 2 as ONE launch.  SURVEY.md section 8(d) defines the unit as {A[6], B[6], x, vals[4]} (17 bytes in) ->

@@ -514,3 +514,100 @@ def test_config2_host_path(host, W):
     P = W.g1_subgroup_table()[ai]
     want = host.g1_mul(torch.from_numpy(P).cuda(), torch.from_numpy(sc).cuda()).cpu().numpy()
     ps.eq("g1_mul host path", host.g1_mul(P, sc), want)
+
+
+@pytest.mark.parametrize("shape", [(8, 5), (6, 6), (11, 6)])      # a generic shape and two register-resident fast shapes
+def test_adversarial_bytes_in_poly_entry_points(host, oracle, W, shape):
+    """per-item bytes the ABI cannot trust.  A length above the row stride, a coefficient byte above 16, a shift that
+    does not fit the output row are REPORTED (olen 0 / status 2 / 0xFF) -- never computed on, never read or written out of
+    bounds -- and the valid items of the same batch are untouched.  Device and host paths, generic and fast kernels."""
+    import torch
+    import util
+    sa, sb = shape
+    n = 4099
+    a, al, b, bl = util.poly_cases(n, sa, sb, seed=91)
+    bad_len = np.arange(0, n, 7)
+    bad_coef = np.arange(3, n, 11)
+    bad_zero = np.arange(5, n, 13)
+    a2, al2, b2, bl2 = a.copy(), al.copy(), b.copy(), bl.copy()
+    al2[bad_len] = 200                                              # far above the stride (and above PB_POLY_MAX)
+    b2[bad_coef, 0] = 17
+    bl2[bad_coef] = np.maximum(bl2[bad_coef], 1)
+    al2[bad_zero] = 0
+    bad = np.zeros(n, bool); bad[bad_len] = True; bad[bad_coef] = True; bad[bad_zero] = True
+    for op in (host.POLY_MUL, host.POLY_ADD, host.POLY_SUB):
+        so = sa + sb - 1 if op == host.POLY_MUL else max(sa, sb)
+        want, wl = oracle.poly_binop(op, a, al, b, bl, so)
+        for path in ("host", "device"):
+            args = (a2, al2, b2, bl2) if path == "host" else tuple(torch.from_numpy(v).cuda() for v in (a2, al2, b2, bl2))
+            got, gl = host.poly_binop(op, *args, so)
+            got, gl = (np.asarray(got.cpu()) if path == "device" else got), (np.asarray(gl.cpu()) if path == "device" else gl)
+            assert (gl[bad] == 0).all() and not got[bad].any(), (op, path)
+            ps.eq(f"binop {op} {path}: valid items", (got[~bad], gl[~bad]), (want[~bad], wl[~bad]))
+    # poly_eval: 0xFF for an invalid row or an x byte above 16
+    x = np.random.default_rng(5).integers(0, 17, n, dtype=np.uint8)
+    x2 = x.copy(); x2[bad_zero] = 99
+    a3 = a.copy(); a3[bad_coef, 0] = 255
+    al3 = np.maximum(al, 1); al3[bad_len] = sa + 1
+    got = host.poly_eval(torch.from_numpy(a3).cuda(), torch.from_numpy(al3).cuda(), torch.from_numpy(x2).cuda()).cpu().numpy()
+    assert (got[bad] == 0xFF).all()
+    ps.eq("eval: valid items", got[~bad], oracle.poly_eval(a, np.maximum(al, 1), x)[~bad])
+    # poly_divide: status 2
+    al_div = al.copy(); al_div[bad_len] = 200                       # (a zero numerator length is a valid input of poly_divide)
+    quot, ql, rem, rl, st = host.poly_divide(torch.from_numpy(a2).cuda(), torch.from_numpy(al_div).cuda(),
+                                             torch.from_numpy(b2).cuda(), torch.from_numpy(bl2).cuda())
+    st = st.cpu().numpy()
+    assert (st[bad_len] == 2).all() and (st[bad_coef] == 2).all() and not quot.cpu().numpy()[st == 2].any() and not rem.cpu().numpy()[st == 2].any()
+    wq, wql, wr, wrl, wst = oracle.poly_divide(a, al, b, bl, sa, max(sb - 1, 1))
+    ok = ~(np.isin(np.arange(n), bad_len) | np.isin(np.arange(n), bad_coef))
+    ps.eq("divide: valid items", (quot.cpu().numpy()[ok], ql.cpu().numpy()[ok], rem.cpu().numpy()[ok], rl.cpu().numpy()[ok], st[ok]),
+          (wq[ok], wql[ok], wr[ok], wrl[ok], wst[ok]))
+
+
+def test_adversarial_bytes_unop_slice_lagrange_commit(host, oracle, W):
+    import torch
+    import util
+    rng = np.random.default_rng(92)
+    n = 3001
+    p, pl, _, _ = util.poly_cases(n, 10, 3, seed=93)
+    k = rng.integers(0, 17, n, dtype=np.uint8)
+    # shift: 255 cannot fit any row; a shift that exactly fits is fine
+    kk = k.copy(); kk[::5] = 255
+    out, ol = host.poly_shift(torch.from_numpy(p).cuda(), torch.from_numpy(pl).cuda(), torch.from_numpy(kk).cuda(), 10 + 16)
+    out, ol = out.cpu().numpy(), ol.cpu().numpy()
+    want, wl = oracle.poly_unop(host.POLY_SHIFT, p, pl, k, 26)
+    is_zero = np.array([not p[i, :pl[i]].any() for i in range(n)])
+    flagged = (np.arange(n) % 5 == 0) & ~is_zero                     # the zero polynomial shifts to [0] whatever the amount (poly.h:199-216)
+    assert (ol[flagged] == 0).all() and not out[flagged].any()
+    ps.eq("shift: valid items", (out[~flagged & (np.arange(n) % 5 != 0)], ol[~flagged & (np.arange(n) % 5 != 0)]),
+          (want[~flagged & (np.arange(n) % 5 != 0)], wl[~flagged & (np.arange(n) % 5 != 0)]))
+    # scale by a byte that is not a field element; a length above the stride
+    ks = k.copy(); ks[::4] = 40
+    pl2 = pl.copy(); pl2[1::4] = 11
+    out, ol = host.poly_scale(torch.from_numpy(p).cuda(), torch.from_numpy(pl2).cuda(), torch.from_numpy(ks).cuda())
+    ol = ol.cpu().numpy()
+    assert (ol[::4] == 0).all() and (ol[1::4] == 0).all() and (ol[2::4] >= 1).all()
+    # slice / lagrange: status 2
+    _, _, st = host.poly_slice(torch.from_numpy(p).cuda(), torch.from_numpy(pl2).cuda(), torch.from_numpy(np.zeros(n, np.uint8)).cuda(),
+                               torch.from_numpy(np.ones(n, np.uint8)).cuda())
+    assert (st.cpu().numpy()[1::4] == 2).all() and (st.cpu().numpy()[2::4] == 0).all()
+    xs = np.tile(np.arange(4, dtype=np.uint8), (n, 1)); ys = rng.integers(0, 17, (n, 4), dtype=np.uint8)
+    ys[::3, 2] = 17
+    _, _, st = host.poly_lagrange(torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda())
+    assert (st.cpu().numpy()[::3] == 2).all() and (st.cpu().numpy()[1::3] == 0).all()
+    # interpolate_at_h: length 0 for a value byte above 16
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    vals = rng.integers(0, 17, (n, 4), dtype=np.uint8); vals[::6, 1] = 250
+    o, l = pk.interpolate_at_h(torch.from_numpy(vals).cuda())
+    assert (l.cpu().numpy()[::6] == 0).all() and not o.cpu().numpy()[::6].any() and (l.cpu().numpy()[1::6] >= 1).all()
+    # srs_eval_at_s (table kernel and raw kernel): a coefficient byte that would index past its table row, a length above the stride
+    polys = rng.integers(0, 17, (n, 9), dtype=np.uint8); plen = rng.integers(1, 10, n).astype(np.uint8)
+    want, wst = pk.srs_eval_at_s(polys, plen)
+    polys2, plen2 = polys.copy(), plen.copy()
+    polys2[::7, 0] = 200; plen2[3::7] = 77
+    for fn in (lambda: pk.srs_eval_at_s(torch.from_numpy(polys2).cuda(), torch.from_numpy(plen2).cuda()),
+               lambda: host.srs_eval_at_s_raw(W.generator_srs(9)[0], torch.from_numpy(polys2).cuda(), torch.from_numpy(plen2).cuda())):
+        got, st = (t.cpu().numpy() for t in fn())
+        assert (st[::7] == 2).all() and (st[3::7] == 2).all() and not got[st == 2].any()
+        okm = st != 2
+        ps.eq("commit: valid items", (got[okm], st[okm]), (want[okm], wst[okm]))
