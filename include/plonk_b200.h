@@ -133,6 +133,12 @@ int pb_poly_divide_dev(const uint8_t *num, const uint8_t *nlen, size_t sn, const
 int pb_poly_divide(const uint8_t *num, const uint8_t *nlen, size_t sn, const uint8_t *den, const uint8_t *dlen, size_t sd,
                    uint8_t *quot, uint8_t *qlen, size_t sq, uint8_t *rem, uint8_t *rlen, size_t sr,
                    uint8_t *status, size_t n);
+/* poly_divide by the context's Z_H = x^4 - 1 (the prover's own call, plonk.h:505: poly_divide(&t_numer, &plonk->z_h_x, ...)):
+ * numerator stride sn = 11 or 22; quot[n][sn - 4], rem[n][4]; byte-identical to pb_poly_divide with that divisor */
+int pb_poly_divide_zh_dev(const pb_ctx *ctx, const uint8_t *num, const uint8_t *nlen, size_t sn, uint8_t *quot, uint8_t *qlen,
+                          uint8_t *rem, uint8_t *rlen, uint8_t *status, size_t n, void *stream);
+int pb_poly_divide_zh(const pb_ctx *ctx, const uint8_t *num, const uint8_t *nlen, size_t sn, uint8_t *quot, uint8_t *qlen,
+                      uint8_t *rem, uint8_t *rlen, uint8_t *status, size_t n);
 /* poly_eval (poly.h:265-272) */
 int pb_poly_eval_dev(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *x, uint8_t *out, size_t n, void *stream);
 int pb_poly_eval(const uint8_t *p, const uint8_t *plen, size_t sp, const uint8_t *x, uint8_t *out, size_t n);

@@ -395,9 +395,13 @@ int pb_poly_binop_dev(int op, const uint8_t* a, const uint8_t* alen, size_t sa, 
   // register-resident fast path for the shapes of BASELINE config 2 and of the prover (natural output stride, aligned)
   const bool al = aligned16(a) && aligned16(b) && aligned16(out);
   if (op == PB_POLY_MUL && al && so == sa + sb - 1) {
+    // full groups of PF4_ITEMS items: four items per thread (poly_fast.cuh); the ragged tail: one item per thread
+    const size_t m4 = (aligned16(alen) && aligned16(blen) && aligned16(olen)) ? n / PF4_ITEMS * PF4_ITEMS : 0;
 #define PB_MUL_FAST(A_, B_)                                                                                         \
     if (sa == A_ && sb == B_) {                                                                                     \
-      poly_mul_fast_kernel<A_, B_><<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(a, alen, b, blen, out, olen, n); \
+      if (m4) poly_mul_fast4_kernel<A_, B_><<<(unsigned)(m4 / PF4_ITEMS), PF4_BLOCK, 0, S(stream)>>>(a, alen, b, blen, out, olen); \
+      if (n > m4) poly_mul_fast_kernel<A_, B_><<<blocks_for(n - m4, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(           \
+          a + m4 * A_, alen + m4, b + m4 * B_, blen + m4, out + m4 * (A_ + B_ - 1), olen + m4, n - m4);              \
       LAUNCH_CHECK("poly_mul_fast_kernel");                                                                         \
       return PB_OK;                                                                                                 \
     }
@@ -449,14 +453,46 @@ int pb_poly_divide(const uint8_t* num, const uint8_t* nlen, size_t sn, const uin
                  return pb_poly_divide_dev(di[0], di[1], sn, di[2], di[3], sd, dq[0], dq[1], sq, dq[2], dq[3], sr, dq[4], m, st); });
 }
 
+// poly_divide(p, Z_H) against the context's Z_H = x^4 - 1 (plonk.h:505): numerators of stride 11 (config 2: a product of two
+// 6-coefficient polynomials) or 22 (the prover's t_numer); quotient sn - 4 columns, remainder 4 columns
+int pb_poly_divide_zh_dev(const pb_ctx* ctx, const uint8_t* num, const uint8_t* nlen, size_t sn, uint8_t* quot, uint8_t* qlen, uint8_t* rem,
+                          uint8_t* rlen, uint8_t* status, size_t n, void* stream) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && num && nlen && quot && qlen && rem && rlen && status);
+  ARG(sn == 11 || sn == 22);
+  ARG(aligned16(num) && aligned16(quot) && aligned16(rem));
+  const size_t m4 = (aligned16(nlen) && aligned16(qlen) && aligned16(rlen) && aligned16(status)) ? n / PF4_ITEMS * PF4_ITEMS : 0;
+#define PB_DIVZH(N_)                                                                                                                          \
+  if (sn == N_) {                                                                                                                             \
+    if (m4) poly_divide_zh4_kernel<N_><<<(unsigned)(m4 / PF4_ITEMS), PF4_BLOCK, 0, S(stream)>>>(num, nlen, quot, qlen, rem, rlen, status);   \
+    if (n > m4) poly_divide_zh_kernel<N_><<<blocks_for(n - m4, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(                                         \
+        num + m4 * N_, nlen + m4, quot + m4 * (N_ - 4), qlen + m4, rem + m4 * 4, rlen + m4, status + m4, n - m4);                            \
+  }
+  PB_DIVZH(11) PB_DIVZH(22)
+#undef PB_DIVZH
+  LAUNCH_CHECK("poly_divide_zh_kernel");
+  return PB_OK;
+}
+int pb_poly_divide_zh(const pb_ctx* ctx, const uint8_t* num, const uint8_t* nlen, size_t sn, uint8_t* quot, uint8_t* qlen, uint8_t* rem,
+                      uint8_t* rlen, uint8_t* status, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(ctx && num && nlen && quot && qlen && rem && rlen && status);
+  ARG(sn == 11 || sn == 22);
+  return piped(ctx->device, {HIN(num, sn), HIN(nlen, 1), HOUT(quot, sn - 4), HOUT(qlen, 1), HOUT(rem, 4), HOUT(rlen, 1), HOUT(status, 1)}, n,
+               [&](uint8_t* const* di, uint8_t* const* dq, size_t m, cudaStream_t st) {
+                 return pb_poly_divide_zh_dev(ctx, di[0], di[1], sn, dq[0], dq[1], dq[2], dq[3], dq[4], m, st); });
+}
+
 int pb_poly_eval_dev(const uint8_t* p, const uint8_t* plen, size_t sp, const uint8_t* x, uint8_t* out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(p && plen && x && out && sp >= 1);
   if (n == 0) return PB_OK;
   if (aligned16(p)) {
+    const size_t m4 = (aligned16(plen) && aligned16(x) && aligned16(out)) ? n / PF4_ITEMS * PF4_ITEMS : 0;
 #define PB_EVAL_FAST(P_)                                                                                   \
     if (sp == P_) {                                                                                        \
-      poly_eval_fast_kernel<P_><<<blocks_for(n, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(p, plen, x, out, n);  \
+      if (m4) poly_eval_fast4_kernel<P_><<<(unsigned)(m4 / PF4_ITEMS), PF4_BLOCK, 0, S(stream)>>>(p, plen, x, out); \
+      if (n > m4) poly_eval_fast_kernel<P_><<<blocks_for(n - m4, PF_BLOCK), PF_BLOCK, 0, S(stream)>>>(p + m4 * P_, plen + m4, x + m4, out + m4, n - m4); \
       LAUNCH_CHECK("poly_eval_fast_kernel");                                                               \
       return PB_OK;                                                                                        \
     }
@@ -535,7 +571,9 @@ int pb_interpolate_at_h_dev(const pb_ctx* ctx, const uint8_t* vals, uint8_t* out
   { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
   ARG(aligned16(vals) && aligned16(out));
   if (n == 0) return PB_OK;
-  interpolate_kernel<<<blocks_for(n, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, vals, out, olen, n);
+  const size_t m4 = aligned16(olen) ? n / PF4_ITEMS * PF4_ITEMS : 0;
+  if (m4) interpolate4_kernel<<<(unsigned)(m4 / PF4_ITEMS), PF4_BLOCK, 0, S(stream)>>>(ctx->cc, vals, out, olen);
+  if (n > m4) interpolate_kernel<<<blocks_for(n - m4, BLOCK_LIGHT), BLOCK_LIGHT, 0, S(stream)>>>(ctx->cc, vals + 4 * m4, out + 4 * m4, olen + m4, n - m4);
   LAUNCH_CHECK("interpolate_kernel");
   return PB_OK;
 }

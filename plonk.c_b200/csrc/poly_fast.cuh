@@ -320,6 +320,50 @@ PB_D void store_slice4(uint8_t* __restrict__ g, const uint32_t* smem, size_t blo
   }
 }
 
+// NW consecutive words of a thread (thread tg owns words [tg * NW, tg * NW + NW)) with the widest aligned vector access
+template <int NW>
+PB_D void load_words(uint32_t (&w)[NW], const uint8_t* __restrict__ base, size_t tg) {
+  if constexpr (NW % 4 == 0) {
+    const uint4* g = reinterpret_cast<const uint4*>(base) + tg * (NW / 4);
+#pragma unroll
+    for (int k = 0; k < NW / 4; k++) { const uint4 v = g[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+  } else if constexpr (NW % 2 == 0) {
+    const uint2* g = reinterpret_cast<const uint2*>(base) + tg * (NW / 2);
+#pragma unroll
+    for (int k = 0; k < NW / 2; k++) { const uint2 v = g[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+  } else {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(base) + tg * NW;
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = g[k];
+  }
+}
+template <int NW>
+PB_D void store_words(uint8_t* __restrict__ base, size_t tg, const uint32_t (&w)[NW]) {
+  if constexpr (NW % 4 == 0) {
+    uint4* g = reinterpret_cast<uint4*>(base) + tg * (NW / 4);
+#pragma unroll
+    for (int k = 0; k < NW / 4; k++) g[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  } else if constexpr (NW % 2 == 0) {
+    uint2* g = reinterpret_cast<uint2*>(base) + tg * (NW / 2);
+#pragma unroll
+    for (int k = 0; k < NW / 2; k++) g[k] = make_uint2(w[2 * k], w[2 * k + 1]);
+  } else {
+    uint32_t* g = reinterpret_cast<uint32_t*>(base) + tg * NW;
+#pragma unroll
+    for (int k = 0; k < NW; k++) g[k] = w[k];
+  }
+}
+// item IT (of four) of ITEM-byte records held in `w` (ITEM words), shifted down to a word boundary: out[0..] little-endian
+template <int ITEM, int IT>
+PB_D void item_words(uint32_t (&out)[(ITEM + 3) / 4], const uint32_t (&w)[ITEM]) {
+  constexpr int B0 = ITEM * IT, W0 = B0 / 4, SH = 8 * (B0 % 4);
+#pragma unroll
+  for (int k = 0; k < (ITEM + 3) / 4; k++) {
+    const uint32_t lo = W0 + k < ITEM ? w[W0 + k] : 0u, hi = W0 + k + 1 < ITEM ? w[W0 + k + 1] : 0u;
+    out[k] = SH == 0 ? lo : __funnelshift_r(lo, hi, SH);
+  }
+}
+
 template <int IT>
 PB_D void config2_item(const CircuitConst& cc, const uint32_t (&wa)[6], const uint32_t (&wb)[6], uint32_t xw, const uint32_t (&vw)[4],
                        uint32_t (&pw)[11], uint32_t (&qw)[7], uint32_t (&rw)[4], uint32_t (&fw)[4], uint32_t (&lens)[4], uint32_t& yw) {
@@ -364,10 +408,7 @@ __global__ void __launch_bounds__(PF4_BLOCK, PB_PF4_MINBLOCKS) config2_kernel4(c
                                                              uint8_t* __restrict__ quot_len, uint8_t* __restrict__ rem,
                                                              uint8_t* __restrict__ rem_len, uint8_t* __restrict__ evals,
                                                              uint8_t* __restrict__ interp, uint8_t* __restrict__ interp_len) {
-  __shared__ __align__(16) uint32_t sp[PF4_BLOCK * 11];
-  __shared__ __align__(16) uint32_t sq[PF4_BLOCK * 7];
-  const int tid = threadIdx.x;
-  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + tid;      // this thread's items: 4 tg .. 4 tg + 3
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + threadIdx.x;      // this thread's items: 4 tg .. 4 tg + 3
   uint32_t wa[6], wb[6], vw[4];
   {
     const uint2* A = reinterpret_cast<const uint2*>(a) + 3 * tg;
@@ -394,25 +435,170 @@ __global__ void __launch_bounds__(PF4_BLOCK, PB_PF4_MINBLOCKS) config2_kernel4(c
   reinterpret_cast<uint32_t*>(quot_len)[tg] = lens[1];
   reinterpret_cast<uint32_t*>(rem_len)[tg] = lens[2];
   reinterpret_cast<uint32_t*>(interp_len)[tg] = lens[3];
-#ifndef PB_PF4_DIRECT
-#define PB_PF4_DIRECT 0
-#endif
-#if PB_PF4_DIRECT
   // word stores straight to global memory: a warp's 11 (7) store instructions together cover its contiguous 1408 (896) bytes
-  (void)sp; (void)sq;
+  // (measured against staging the block's slice through shared memory for 128-bit stores: 51.4 vs 53.1 us per 2^22 items)
+  store_words<11>(prod, tg, pw);
+  store_words<7>(quot, tg, qw);
+}
+
+// ---- the separate entry points for the config-2 shapes, four items per thread (full PF4_ITEMS groups; same rules and
+// results as the one-item kernels above, which run the ragged tail)
+template <int SA, int SB, int IT>
+PB_D void mul_item4(const uint32_t (&wa)[SA], const uint32_t (&wb)[SB], uint32_t la4, uint32_t lb4, uint32_t (&pw)[SA + SB - 1], uint32_t& lens) {
+  constexpr int SO = SA + SB - 1;
+  uint32_t ia[(SA + 3) / 4], ib[(SB + 3) / 4], ra[SA], rb[SB], ro[SO];
+  item_words<SA, IT>(ia, wa);
+  item_words<SB, IT>(ib, wb);
+  const uint32_t la = __byte_perm(la4, 0u, 0x4440 | IT), lb = __byte_perm(lb4, 0u, 0x4440 | IT);
+  bool ok = unpack_masked(ra, ia, la);
+  ok &= unpack_masked(rb, ib, lb);
+  ok &= la != 0u && lb != 0u;
 #pragma unroll
-  for (int k = 0; k < 11; k++) reinterpret_cast<uint32_t*>(prod)[tg * 11 + k] = pw[k];
+  for (int k = 0; k < SO; k++) ro[k] = 0u;
+  mul_acc<SA, SB>(ro, ra, rb);
 #pragma unroll
-  for (int k = 0; k < 7; k++) reinterpret_cast<uint32_t*>(quot)[tg * 7 + k] = qw[k];
-#else
+  for (int k = 0; k < SO; k++) ro[k] = ok ? red17(ro[k]) : 0u;
+  put_bytes<SO, SO * IT>(pw, ro);
+  lens |= (ok ? canon_len(ro) : 0u) << (8 * IT);
+}
+template <int SA, int SB>
+__global__ void __launch_bounds__(PF4_BLOCK) poly_mul_fast4_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ alen,
+                                                                   const uint8_t* __restrict__ b, const uint8_t* __restrict__ blen,
+                                                                   uint8_t* __restrict__ out, uint8_t* __restrict__ olen) {
+  constexpr int SO = SA + SB - 1;
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + threadIdx.x;
+  uint32_t wa[SA], wb[SB], pw[SO], lens = 0u;
+  load_words<SA>(wa, a, tg);
+  load_words<SB>(wb, b, tg);
+  const uint32_t la4 = reinterpret_cast<const uint32_t*>(alen)[tg], lb4 = reinterpret_cast<const uint32_t*>(blen)[tg];
 #pragma unroll
-  for (int k = 0; k < 11; k++) sp[tid * 11 + k] = pw[k];
+  for (int k = 0; k < SO; k++) pw[k] = 0u;
+  mul_item4<SA, SB, 0>(wa, wb, la4, lb4, pw, lens);
+  mul_item4<SA, SB, 1>(wa, wb, la4, lb4, pw, lens);
+  mul_item4<SA, SB, 2>(wa, wb, la4, lb4, pw, lens);
+  mul_item4<SA, SB, 3>(wa, wb, la4, lb4, pw, lens);
+  store_words<SO>(out, tg, pw);
+  reinterpret_cast<uint32_t*>(olen)[tg] = lens;
+}
+
+template <int SP, int IT>
+PB_D void eval_item4(const uint32_t (&w)[SP], uint32_t l4, uint32_t x4, uint32_t& yw) {
+  uint32_t iw[(SP + 3) / 4], c[SP];
+  item_words<SP, IT>(iw, w);
+  const uint32_t len = __byte_perm(l4, 0u, 0x4440 | IT), xv = __byte_perm(x4, 0u, 0x4440 | IT);
+  const bool ok = unpack_masked(c, iw, len) && xv <= 16u;
+  uint32_t y = 0u;
 #pragma unroll
-  for (int k = 0; k < 7; k++) sq[tid * 7 + k] = qw[k];
-  __syncthreads();
-  store_slice4<11>(prod, sp, blockIdx.x);
-  store_slice4<7>(quot, sq, blockIdx.x);
-#endif
+  for (int k = SP - 1; k >= 0; k--) y = red17(y * (xv & 31u) + c[k]);
+  yw |= (ok ? y : 0xFFu) << (8 * IT);
+}
+template <int SP>
+__global__ void __launch_bounds__(PF4_BLOCK) poly_eval_fast4_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen,
+                                                                    const uint8_t* __restrict__ x, uint8_t* __restrict__ out) {
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + threadIdx.x;
+  uint32_t w[SP], yw = 0u;
+  load_words<SP>(w, p, tg);
+  const uint32_t l4 = reinterpret_cast<const uint32_t*>(plen)[tg], x4 = reinterpret_cast<const uint32_t*>(x)[tg];
+  eval_item4<SP, 0>(w, l4, x4, yw);
+  eval_item4<SP, 1>(w, l4, x4, yw);
+  eval_item4<SP, 2>(w, l4, x4, yw);
+  eval_item4<SP, 3>(w, l4, x4, yw);
+  reinterpret_cast<uint32_t*>(out)[tg] = yw;
+}
+
+__global__ void __launch_bounds__(PF4_BLOCK) interpolate4_kernel(const __grid_constant__ CircuitConst cc, const uint8_t* __restrict__ vals,
+                                                                 uint8_t* __restrict__ out, uint8_t* __restrict__ olen) {
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + threadIdx.x;
+  const uint4 v4 = reinterpret_cast<const uint4*>(vals)[tg];
+  const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
+  uint32_t fw[4], lens = 0u;
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const uint32_t v[4] = {vw[it] & 0xFFu, __byte_perm(vw[it], 0u, 0x4441), __byte_perm(vw[it], 0u, 0x4442), vw[it] >> 24};
+    uint32_t f[4];
+    const bool ok = ((((vw[it] & 0x7F7F7F7Fu) + 0x6F6F6F6Fu) | vw[it]) & 0x80808080u) == 0u;    // every byte <= 16
+    interpolate(cc, v, f);
+    fw[it] = ok ? f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24) : 0u;
+    lens |= (ok ? canon_len(f) : 0u) << (8 * it);
+  }
+  reinterpret_cast<uint4*>(out)[tg] = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+  reinterpret_cast<uint32_t*>(olen)[tg] = lens;
+}
+
+// poly_divide(p, Z_H) with the context's Z_H = x^4 - 1 (the prover's own call: plonk.h:505 divides t_numer by pk->z_h_x).  The
+// division by this monic sparse divisor is q[j] = p[j+4] + q[j+4], remainder p[k] + q[k]: SN - 4 additions per item instead of
+// a general long division with a per-item divisor.  Quotient SN - 4 columns, remainder 4 columns, status 0 (or ITEM_INVALID).
+template <int SN, int IT>
+PB_D void divzh_item4(const uint32_t (&w)[SN], uint32_t l4, uint32_t (&qw)[SN - 4], uint32_t& rw, uint32_t& ql4, uint32_t& rl4, uint32_t& st4) {
+  constexpr int SQ = SN - 4;
+  uint32_t iw[(SN + 3) / 4], p[SN], q[SQ], r[4];
+  item_words<SN, IT>(iw, w);
+  const uint32_t len = __byte_perm(l4, 0u, 0x4440 | IT);
+  const bool ok = unpack_masked(p, iw, len);
+#pragma unroll
+  for (int j = SQ - 1; j >= 0; j--) q[j] = j + 4 < SQ ? add17(p[j + 4], q[j + 4]) : p[j + 4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) r[k] = add17(p[k], q[k]);
+  // lengths as poly_divide reports them (poly.h:157-170): the numerator is trimmed first (nl = 0 for a length-0 row); the
+  // remainder has min(4, nl) columns, trimmed while > 1 -- for nl < 4 the quotient is zero and r = p
+  const uint32_t nl = len == 0u ? 0u : canon_len(p);
+  uint32_t rl = nl == 0u ? 0u : canon_len(r);
+#pragma unroll
+  for (int k = 0; k < SQ; k++) q[k] = ok ? q[k] : 0u;
+  put_bytes<SQ, SQ * IT>(qw, q);
+  rw = ok ? r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24) : 0u;
+  ql4 |= (ok ? canon_len(q) : 0u) << (8 * IT);
+  rl4 |= (ok ? rl : 0u) << (8 * IT);
+  st4 |= (ok ? 0u : (uint32_t)ITEM_INVALID) << (8 * IT);
+}
+template <int SN>
+__global__ void __launch_bounds__(PF4_BLOCK) poly_divide_zh4_kernel(const uint8_t* __restrict__ num, const uint8_t* __restrict__ nlen,
+                                                                    uint8_t* __restrict__ quot, uint8_t* __restrict__ qlen,
+                                                                    uint8_t* __restrict__ rem, uint8_t* __restrict__ rlen,
+                                                                    uint8_t* __restrict__ status) {
+  constexpr int SQ = SN - 4;
+  const size_t tg = (size_t)blockIdx.x * PF4_BLOCK + threadIdx.x;
+  uint32_t w[SN], qw[SQ], rw[4], ql4 = 0u, rl4 = 0u, st4 = 0u;
+  load_words<SN>(w, num, tg);
+  const uint32_t l4 = reinterpret_cast<const uint32_t*>(nlen)[tg];
+#pragma unroll
+  for (int k = 0; k < SQ; k++) qw[k] = 0u;
+  divzh_item4<SN, 0>(w, l4, qw, rw[0], ql4, rl4, st4);
+  divzh_item4<SN, 1>(w, l4, qw, rw[1], ql4, rl4, st4);
+  divzh_item4<SN, 2>(w, l4, qw, rw[2], ql4, rl4, st4);
+  divzh_item4<SN, 3>(w, l4, qw, rw[3], ql4, rl4, st4);
+  store_words<SQ>(quot, tg, qw);
+  reinterpret_cast<uint4*>(rem)[tg] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+  reinterpret_cast<uint32_t*>(qlen)[tg] = ql4;
+  reinterpret_cast<uint32_t*>(rlen)[tg] = rl4;
+  reinterpret_cast<uint32_t*>(status)[tg] = st4;
+}
+// the same, one item per thread (ragged tails and unaligned batches)
+template <int SN>
+__global__ void __launch_bounds__(PF_BLOCK) poly_divide_zh_kernel(const uint8_t* __restrict__ num, const uint8_t* __restrict__ nlen,
+                                                                  uint8_t* __restrict__ quot, uint8_t* __restrict__ qlen, uint8_t* __restrict__ rem,
+                                                                  uint8_t* __restrict__ rlen, uint8_t* __restrict__ status, size_t n) {
+  constexpr int SQ = SN - 4;
+  const size_t t = (size_t)blockIdx.x * PF_BLOCK + threadIdx.x;
+  if (t >= n) return;
+  uint32_t p[SN], q[SQ], r[4];
+  const uint32_t len = nlen[t];
+  bool ok = len <= (uint32_t)SN;
+#pragma unroll
+  for (int k = 0; k < SN; k++) { const uint32_t c = num[t * SN + k]; p[k] = (uint32_t)k < len ? c : 0u; ok &= p[k] <= 16u; }
+#pragma unroll
+  for (int j = SQ - 1; j >= 0; j--) q[j] = j + 4 < SQ ? add17(p[j + 4] & 31u, q[j + 4]) : (p[j + 4] & 31u);
+#pragma unroll
+  for (int k = 0; k < 4; k++) r[k] = add17(p[k] & 31u, q[k]);
+  const uint32_t nl = len == 0u ? 0u : canon_len(p);
+  const uint32_t rl = nl == 0u ? 0u : canon_len(r);
+#pragma unroll
+  for (int k = 0; k < SQ; k++) quot[t * SQ + k] = ok ? (uint8_t)q[k] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) rem[t * 4 + k] = ok ? (uint8_t)r[k] : 0;
+  qlen[t] = ok ? (uint8_t)canon_len(q) : 0;
+  rlen[t] = ok ? (uint8_t)rl : 0;
+  status[t] = ok ? 0 : ITEM_INVALID;
 }
 
 }  // namespace pb

@@ -417,6 +417,18 @@ class Plonk:
         c.run(self._h, c.inp(vals), po, pl, C.c_size_t(n))
         return out, olen
 
+    def poly_divide_zh(self, num, nlen):
+        """poly_divide(num, Z_H) with the context's Z_H = x^4 - 1 (plonk.h:505) -> (quot, qlen, rem, rlen, status)."""
+        c = _Call("pb_poly_divide_zh", num)
+        n, sn = _n(num), int(num.shape[1])
+        quot, pq = c.out((n, sn - 4))
+        qlen, pql = c.out((n,))
+        rem, pr = c.out((n, 4))
+        rlen, prl = c.out((n,))
+        status, ps = c.out((n,))
+        c.run(self._h, c.inp(num), c.inp(nlen), C.c_size_t(sn), pq, pql, pr, prl, ps, C.c_size_t(n))
+        return quot, qlen, rem, rlen, status
+
     def config2_items_into(self, a, b, x, vals, outs):
         """Host path with caller-owned (pinned) numpy buffers: outs = (prod[n][11], prod_len[n], quot[n][7], quot_len[n],
         rem[n][4], rem_len[n], evals[n], interp[n][4], interp_len[n])."""

@@ -611,3 +611,29 @@ def test_adversarial_bytes_unop_slice_lagrange_commit(host, oracle, W):
         assert (st[::7] == 2).all() and (st[3::7] == 2).all() and not got[st == 2].any()
         okm = st != 2
         ps.eq("commit: valid items", (got[okm], st[okm]), (want[okm], wst[okm]))
+
+
+def test_poly_divide_by_zh(host, oracle, W):
+    """pb_poly_divide_zh (the context's Z_H = x^4 - 1, plonk.h:505) == poly_divide with that divisor passed per item: strides 11
+    and 22, ragged sizes around the four-items-per-thread groups, zero / short / length-0 numerators, invalid rows."""
+    import torch
+    rng = np.random.default_rng(33)
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
+    for sn in (11, 22):
+        for n in (1, 511, 512, 513, 20011):
+            num = rng.integers(0, 17, (n, sn), dtype=np.uint8)
+            num[rng.random((n, sn)) < 0.3] = 0
+            nl = rng.integers(1, sn + 1, n).astype(np.uint8)      # (a length-0 numerator makes the reference read past a calloc(0): poly.h:133-159)
+            num[: n // 10] = 0
+            zh = np.tile(np.array([16, 0, 0, 0, 1], np.uint8), (n, 1)); five = np.full(n, 5, np.uint8)
+            want = oracle.poly_divide(num, nl, zh, five, sn - 4, 4)
+            for path in ("device", "host"):
+                got = pk.poly_divide_zh(*( (torch.from_numpy(num).cuda(), torch.from_numpy(nl).cuda()) if path == "device" else (num, nl)))
+                got = tuple(np.asarray(g.cpu()) if path == "device" else g for g in got)
+                ps.eq(f"divide by Z_H, stride {sn}, n {n}, {path}", got, want)
+        num2 = num.copy(); nl2 = nl.copy()
+        num2[::9, 0] = 30; nl2[::9] = np.maximum(nl2[::9], 1); nl2[4::9] = sn + 1
+        q, ql, r, rl, st = (g.cpu().numpy() for g in pk.poly_divide_zh(torch.from_numpy(num2).cuda(), torch.from_numpy(nl2).cuda()))
+        assert (st[::9] == 2).all() and (st[4::9] == 2).all() and not q[st == 2].any() and not r[st == 2].any()
+        okm = st != 2
+        ps.eq("divide by Z_H: valid items", (q[okm], ql[okm], r[okm], rl[okm], st[okm]), tuple(w[okm] for w in want))
