@@ -190,6 +190,19 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_divide_fast_kernel(const uint8_
   store_slice<SR>(rem, sr, first, n);
 }
 
+// Horner from the top coefficient (poly.h:265-272) with a reduction every third step only: for canonical y, x, c the running
+// value stays below 17 * 16^3 + 16^3 < 2^17 between reductions, far inside red17's range; the result is the same residue
+template <int N>
+PB_D uint32_t horner17(const uint32_t (&c)[N], uint32_t x) {
+  uint32_t y = 0u;
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    y = y * x + c[k];
+    if ((N - 1 - k) % 3 == 2 || k == 0) y = red17(y);
+  }
+  return y;
+}
+
 // poly_eval (poly.h:265-272) for a fixed stride
 template <int SP>
 __global__ void __launch_bounds__(PF_BLOCK) poly_eval_fast_kernel(const uint8_t* __restrict__ p, const uint8_t* __restrict__ plen,
@@ -200,9 +213,7 @@ __global__ void __launch_bounds__(PF_BLOCK) poly_eval_fast_kernel(const uint8_t*
   load_record<SP>(w, p, t, n);
   const uint32_t len = plen[t], xv = x[t];
   const bool ok = unpack_masked(c, w, len) && xv <= 16u;
-  uint32_t y = 0u;
-#pragma unroll
-  for (int k = SP - 1; k >= 0; k--) y = red17(y * (xv & 31u) + c[k]);   // Horner from the top; masked coefficients are 0 and y stays 0 above len
+  const uint32_t y = horner17(c, xv & 31u);                     // masked coefficients are 0, so y stays 0 above len
   out[t] = ok ? (uint8_t)y : 0xFF;
 }
 
@@ -246,10 +257,7 @@ __global__ void __launch_bounds__(PF_BLOCK) config2_kernel(const __grid_constant
     rem_len[t] = (uint8_t)canon_len(r);
     // poly_eval(A, x), Horner from the top (poly.h:265-272)
     const uint32_t xv = x[t];
-    uint32_t y = 0u;
-#pragma unroll
-    for (int k = 5; k >= 0; k--) y = red17(y * xv + ra[k]);
-    evals[t] = (uint8_t)y;
+    evals[t] = (uint8_t)horner17(ra, xv & 31u);
     // interpolate_at_h(vals) = h_pows_inv * vals (plonk.h:162-195)
     const uint32_t wv = reinterpret_cast<const uint32_t*>(vals)[t];
     uint32_t v[4] = {wv & 0xFFu, (wv >> 8) & 0xFFu, (wv >> 16) & 0xFFu, wv >> 24}, f[4];
@@ -386,10 +394,7 @@ PB_D void config2_item(const CircuitConst& cc, const uint32_t (&wa)[6], const ui
   rw[IT] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
   // poly_eval(A, x), Horner from the top (poly.h:265-272)
   const uint32_t xv = __byte_perm(xw, 0u, 0x4440 | IT);
-  uint32_t y = 0u;
-#pragma unroll
-  for (int k = 5; k >= 0; k--) y = red17(y * xv + ra[k]);
-  yw |= y << (8 * IT);
+  yw |= horner17(ra, xv & 31u) << (8 * IT);
   // interpolate_at_h(vals) = h_pows_inv * vals (plonk.h:162-195)
   const uint32_t v[4] = {vw[IT] & 0xFFu, __byte_perm(vw[IT], 0u, 0x4441), __byte_perm(vw[IT], 0u, 0x4442), vw[IT] >> 24};
   interpolate(cc, v, f);
@@ -487,9 +492,7 @@ PB_D void eval_item4(const uint32_t (&w)[SP], uint32_t l4, uint32_t x4, uint32_t
   item_words<SP, IT>(iw, w);
   const uint32_t len = __byte_perm(l4, 0u, 0x4440 | IT), xv = __byte_perm(x4, 0u, 0x4440 | IT);
   const bool ok = unpack_masked(c, iw, len) && xv <= 16u;
-  uint32_t y = 0u;
-#pragma unroll
-  for (int k = SP - 1; k >= 0; k--) y = red17(y * (xv & 31u) + c[k]);
+  const uint32_t y = horner17(c, xv & 31u);
   yw |= (ok ? y : 0xFFu) << (8 * IT);
 }
 template <int SP>

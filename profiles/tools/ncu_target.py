@@ -81,6 +81,9 @@ else:
     print("poly_mul_fast_kernel<6, 6>", n)
     host.poly_divide(prod, plen, zh, five, sq=7, sr=4)
     print("poly_divide_fast_kernel<11, 5>", n)
+    ctx0 = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
+    ctx0.poly_divide_zh(prod, plen)
+    print("poly_divide_zh4_kernel<11>", n)
     host.poly_eval(a6, six, x)
     print("poly_eval_fast_kernel<6>", n)
     ctx = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.identity_srs(6))
