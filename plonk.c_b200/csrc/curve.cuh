@@ -63,7 +63,9 @@ PB_HD G1 g1_double_c(const FieldTables& t, G1 a) {
 PB_HD G1 g1_add_c(const FieldTables& t, G1 a, G1 b) {
   const bool same_x = a.x == b.x;
   const uint32_t sum_y = a.y + b.y;
-  const bool to_id = same_x && (sum_y == 0u || sum_y == P101 || a.y == 0u);
+  // canonical curve points with equal x are equal or mutually inverse, so a.y == 0 implies b.y == 0: the reference's third
+  // test (doubling a 2-torsion point, g1.h:38) is covered by sum_y == 0 on this domain
+  const bool to_id = same_x && (sum_y == 0u || sum_y == P101);
   const uint32_t num = same_x ? 3u * a.x * a.x : (b.y + P101 - a.y);
   const uint32_t den = same_x ? 2u * a.y : (b.x + P101 - a.x);
   const uint32_t m = red101(num * inv101(t, den));

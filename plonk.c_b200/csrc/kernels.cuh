@@ -1003,6 +1003,9 @@ struct __align__(16) VerifyFastSmem {
   __align__(16) VerifyTables vt;
   __align__(16) uint8_t proof[BLOCK * 34];
   __align__(16) uint8_t chal[BLOCK * 5];
+#if PB_VERIFY_SMEM_PICK
+  uint32_t pick[16 * BLOCK];          // per-thread sub-tables of the joint double-and-add, [pair][entry][thread]
+#endif
 };
 
 template <bool WANT_GT>
@@ -1089,7 +1092,11 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
     uu = u[item];
   }
   VerifyOut o;
+#if PB_VERIFY_SMEM_PICK
+  verify_one_fast<WANT_GT>(key, sm.vt, sm.ft, pbytes, op, ch, uu, o, PickSmem<BLOCK>{sm.pick + tid});
+#else
   verify_one_fast<WANT_GT>(key, sm.vt, sm.ft, pbytes, op, ch, uu, o);
+#endif
   verdict[item] = (uint8_t)o.verdict;
   if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
 }

@@ -4,6 +4,7 @@
 // by step and performs the same group operations in the same order, each of them the exact
 // emulation of g1_mul / g1_add / g1_neg / pairing from curve.cuh.
 #pragma once
+#include <type_traits>
 #include "curve.cuh"
 #include "prover.cuh"   // pack_g1 / unpack_g1
 
@@ -122,11 +123,25 @@ PB_HD G1 pick4(uint32_t sel, G1 p, G1 q, G1 pq) {   // sel: 0 -> identity, 1 -> 
   return r;
 }
 
+// The joint double-and-add picks one of {identity, A, B, A + B} per pair and bit.  PICK = a per-thread look-up table of packed
+// points (x | y << 8 | infinite << 16) in shared memory: one load + unpack per pick instead of three compares and nine selects.
+// Layout [pair][entry][lane]: a warp's 32 loads of one instruction hit 32 consecutive words -- no bank conflicts.
+#ifndef PB_VERIFY_SMEM_PICK
+#define PB_VERIFY_SMEM_PICK 1
+#endif
+struct PickNone {};
+template <int NT>
+struct PickSmem {
+  uint32_t* base;                                  // this thread's column: word (pair * 4 + entry) * NT
+  PB_HD void set(int pair, int entry, G1 p) const { base[(pair * 4 + entry) * NT] = p.x | p.y << 8 | p.inf << 16; }
+  PB_HD G1 get(int pair, uint32_t entry) const { return unpack_g1(base[(pair * 4 + entry) * NT]); }
+};
+
 // WANT_GT = false: the caller does not read the two pairing values, so the check shares one final exponentiation
 // (pairings_equal17_c, curve.cuh) and out.lhs / out.rhs stay zero.
-template <bool WANT_GT = true>
+template <bool WANT_GT = true, typename Pick = PickNone>
 PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const FieldTables& ft, const uint32_t (&pb)[27],
-                          const uint32_t (&op)[7], const uint32_t (&ch)[5], uint32_t u, VerifyOut& out) {
+                          const uint32_t (&op)[7], const uint32_t (&ch)[5], uint32_t u, VerifyOut& out, Pick pick = Pick()) {
   out.lhs = GT{0u, 0u};
   out.rhs = GT{0u, 0u};
   bool bad_pt = false;
@@ -179,19 +194,32 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
   const G1 A0 = P[7], B0 = P[8], A1 = P[5], B1 = P[6], A2 = P[0], B2 = P[1], A3 = P[2], B3 = P[3];
   const uint32_t sa0 = z, sb0 = red17(red17(u * z) * OMEGA), sa1 = z6, sb1 = z12, sa2 = v2, sb2 = v3, sa3 = v4, sb3 = d_z;
   const G1 S0 = g1_add_c(ft, A0, B0), S1 = g1_add_c(ft, A1, B1), S2 = g1_add_c(ft, A2, B2), S3 = g1_add_c(ft, A3, B3);
+  constexpr bool SMEM = !std::is_same<Pick, PickNone>::value;
+  if constexpr (SMEM) {
+    const G1 id = g1_identity();
+    pick.set(0, 0, id); pick.set(0, 1, A0); pick.set(0, 2, B0); pick.set(0, 3, S0);
+    pick.set(1, 0, id); pick.set(1, 1, A1); pick.set(1, 2, B1); pick.set(1, 3, S1);
+    pick.set(2, 0, id); pick.set(2, 1, A2); pick.set(2, 2, B2); pick.set(2, 3, S2);
+    pick.set(3, 0, id); pick.set(3, 1, A3); pick.set(3, 2, B3); pick.set(3, 3, S3);
+  }
+  auto sel = [&](int pair, uint32_t sa, uint32_t sb, int bit, const G1& A, const G1& B, const G1& S) -> G1 {
+    const uint32_t e = ((sa >> bit) & 1u) | (((sb >> bit) & 1u) << 1);
+    if constexpr (SMEM) return pick.get(pair, e);
+    else return pick4(e, A, B, S);
+  };
   // top bit first, peeled: the accumulators start at the identity, whose doubling is the identity and to which an
   // addition returns the other operand, so the first doubling and the first addition of each chain are a plain pick
-  G1 s = pick4(((sa0 >> 4) & 1u) | (((sb0 >> 4) & 1u) << 1), A0, B0, S0);
-  s = g1_add_c(ft, s, pick4(((sa1 >> 4) & 1u) | (((sb1 >> 4) & 1u) << 1), A1, B1, S1));
-  s = g1_add_c(ft, s, pick4(((sa2 >> 4) & 1u) | (((sb2 >> 4) & 1u) << 1), A2, B2, S2));
-  s = g1_add_c(ft, s, pick4(((sa3 >> 4) & 1u) | (((sb3 >> 4) & 1u) << 1), A3, B3, S3));
+  G1 s = sel(0, sa0, sb0, 4, A0, B0, S0);
+  s = g1_add_c(ft, s, sel(1, sa1, sb1, 4, A1, B1, S1));
+  s = g1_add_c(ft, s, sel(2, sa2, sb2, 4, A2, B2, S2));
+  s = g1_add_c(ft, s, sel(3, sa3, sb3, 4, A3, B3, S3));
   G1 l = pick4((u >> 4) & 1u, B0, B0, B0);
   for (int bit = 3; bit >= 0; --bit) {
     s = g1_double_c(ft, s);
-    s = g1_add_c(ft, s, pick4(((sa0 >> bit) & 1u) | (((sb0 >> bit) & 1u) << 1), A0, B0, S0));
-    s = g1_add_c(ft, s, pick4(((sa1 >> bit) & 1u) | (((sb1 >> bit) & 1u) << 1), A1, B1, S1));
-    s = g1_add_c(ft, s, pick4(((sa2 >> bit) & 1u) | (((sb2 >> bit) & 1u) << 1), A2, B2, S2));
-    s = g1_add_c(ft, s, pick4(((sa3 >> bit) & 1u) | (((sb3 >> bit) & 1u) << 1), A3, B3, S3));
+    s = g1_add_c(ft, s, sel(0, sa0, sb0, bit, A0, B0, S0));
+    s = g1_add_c(ft, s, sel(1, sa1, sb1, bit, A1, B1, S1));
+    s = g1_add_c(ft, s, sel(2, sa2, sb2, bit, A2, B2, S2));
+    s = g1_add_c(ft, s, sel(3, sa3, sb3, bit, A3, B3, S3));
     l = g1_double_c(ft, l);                                              // u [W_zw] for the left-hand side
     l = g1_add_c(ft, l, pick4((u >> bit) & 1u, B0, B0, B0));
   }

@@ -221,8 +221,10 @@ void hc_verify_fast(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs,
     if (chal) { for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j]; uu = u[i]; }
     else fs_derive(fs_seed, pbv, op, ch, uu);
     VerifyOut o;
-    if (gt) verify_one_fast<true>(k, vt, ft, pbv, op, ch, uu, o);
-    else verify_one_fast<false>(k, vt, ft, pbv, op, ch, uu, o);   // verdict only: one shared final exponentiation
+    uint32_t pick_buf[16];                                          // the kernel's per-thread sub-table column (stride 1 here)
+    if (gt) verify_one_fast<true>(k, vt, ft, pbv, op, ch, uu, o, PickSmem<1>{pick_buf});
+    else if (i & 1) verify_one_fast<false>(k, vt, ft, pbv, op, ch, uu, o, PickSmem<1>{pick_buf});   // verdict only: one shared final exponentiation
+    else verify_one_fast<false>(k, vt, ft, pbv, op, ch, uu, o);     // ... and the select-based picks on every other item
     verdict[i] = (uint8_t)o.verdict;
     if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
   }
