@@ -1301,7 +1301,8 @@ int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal
 // dense list of the completed proofs of a chunk (stream-ordered): offs[0 .. groups) and the count in offs[cap / 128 + 3]
 static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t m, uint32_t* offs, uint32_t* count,
                          uint8_t* dense, uint8_t* sv, bool pack, cudaStream_t st, uint32_t* count_host = nullptr) {
-  done_offsets_kernel<<<1, 1024, 0, st>>>(status, m, offs, count, count_host);
+  done_counts_kernel<<<blocks_for((m + GBLOCK - 1) / GBLOCK, 256), 256, 0, st>>>(status, m, offs);
+  done_offsets_kernel<<<1, 1024, 0, st>>>(m, offs, count, count_host);
   LAUNCH_CHECK("done_offsets_kernel");
   if (pack) gather_done_kernel<true><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
   else gather_done_kernel<false><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);

@@ -1120,31 +1120,34 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) compact_kernel(const uint8_t* __r
 // ------------------------------------------------------------------ compact / packed outputs, synthetic inputs (wire.cuh)
 // Only the proofs that exist travel back to the host: a dense array of the completed proofs (status 0) in item order.
 // Step 1: offs[g] = number of completed items before group g (GBLOCK items per group), *total = all of them.
-// One block: the status bytes of a chunk are at most a megabyte and hot in L2.
 constexpr int GBLOCK = 128;
+// Step 1a (all SMs): offs[g] = number of completed items of group g; one group of GBLOCK status bytes per thread.
+__global__ void __launch_bounds__(256) done_counts_kernel(const uint8_t* __restrict__ status, size_t m, uint32_t* __restrict__ offs) {
+  const uint32_t G = (uint32_t)((m + GBLOCK - 1) / GBLOCK);
+  const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+  if (g >= G) return;
+  const bool al = (reinterpret_cast<uintptr_t>(status) & 15u) == 0;
+  const size_t lo = (size_t)g * GBLOCK, hi = lo + GBLOCK < m ? lo + GBLOCK : m;
+  uint32_t c = 0;
+  if (al && hi - lo == GBLOCK) {
+#pragma unroll
+    for (int k = 0; k < GBLOCK / 16; k++) {
+      const uint4 q = reinterpret_cast<const uint4*>(status + lo)[k];
+      c += (uint32_t)(__popc(__vcmpeq4(q.x, 0u)) + __popc(__vcmpeq4(q.y, 0u)) + __popc(__vcmpeq4(q.z, 0u)) + __popc(__vcmpeq4(q.w, 0u))) >> 3;
+    }
+  } else {
+    for (size_t i = lo; i < hi; i++) c += status[i] == 0 ? 1u : 0u;
+  }
+  offs[g] = c;
+}
+// Step 1b (one block): exclusive scan of the group counts in place, *total = their sum.
 // total_host (optional): a second copy of the count in mapped pinned host memory -- the host-pointer pipelines read it after
 // the chunk's event instead of queueing a 4-byte D2H copy behind megabytes of proofs on the copy engine.
-__global__ void __launch_bounds__(1024) done_offsets_kernel(const uint8_t* __restrict__ status, size_t m, uint32_t* __restrict__ offs,
-                                                            uint32_t* __restrict__ total, uint32_t* __restrict__ total_host = nullptr) {
+__global__ void __launch_bounds__(1024) done_offsets_kernel(size_t m, uint32_t* __restrict__ offs, uint32_t* __restrict__ total,
+                                                            uint32_t* __restrict__ total_host = nullptr) {
   __shared__ uint32_t wsum[32];
   const uint32_t G = (uint32_t)((m + GBLOCK - 1) / GBLOCK);
-  const bool al = (reinterpret_cast<uintptr_t>(status) & 15u) == 0;
-  for (uint32_t g = threadIdx.x; g < G; g += 1024u) {
-    const size_t lo = (size_t)g * GBLOCK, hi = lo + GBLOCK < m ? lo + GBLOCK : m;
-    uint32_t c = 0;
-    if (al && hi - lo == GBLOCK) {
-#pragma unroll
-      for (int k = 0; k < GBLOCK / 16; k++) {
-        const uint4 q = reinterpret_cast<const uint4*>(status + lo)[k];
-        c += (uint32_t)(__popc(__vcmpeq4(q.x, 0u)) + __popc(__vcmpeq4(q.y, 0u)) + __popc(__vcmpeq4(q.z, 0u)) + __popc(__vcmpeq4(q.w, 0u))) >> 3;
-      }
-    } else {
-      for (size_t i = lo; i < hi; i++) c += status[i] == 0 ? 1u : 0u;
-    }
-    offs[g] = c;
-  }
-  __syncthreads();
-  // exclusive scan in place: thread t owns the contiguous groups [t * per, (t + 1) * per)
+  // thread t owns the contiguous groups [t * per, (t + 1) * per)
   const uint32_t per = (G + 1023u) / 1024u;
   const uint32_t lo = threadIdx.x * per < G ? threadIdx.x * per : G, hi = lo + per < G ? lo + per : G;
   uint32_t mine = 0;
