@@ -348,10 +348,11 @@ int pb_field_op_dev(int field, int op, const uint8_t* a, const uint8_t* b, uint8
     if (grid > 148u * 8u) grid = 148u * 8u;
     if (field == 17) field_pow_kernel<17><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
     else field_pow_kernel<101><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
-  } else if (field == 17) {
-    field_op_kernel<17><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
   } else {
-    field_op_kernel<101><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(op, a, b, out, n);
+#define PB_FIELD_OP(F_, O_) if (field == F_ && op == O_) field_op_kernel<F_, O_><<<grid, BLOCK_LIGHT, 0, S(stream)>>>(a, b, out, n);
+    PB_FIELD_OP(17, 0) PB_FIELD_OP(17, 1) PB_FIELD_OP(17, 2) PB_FIELD_OP(17, 3) PB_FIELD_OP(17, 4) PB_FIELD_OP(17, 5)
+    PB_FIELD_OP(101, 0) PB_FIELD_OP(101, 1) PB_FIELD_OP(101, 2) PB_FIELD_OP(101, 3) PB_FIELD_OP(101, 4) PB_FIELD_OP(101, 5)
+#undef PB_FIELD_OP
   }
   LAUNCH_CHECK("field_op_kernel");
   return PB_OK;

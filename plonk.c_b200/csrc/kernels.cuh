@@ -112,9 +112,12 @@ PB_D uint32_t field_apply(const FieldTables& ft, int op, uint32_t a, uint32_t b)
 }
 
 // 16 elements per thread through 128-bit loads/stores; the tail (n % 16) is handled byte-wise by the last threads.
-template <int FIELD>
-__global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+// OP is a template parameter: the operation is resolved at compile time (one small kernel per field and operation) instead of
+// a switch on a kernel argument inside a loop that has ~10 instructions per element to spend
+template <int FIELD, int OP>
+__global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                                uint8_t* __restrict__ out, size_t n) {
+  constexpr int op = OP;
   __shared__ FieldTables ft;
   build_field_tables(ft);
   __syncthreads();
@@ -126,6 +129,12 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uin
     uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w}, wo[4];
 #pragma unroll
     for (int w = 0; w < 4; w++) {
+      if constexpr (OP == 4) {
+        // negation of four canonical residues at once: p - a byte-wise (no borrow: a <= p - 1), zero bytes stay zero
+        const uint32_t nz = (((wa[w] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | wa[w]) & 0x80808080u;     // bit 7 of every non-zero byte
+        const bool canon = ((((wa[w] & 0x7F7F7F7Fu) + (0x80u - FIELD) * 0x01010101u) | wa[w]) & 0x80808080u) == 0u;   // every byte < p
+        if (canon) { wo[w] = ((uint32_t)FIELD * 0x01010101u - wa[w]) & ((nz >> 7) * 0xFFu); continue; }
+      }
       uint32_t r = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++)
@@ -138,25 +147,40 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_op_kernel(int op, const uin
     out[i] = (uint8_t)field_apply<FIELD>(ft, op, a[i], b ? b[i] : 0u);
 }
 
-// hf_pow / gf_pow (hf.h:127-137, gf.h:140-151) with a one-byte exponent: the reference's square-and-multiply returns
-// (a mod p)^e with 0^0 = 1, so the result is a look-up in a per-block table tab[a][k] = a^k, k < p - 1 (Fermat:
-// a^(p-1) = 1 for a != 0), with the base-zero row handled by a select.  272 B (F17) / 10 KB (F101) of shared memory,
-// built once per block (one row per thread, p - 2 multiplications).  16 elements per thread, 128-bit accesses.
+// hf_pow / gf_pow (hf.h:127-137, gf.h:140-151) with a one-byte exponent.  The reference's square-and-multiply returns
+// (a mod p)^e with 0^0 = 1; over a prime field that is alog[(log a * e) mod (p - 1)] for a != 0, with discrete logarithms
+// to the primitive root 3 (F17) / 2 (F101).  Both tables are built at COMPILE time and are at most 101 bytes each, i.e.
+// they sit inside one 128-byte row of shared memory: no bank conflicts for any access pattern.  (Round 1 looked a^k up in
+// a 10 KB per-block table: 10.5 M bank conflicts per 2^27-element launch, 58 % of the HBM roofline for gf_pow.)
+template <int FIELD>
+struct PowTablesImage {
+  uint32_t w[64];                           // bytes 0..127: log[a] (log[0] unused), bytes 128..255: alog[k], k < p - 1
+  constexpr PowTablesImage() : w{} {
+    constexpr uint32_t P = FIELD, G = FIELD == 17 ? 3u : 2u;
+    uint32_t v = 1u;
+    for (uint32_t k = 0; k < P - 1; k++) {
+      w[(128 + k) / 4] |= v << (8u * ((128 + k) % 4u));      // alog[k] = g^k
+      w[v / 4] |= k << (8u * (v % 4u));                      // log[g^k] = k
+      v = v * G % P;
+    }
+  }
+};
+__device__ __align__(16) const PowTablesImage<17> g_pow_tables_17 = PowTablesImage<17>();
+__device__ __align__(16) const PowTablesImage<101> g_pow_tables_101 = PowTablesImage<101>();
+
 template <int FIELD>
 __global__ void __launch_bounds__(BLOCK_LIGHT) field_pow_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ e,
                                                                 uint8_t* __restrict__ out, size_t n) {
-  constexpr uint32_t P = FIELD, ORD = FIELD - 1;
-  __shared__ uint8_t tab[P * ORD];
-  for (uint32_t row = threadIdx.x; row < P; row += blockDim.x) {
-    uint32_t v = 1u;
-    for (uint32_t k = 0; k < ORD; k++) { tab[row * ORD + k] = (uint8_t)v; v = FIELD == 17 ? mul17(v, row) : mul101(v, row); }
-  }
+  constexpr uint32_t ORD = FIELD - 1;
+  __shared__ __align__(128) uint8_t tab[256];
+  if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(tab)[threadIdx.x] = FIELD == 17 ? g_pow_tables_17.w[threadIdx.x] : g_pow_tables_101.w[threadIdx.x];
   __syncthreads();
   auto one = [&](uint32_t base, uint32_t ex) -> uint32_t {
     const uint32_t b = FIELD == 17 ? red17(base) : red101(base);
-    const uint32_t k = FIELD == 17 ? (ex & 15u) : ex - 100u * ((ex * 41u) >> 12);     // ex mod (p - 1), ex < 256
-    const uint32_t t = tab[b * ORD + k];
-    return (b == 0u && ex != 0u) ? 0u : t;                                             // row 0 holds 0^0 = 1 only
+    const uint32_t t = tab[b] * ex;                                                    // log a * e < 100 * 256
+    const uint32_t k = FIELD == 17 ? (t & 15u) : t - 100u * ((t * 5243u) >> 19);       // mod (p - 1); floor(t / 100) exact for t < 43 690
+    const uint32_t r = tab[128u + k];
+    return b == 0u ? (ex == 0u ? 1u : 0u) : r;                                         // 0^0 = 1, 0^e = 0
   };
   const size_t nvec = n / 16;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -174,6 +198,7 @@ __global__ void __launch_bounds__(BLOCK_LIGHT) field_pow_kernel(const uint8_t* _
     reinterpret_cast<uint4*>(out)[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
   }
   for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint8_t)one(a[i], e[i]);
+  (void)ORD;
 }
 
 // hf_new / gf_new (hf.h:25-35, gf.h:24-34): C remainder of a signed 64-bit value, negatives folded up
