@@ -315,10 +315,11 @@ int pb_synth_batch_dev(const pb_ctx *ctx, uint64_t seed, uint64_t start, size_t 
 /* ---- Fiat-Shamir mode (optional).  The reference's prover takes its challenges from
  * the caller (CHALLENGE, plonk.h:16-22,227) -- the entry points above keep that interface and are bit-exact with it.
  * Here the five challenges, and the verifier's u, are drawn from a transcript hash of the circuit, the SRS and the proof
- * elements produced so far (specification: oracle/fs_spec.inc; kernel side: csrc/transcript.cuh).  Given the challenges
+ * elements produced so far -- a duplex sponge over a 128-bit ARX state, HalfSipHash's round function (specification:
+ * oracle/fs_spec.inc; kernel side: csrc/transcript.cuh).  Given the challenges
  * the transcript yields, proofs and statuses are exactly what plonk_prove returns for them. */
-/* initial transcript state for this context's circuit + SRS */
-int pb_ctx_fs_seed(const pb_ctx *ctx, uint32_t *out);
+/* the transcript state after absorbing this context's circuit + SRS: four 32-bit words */
+int pb_ctx_fs_seed(const pb_ctx *ctx, uint32_t out[4]);
 /* witness[n][12], rnd[n][9] -> proofs[n][34], status[n]; chal_out (optional, may be NULL): [n][6] = alpha beta gamma z v u
  * as drawn, 0xFF for a challenge the reference's execution exits before drawing */
 int pb_plonk_prove_fs_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, uint8_t *proofs, uint8_t *status,

@@ -274,8 +274,11 @@ class OracleLib:
         return proofs, status, chal
 
     def fs_seed(self, circuit, g1s, g2):
+        """the transcript state after absorbing circuit and SRS: four 32-bit words as one Python int (v0 | v1 << 32 | v2 << 64 | v3 << 96)"""
         circuit, g1s, g2 = _u8(circuit), _u8(g1s), _u8(g2)
-        return int(self._f("fs_seed", [u8p, u8p, C.c_uint32, u8p], C.c_uint32)(_p(circuit), _p(g1s), g1s.shape[0], _p(g2)))
+        out = np.zeros(4, np.uint32)
+        self._f("fs_seed", [u8p, u8p, C.c_uint32, u8p, C.c_void_p], None)(_p(circuit), _p(g1s), g1s.shape[0], _p(g2), out.ctypes.data_as(C.c_void_p))
+        return sum(int(w) << (32 * k) for k, w in enumerate(out))
 
     def fs_challenges(self, circuit, g1s, g2, proofs):
         return self.fs_derive(self.fs_seed(circuit, g1s, g2), proofs)
@@ -290,7 +293,8 @@ class OracleLib:
         proofs = _u8(proofs)
         n = proofs.shape[0]
         chal = np.zeros((n, 6), np.uint8)
-        self._f("fs_derive", [C.c_uint32, u8p, C.c_size_t, u8p])(seed, _p(proofs), n, _p(chal))
+        words = np.array([(int(seed) >> (32 * k)) & 0xFFFFFFFF for k in range(4)], np.uint32)
+        self._f("fs_derive", [C.c_void_p, u8p, C.c_size_t, u8p])(words.ctypes.data_as(C.c_void_p), _p(proofs), n, _p(chal))
         return chal
 
     def verifier_key(self, circuit, g1s, g2):

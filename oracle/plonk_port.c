@@ -435,7 +435,7 @@ static void put_g1(uint8_t *o, g1 p) { o[0] = p.x; o[1] = p.y; o[2] = p.inf ? 1 
 /* plonk.h:223-656.  Returns the SURVEY.md Appendix-B row of the first exit that fires (0 = done). */
 /* Fiat-Shamir mode (fs != NULL; spec: fs_spec.inc): ch is ignored, each challenge is drawn from the transcript at
  * the point where the protocol fixes it, and fs->ch / fs->known report what was drawn before the first exit. */
-typedef struct { uint32_t st; uint8_t ch[6], known[6]; } fs_t;
+typedef struct { fs_state st; uint8_t ch[6], known[6]; } fs_t;
 static int plonk_prove_(const plonk_t *pk, const circuit_t *cs, const fe *wa, const fe *wb, const fe *wc,
                         const fe ch[5], const fe rnd[9], uint8_t proof[34], fs_t *fs) {
   const int n = 4;
@@ -846,7 +846,7 @@ void port_interpolate_at_h(const uint8_t *vals, uint8_t *out, uint8_t *olen, siz
 typedef struct {
   plonk_t pk; circuit_t cs;
   const uint8_t *wit, *rnd, *chal; uint8_t *proofs, *status;
-  int fs_mode; uint32_t fs_seed; uint8_t *chal_out;
+  int fs_mode; fs_state fs_seed; uint8_t *chal_out;
 } prove_ctx;
 static void prove_range(void *c, size_t lo, size_t hi) {
   prove_ctx *x = c;
@@ -875,7 +875,7 @@ void port_plonk_prove_batch(const uint8_t *circuit, const uint8_t *g1s, uint32_t
   plonk_new_(&c->pk, &s);
   circuit_from(&c->cs, circuit);
   c->wit = wit; c->rnd = rnd; c->chal = chal; c->proofs = proofs; c->status = status;
-  c->fs_mode = 0; c->fs_seed = 0; c->chal_out = NULL;
+  c->fs_mode = 0; memset(&c->fs_seed, 0, sizeof c->fs_seed); c->chal_out = NULL;
   run_ranges(prove_range, c, n, nthreads);
   free(c);
 }
@@ -892,11 +892,14 @@ void port_plonk_prove_fs_batch(const uint8_t *circuit, const uint8_t *g1s, uint3
   run_ranges(prove_range, c, n, nthreads);
   free(c);
 }
-uint32_t port_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2b) {
-  return fs_seed(circuit, g1s, srs_len, g2b);
+void port_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2b, uint32_t out[4]) {
+  const fs_state st = fs_seed(circuit, g1s, srs_len, g2b);
+  memcpy(out, st.v, sizeof st.v);
 }
-void port_fs_derive(uint32_t seed, const uint8_t *proofs, size_t n, uint8_t *chal6) {
-  for (size_t i = 0; i < n; i++) fs_derive(seed, proofs + 34 * i, chal6 + 6 * i);
+void port_fs_derive(const uint32_t seed[4], const uint8_t *proofs, size_t n, uint8_t *chal6) {
+  fs_state st;
+  memcpy(st.v, seed, sizeof st.v);
+  for (size_t i = 0; i < n; i++) fs_derive(st, proofs + 34 * i, chal6 + 6 * i);
 }
 
 /* ---------------- verifier (parity unpinned: see verify_spec.inc) over the restated primitives */

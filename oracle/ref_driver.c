@@ -727,7 +727,7 @@ static void prove_fs_range(void *c, size_t lo, size_t hi) {
   size_t mark0 = arena_mark();
   ref_ctx_t ctx;
   ctx_build(&ctx, x->circuit, x->g1s, x->srs_len, x->g2);
-  const uint32_t seed = fs_seed(x->circuit, x->g1s, x->srs_len, x->g2);
+  const fs_state seed = fs_seed(x->circuit, x->g1s, x->srs_len, x->g2);
   size_t mark = arena_mark();
   for (size_t i = lo; i < hi; i++) {
     HF a[4], b[4], cc[4], rnd[9];
@@ -742,7 +742,7 @@ static void prove_fs_range(void *c, size_t lo, size_t hi) {
     uint8_t known[6] = {0, 0, 0, 0, 0, 0};
     uint8_t rec[34];            /* the transcript's view of the PROOF record, filled stage by stage */
     uint8_t *o = x->proofs + 34 * i;
-    uint32_t st = seed;
+    fs_state st = seed;
     int stage = 0;              /* rounds whose challenges are fixed: 0 none, 1 beta/gamma, 2 alpha, 3 z, 4 v */
     memset(rec, 0, sizeof rec);
     for (;;) {
@@ -801,12 +801,15 @@ void ref_plonk_prove_fs_batch(const uint8_t *circuit, const uint8_t *g1s, uint32
   prove_fs_ctx c = {circuit, g1s, srs_len, g2, wit, rnd, proofs, status, chal};
   run_ranges(prove_fs_range, &c, n, nthreads);
 }
-uint32_t ref_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2) {
-  return fs_seed(circuit, g1s, srs_len, g2);
+void ref_fs_seed(const uint8_t *circuit, const uint8_t *g1s, uint32_t srs_len, const uint8_t *g2, uint32_t out[4]) {
+  const fs_state st = fs_seed(circuit, g1s, srs_len, g2);
+  memcpy(out, st.v, sizeof st.v);
 }
 /* the verifier's side of the transcript: all six challenges from complete PROOF records */
-void ref_fs_derive(uint32_t seed, const uint8_t *proofs, size_t n, uint8_t *chal6) {
-  for (size_t i = 0; i < n; i++) fs_derive(seed, proofs + 34 * i, chal6 + 6 * i);
+void ref_fs_derive(const uint32_t seed[4], const uint8_t *proofs, size_t n, uint8_t *chal6) {
+  fs_state st;
+  memcpy(st.v, seed, sizeof st.v);
+  for (size_t i = 0; i < n; i++) fs_derive(st, proofs + 34 * i, chal6 + 6 * i);
 }
 
 /* --------------------------- verifier: NOT in the reference (plonk.h:656-659).  Parity unpinned.

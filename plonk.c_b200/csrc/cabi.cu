@@ -1268,7 +1268,7 @@ int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, cons
 }
 
 // ---- Fiat-Shamir mode (transcript.cuh; specification oracle/fs_spec.inc)
-int pb_ctx_fs_seed(const pb_ctx* ctx, uint32_t* out) { ARG(ctx && out); *out = ctx->cc.fs_seed; return PB_OK; }
+int pb_ctx_fs_seed(const pb_ctx* ctx, uint32_t out[4]) { ARG(ctx && out); memcpy(out, ctx->cc.fs_seed.v, 16); return PB_OK; }
 int pb_plonk_prove_fs_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, uint8_t* proofs, uint8_t* status,
                           uint8_t* chal_out, size_t n, void* stream) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer

@@ -41,7 +41,7 @@ struct CircuitConst {
   uint32_t l1[4];       // L1(x) = interpolate([1,0,0,0])                                 (plonk.h:390-391)
   uint32_t srs_len;     // SRS.len (srs.h:13)
   uint32_t bad_copy;    // a COPY_OF.type outside {A,B,C}: every proof exits at plonk.h:155-157
-  uint32_t fs_seed;     // Fiat-Shamir mode only: initial transcript state (transcript.cuh)
+  FsState fs_seed;      // Fiat-Shamir mode only: the transcript state after absorbing circuit and SRS (transcript.cuh)
 };
 
 // Tables that are indexed per lane (so they live in shared memory, not in the constant bank).

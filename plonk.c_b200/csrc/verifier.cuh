@@ -6,6 +6,7 @@
 #pragma once
 #include <type_traits>
 #include "curve.cuh"
+#include "transcript.cuh"
 #include "prover.cuh"   // pack_g1 / unpack_g1
 
 namespace pb {
@@ -15,7 +16,7 @@ struct VerifyKey {
   G1 qm, ql, qr, qo, qc, s1, s2, s3;   // srs_eval_at_s of the interpolated selector / permutation polynomials
   G1 g1_one;                           // srs.g1s[0]
   G2 g2_one, g2_s;                     // srs.g2_1, srs.g2_s
-  uint32_t fs_seed;                    // Fiat-Shamir mode only: initial transcript state (transcript.cuh)
+  FsState fs_seed;                     // Fiat-Shamir mode only: the transcript state after absorbing circuit and SRS (transcript.cuh)
 };
 
 struct VerifyOut {

@@ -506,9 +506,10 @@ class Plonk:
 
     # ---- Fiat-Shamir mode (include/plonk_b200.h; specification oracle/fs_spec.inc)
     def fs_seed(self):
-        out = C.c_uint32()
-        _check(lib().pb_ctx_fs_seed(self._h, C.byref(out)))
-        return int(out.value)
+        """the transcript state after absorbing circuit and SRS, as one int: v0 | v1 << 32 | v2 << 64 | v3 << 96"""
+        out = np.zeros(4, np.uint32)
+        _check(lib().pb_ctx_fs_seed(self._h, out.ctypes.data_as(C.c_void_p)))
+        return sum(int(w) << (32 * k) for k, w in enumerate(out))
 
     def prove_fs(self, witness, rnd, want_challenges=False):
         """-> (proofs[n][34], status[n]) and, on request, chal[n][6] = alpha beta gamma z v u (0xFF where not drawn)."""

@@ -40,7 +40,8 @@ np.savez_compressed(os.path.join(HERE, "protocol.npz"), **out)
 out = {}
 for mode, mk in list(util.SRS_MODES.items()) + [("garbage10", lambda W: util.garbage_srs())]:
     g1s, g2 = mk(W)
-    out[mode + "_seed"] = np.array([R.fs_seed(C, g1s, g2)], np.uint32)
+    seed = R.fs_seed(C, g1s, g2)                          # four 32-bit words as one int
+    out[mode + "_seed"] = np.array([(seed >> (32 * k)) & 0xFFFFFFFF for k in range(4)], np.uint32)
     for var in ("U17", "NZ"):
         wit, rnd, _, _ = W.make_batch(78, 0, N, var)
         wit[0], rnd[0] = W.GOLDEN_WITNESS[0], W.GOLDEN_RAND[0]

@@ -179,8 +179,13 @@ void hc_prove_wide(const uint32_t* cc_words, const uint32_t* table, const uint8_
   tb.T3 = store.data() + 2u * (size_t)WIDE_T3_ENTRIES;
   prove_batch(cc, tb, wit, rnd, chal, proofs, status, chal_out, n);
 }
-uint32_t hc_fs_seed(const uint8_t* circuit, const uint8_t* g1s, uint32_t srs_len, const uint8_t* g2) { return fs_seed_host(circuit, g1s, srs_len, g2); }
-void hc_fs_challenges(uint32_t seed, const uint8_t* proofs, uint8_t* chal6, size_t n) {
+void hc_fs_seed(const uint8_t* circuit, const uint8_t* g1s, uint32_t srs_len, const uint8_t* g2, uint32_t out[4]) {
+  const FsState st = fs_seed_host(circuit, g1s, srs_len, g2);
+  memcpy(out, st.v, 16);
+}
+void hc_fs_challenges(const uint32_t seed4[4], const uint8_t* proofs, uint8_t* chal6, size_t n) {
+  FsState seed;
+  memcpy(seed.v, seed4, 16);
   for (size_t i = 0; i < n; i++) {
     uint32_t pbv[27], op[7], ch[5], u;
     for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
@@ -192,8 +197,10 @@ void hc_fs_challenges(uint32_t seed, const uint8_t* proofs, uint8_t* chal6, size
 }
 // fast-path verifier: tables built exactly as verify_tables_kernel does, from g1_mul rows of the nine key points
 // chal NULL = Fiat-Shamir mode (challenges and u from the proof bytes, transcript seeded with fs_seed)
-void hc_verify_fast(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+void hc_verify_fast(const uint8_t* key, const uint32_t seed4[4], const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   FieldTables ft = make_ft();
+  FsState fs_seed;
+  memcpy(fs_seed.v, seed4, 16);
   VerifyKey k;
   G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
   for (int j = 0; j < 9; j++) *dst[j] = ld(key + 3 * j);
@@ -359,8 +366,10 @@ int hc_bounds_checked() {
 }
 int hc_sizeof_cc() { return (int)sizeof(CircuitConst); }
 // key: 9 G1 as bytes [27] + g2[4]
-void hc_verify(const uint8_t* key, uint32_t fs_seed, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+void hc_verify(const uint8_t* key, const uint32_t seed4[4], const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
   FieldTables ft = make_ft();
+  FsState fs_seed;
+  memcpy(fs_seed.v, seed4, 16);
   VerifyKey k;
   G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
   for (int j = 0; j < 9; j++) *dst[j] = ld(key + 3 * j);

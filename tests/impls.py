@@ -238,13 +238,19 @@ class HostcheckImpl:
 
     def fs_seed(self, circuit, g1s, g2):
         circuit, g1s, g2 = (np.ascontiguousarray(x, np.uint8) for x in (circuit, g1s, g2))
-        self.lib.hc_fs_seed.restype = C.c_uint32
-        return int(self.lib.hc_fs_seed(_p(circuit), _p(g1s), C.c_uint32(g1s.shape[0]), _p(g2)))
+        out = np.zeros(4, np.uint32)
+        self.lib.hc_fs_seed(_p(circuit), _p(g1s), C.c_uint32(g1s.shape[0]), _p(g2), out.ctypes.data_as(C.c_void_p))
+        return sum(int(w) << (32 * k) for k, w in enumerate(out))
+
+    @staticmethod
+    def _seed_words(seed):
+        return np.array([(int(seed) >> (32 * k)) & 0xFFFFFFFF for k in range(4)], np.uint32)
 
     def fs_challenges(self, circuit, g1s, g2, proofs):
         proofs = np.ascontiguousarray(proofs, np.uint8)
         out = np.zeros((proofs.shape[0], 6), np.uint8)
-        self.lib.hc_fs_challenges(C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), _p(out), C.c_size_t(proofs.shape[0]))
+        sw = self._seed_words(self.fs_seed(circuit, g1s, g2))
+        self.lib.hc_fs_challenges(sw.ctypes.data_as(C.c_void_p), _p(proofs), _p(out), C.c_size_t(proofs.shape[0]))
         return out
 
     def _prove_fn(self):
@@ -268,7 +274,7 @@ class HostcheckImpl:
         SP, _ = o.interpolate_at_h(sig)
         vinv = o.plonk_setup_dump()["h_pows_inv"]
         l1, _ = o.interpolate_at_h(np.array([[1, 0, 0, 0]], np.uint8))
-        w = np.concatenate([qv.ravel(), QP.ravel(), sig.ravel(), SP.ravel(), vinv.ravel(), l1.ravel(), [srs_len, 0, fs_seed]]).astype(np.uint32)
+        w = np.concatenate([qv.ravel(), QP.ravel(), sig.ravel(), SP.ravel(), vinv.ravel(), l1.ravel(), [srs_len, 0], self._seed_words(fs_seed)]).astype(np.uint32)
         assert w.size * 4 == self.lib.hc_sizeof_cc()
         return np.ascontiguousarray(w)
 
@@ -307,7 +313,7 @@ class HostcheckImpl:
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt
 
     def plonk_verdict_only(self, circuit, g1s, g2, proofs, chal, u):
@@ -315,7 +321,7 @@ class HostcheckImpl:
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict = np.zeros(n, np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(0), _p(proofs), _p(chal), _p(u), _p(verdict), None, C.c_size_t(n))
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), None, C.c_size_t(n))
         return verdict
 
     def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
@@ -323,6 +329,6 @@ class HostcheckImpl:
         proofs = np.ascontiguousarray(proofs, np.uint8)
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), C.c_uint32(self.fs_seed(circuit, g1s, g2)), _p(proofs), None, None,
+        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(self.fs_seed(circuit, g1s, g2)).ctypes.data_as(C.c_void_p), _p(proofs), None, None,
                                                                       _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt

@@ -331,7 +331,7 @@ def check_fiat_shamir_golden(impl, W, n=2048):
     C = W.PLONK_TEST_CIRCUIT
     for mode in list(util.SRS_MODES) + ["garbage10"]:
         g1s, g2 = p[mode + "_g1s"], p[mode + "_g2"]
-        assert impl.fs_seed(C, g1s, g2) == int(g[mode + "_seed"][0]), f"golden fs_seed {mode}"
+        assert impl.fs_seed(C, g1s, g2) == sum(int(w) << (32 * k) for k, w in enumerate(g[mode + "_seed"])), f"golden fs_seed {mode}"
         for var in ("U17", "NZ"):
             wit, rnd, _, _ = W.make_batch(78, 0, n, var)
             wit[0], rnd[0] = W.GOLDEN_WITNESS[0], W.GOLDEN_RAND[0]
