@@ -900,11 +900,7 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
       co[5] = k5 ? (uint8_t)o.ch[5] : 0xFF;
     }
   }
-#ifdef PB_DEBUG_KEEP
-  const bool okp = true;
-#else
   const bool okp = o.status == 0u;     // a failed item's PROOF bytes are zero
-#endif
   // dense list of the completed proofs: the atomic is issued first and its result used last, so that the round trip to L2
   // overlaps the writing of the record (it was 2.7 % of the kernel's stall samples when the warp waited for it on the spot)
   const bool done = live && okp;
