@@ -12,8 +12,9 @@ on-device tally of statuses / verdicts / proof checksum.
 
 value   proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
 e2e     proofs/s through a public host-pointer call, pinned host buffers in and out, H2D and D2H copies inside the
-        timed region.  Three calls are measured, same items, same step count:
-          e2e          pb_plonk_prove_verify_packed   packed wire v2: 16 B in, 22 B per completed proof + 1 B per item out
+        timed region.  Four calls are measured, same items, same step count:
+          e2e            pb_plonk_prove_verify_packed3  packed wire v3: 14 B in, 12 B per completed proof + 1 B per item out
+          e2e_packed_v2  pb_plonk_prove_verify_packed   packed wire v2: 16 B in, 22 B per completed proof + 1 B per item out
           e2e_compact  pb_plonk_prove_verify_compact  the reference's structs in (27 B), only the proofs that exist out
           e2e_struct   pb_plonk_prove_verify          the reference's structs both ways (27 B in, 36 B out; round 1's e2e)
 seeded  proofs/s of pb_plonk_prove_verify_seeded_dev: inputs generated on the device from (seed, start, count), only the
@@ -432,6 +433,9 @@ def run_b200(args):
     np_in = [t.numpy() for t in pin]
     np_out = [t.numpy() for t in hout]
     np_packed_in, np_packed_out = pin_packed.numpy(), [t.numpy() for t in hpacked]
+    pin_packed3 = torch.from_numpy(wire.pack_inputs3(*host_in)).pin_memory()
+    hpacked3 = [torch.empty((n, 12), dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()]
+    np_packed3_in, np_packed3_out = pin_packed3.numpy(), [t.numpy() for t in hpacked3]
     e2e_steps = min(args.steps, 20)
     done_box = [0]
 
@@ -458,6 +462,13 @@ def run_b200(args):
     if not (n_done == int((ref_s == 0).sum()) and np.array_equal(np_packed_out[0][:n_done], wire.pack_proofs(ref_p[ref_s == 0]))
             and np.array_equal(np_packed_out[1], wire.make_sv(ref_s, ref_v))):
         raise SystemExit("bench.py: packed host-pointer path and device path disagree")
+
+    def run_packed3():
+        done_box[0] = pk.prove_verify_packed3_into(np_packed3_in, *np_packed3_out)
+    packed3_ms, packed3_each = e2e_time(run_packed3)
+    if not (done_box[0] == n_done and np.array_equal(np_packed3_out[0][:n_done], wire.pack_proofs3(ref_p[ref_s == 0]))
+            and np.array_equal(np_packed3_out[1], wire.make_sv(ref_s, ref_v))):
+        raise SystemExit("bench.py: packed v3 host-pointer path and device path disagree")
 
     def run_compact():
         done_box[0] = pk.prove_verify_compact_into(*np_in, *np_out)
@@ -540,7 +551,12 @@ def run_b200(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
         "per_rank_ms_per_step": rank_stats(per_rank),
-        "e2e": e2e_entry(packed_ms, packed_each, "pb_plonk_prove_verify_packed (host pointers, pinned; packed wire v2, csrc/wire.cuh)",
+        "e2e": e2e_entry(packed3_ms, packed3_each, "pb_plonk_prove_verify_packed3 (host pointers, pinned; packed wire v3, csrc/wire.cuh)",
+                         n * 14, n + n_done * 12,
+                         "14 B in (27 base-17 digits in 112 bits); out: 12 B per completed proof (dense, item order; the nine commitments as 7-bit "
+                         "indices into the 102 points of the curve, the seven openings as digits) + 1 status/verdict byte per item; same "
+                         "information as the struct arrays (pb_wire3_* / wire.py convert); d2h bytes are rank 0's (data-dependent)"),
+        "e2e_packed_v2": e2e_entry(packed_ms, packed_each, "pb_plonk_prove_verify_packed (host pointers, pinned; packed wire v2, csrc/wire.cuh)",
                          n * 16, n + n_done * 22,
                          "16 B in; out: 22 B per completed proof (dense, item order) + 1 status/verdict byte per item; same information as "
                          "the struct arrays (pb_wire_* / wire.py convert); d2h bytes are rank 0's (data-dependent)"),

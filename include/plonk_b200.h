@@ -300,6 +300,27 @@ int pb_wire_unpack_proofs(const uint8_t *packed, uint8_t *proofs, size_t n);
 int pb_wire_scatter_proofs(const uint8_t *proofs_dense, const uint8_t *status, uint8_t *proofs, size_t n);
 int pb_wire_split_sv(const uint8_t *sv, uint8_t *status /* optional */, uint8_t *verdict /* optional */, size_t n);
 
+/* Packed wire v3 (layout: csrc/wire.cuh; Python twin: plonk.c_b200/wire.py): the same information in 14 B in and 12 B per
+ * COMPLETED proof out (+ the sv byte per item).  Input record = three little-endian u32 + one little-endian u16: bits 0..28
+ * of word k are values 7k..7k+6 as base-17 digits; G = alpha + 17 beta + ... + 17^5 u < 2^25 has its low 16 bits in the u16
+ * and bits 16+3k..18+3k in bits 29..31 of word k.  Proof record = three little-endian u32; a commitment travels as the
+ * 7-bit INDEX of its point in the list of the 102 points of E(F_101) (0 = infinity, then by (x, y)): word k = three
+ * indices | (opening 2k + 17 opening 2k+1) << 21 | two bits of the seventh opening << 30.  Only for contexts whose SRS
+ * points are canonical points of the curve (both benchmark SRS modes; otherwise PB_ERR_ARG: use v2) -- every
+ * commitment is then on the curve.  pb_wire3_pack_proofs refuses records with a point off the curve. */
+#define PB_PACKED3_IN_BYTES 14
+#define PB_PACKED3_PROOF_BYTES 12
+int pb_plonk_prove_verify_packed3(const pb_ctx *ctx, const uint8_t *packed_in, uint8_t *packed_proofs /* capacity n x 12 */,
+                                  size_t *n_done, uint8_t *sv, size_t n);
+/* workspace: pb_packed_workspace_bytes(n) */
+int pb_plonk_prove_verify_packed3_dev(const pb_ctx *ctx, const uint8_t *packed_in, uint8_t *packed_proofs,
+                                      uint32_t *n_done_dev, uint8_t *sv, void *workspace, size_t n, void *stream);
+int pb_wire3_pack_inputs(const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal, const uint8_t *u, uint8_t *packed, size_t n);
+int pb_wire3_unpack_inputs(const uint8_t *packed, uint8_t *witness, uint8_t *rnd, uint8_t *chal, uint8_t *u,
+                           uint8_t *valid /* optional */, size_t n);
+int pb_wire3_pack_proofs(const uint8_t *proofs, uint8_t *packed, size_t n);
+int pb_wire3_unpack_proofs(const uint8_t *packed, uint8_t *proofs, size_t n);
+
 /* Seeded mode (SURVEY.md sections 7.4 / 8(e)): items [start, start + count) of the synthetic stream `seed` are generated
  * on the device (draw j of item i = splitmix64(seed + 16 i + j): witness row, nine blinding scalars, five challenges, u;
  * variant 0 = "U17", 1 = "NZ"; plonk.c_b200/workload.py make_batch is the host twin), proved, verified and tallied there;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -65,8 +66,19 @@ struct Dev {
 #define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
 constexpr size_t PIPE_CHUNK_MAX = 1u << 20;   // largest chunk of the host-pointer pipelines
-constexpr int PIPE_SLOTS = 6;
-constexpr int PIPE_LOOKAHEAD = 3;             // compact / packed modes: chunks enqueued ahead of the one whose count the host waits for
+#ifndef PB_PIPE_TWO_STREAMS
+#define PB_PIPE_TWO_STREAMS 1
+#endif
+#ifndef PB_PIPE_SLOTS
+#define PB_PIPE_SLOTS 8
+#endif
+#ifndef PB_PIPE_LOOKAHEAD
+#define PB_PIPE_LOOKAHEAD 6
+#endif
+constexpr size_t PIPE_TAIL_MIN = 1u << 17;       // smallest chunk of the schedule's tail (PB_PIPE_SMALL overrides, for tuning)
+constexpr int PIPE_SLOTS = PB_PIPE_SLOTS;
+constexpr int PIPE_LOOKAHEAD = PB_PIPE_LOOKAHEAD;   // compact / packed modes: chunks enqueued ahead of the one whose count the host waits for
+static_assert(PIPE_LOOKAHEAD >= 1 && PIPE_LOOKAHEAD < PIPE_SLOTS, "the D2H copy of a slot's previous chunk must be enqueued before the slot is reused");
 // items per pipeline chunk of the host-pointer prove/verify (PB_PIPE_CHUNK overrides, for tuning; multiple of 128)
 size_t pipe_chunk() {
   static size_t v = [] {
@@ -85,7 +97,7 @@ struct PipeSlot {
   uint8_t* dense = nullptr;    // [cap * 34 + 16]: completed proofs only (compact / packed outputs)
   uint32_t* offs = nullptr;    // [cap / 128 + 4]: group offsets of the dense list; the last word is the chunk's count
 };
-enum PipeMode { PIPE_PROVE = 0, PIPE_STRUCT = 1, PIPE_COMPACT = 2, PIPE_PACKED = 3 };
+enum PipeMode { PIPE_PROVE = 0, PIPE_STRUCT = 1, PIPE_COMPACT = 2, PIPE_PACKED = 3, PIPE_PACKED3 = 4 };
 
 }  // namespace
 
@@ -116,7 +128,7 @@ struct pb_ctx {
   std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
   std::mutex pipe_mu;
   bool pipe_ready = false;            // streams and events exist
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;       // H2D engine, SMs, D2H engine
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr;   // H2D engine, SMs (even / odd chunks), D2H engine
   uint8_t *d_u = nullptr, *d_status = nullptr, *d_verdict = nullptr, *d_sv = nullptr;   // whole-batch one-byte arrays of the host-pointer pipelines
   size_t small_cap = 0;
   size_t slot_cap = 0;                // items each slot's buffers hold
@@ -173,6 +185,7 @@ int pipe_init(pb_ctx* c, size_t cap) {
   if (!c->pipe_ready) {
     if (!c->s_in) CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     if (!c->s_k) CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+    if (!c->s_k2) CU(cudaStreamCreateWithFlags(&c->s_k2, cudaStreamNonBlocking));
     if (!c->s_out) CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     for (auto& s : c->slots) {
       if (!s.ev_in) CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
@@ -187,7 +200,7 @@ int pipe_init(pb_ctx* c, size_t cap) {
   }
   cap = (cap + 4095) & ~(size_t)4095;
   if (c->slot_cap >= cap) return PB_OK;
-  CU(cudaStreamSynchronize(c->s_in)); CU(cudaStreamSynchronize(c->s_k)); CU(cudaStreamSynchronize(c->s_out));
+  CU(cudaStreamSynchronize(c->s_in)); CU(cudaStreamSynchronize(c->s_k)); CU(cudaStreamSynchronize(c->s_k2)); CU(cudaStreamSynchronize(c->s_out));
   c->slot_cap = 0;
   for (auto& s : c->slots) {
     for (void** p : {reinterpret_cast<void**>(&s.in), reinterpret_cast<void**>(&s.proofs), reinterpret_cast<void**>(&s.dense),
@@ -1104,7 +1117,7 @@ int pb_ctx_destroy(pb_ctx* c) {
     void* bufs[4] = {s.in, s.proofs, s.dense, s.offs};
     for (auto b : bufs) if (b) cudaFree(b);
   }
-  for (cudaStream_t st : {c->s_in, c->s_k, c->s_out}) if (st) cudaStreamDestroy(st);
+  for (cudaStream_t st : {c->s_in, c->s_k, c->s_k2, c->s_out}) if (st) cudaStreamDestroy(st);
   for (uint8_t* p : {c->d_u, c->d_status, c->d_verdict, c->d_sv, c->d_wtab, c->d_seed_ws}) if (p) cudaFree(p);
   if (c->h_count) cudaFreeHost(c->h_count);
   delete c;
@@ -1161,12 +1174,12 @@ int pb_constraints_satisfy_rows(const uint8_t* selectors, uint32_t rows, const u
 // packed != nullptr selects the packed-input instantiation (wire.cuh): witness / rnd / chal are not read
 static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, uint8_t* proofs, uint8_t* status,
                         size_t n, cudaStream_t st, uint32_t* done_list, uint32_t* done_count, uint8_t* verdict, uint8_t* chal_out = nullptr,
-                        const uint8_t* packed = nullptr) {
+                        const uint8_t* packed = nullptr, int wire3 = 0) {
   const bool pair = ctx->srs_canonical && !ctx->force_exact;
   const bool wide = pair && ctx->d_wide_tables != nullptr;
   const unsigned grid = blocks_for(n, PBLOCK);
 #define PB_LAUNCH_PROVE(TABLES, FSMODE, PK, TB, W, CH, CO) \
-  prove_kernel<TABLES, FSMODE, PK><<<grid, PBLOCK, 0, st>>>(ctx->cc, TB, W, rnd, CH, proofs, status, n, done_list, done_count, verdict, CO)
+  prove_kernel<TABLES, FSMODE, PK><<<grid, PBLOCK, 0, st>>>(ctx->cc, TB, W, rnd, CH, proofs, status, n, done_list, done_count, verdict, CO, wire3)
   if (packed) {
     if (wide) PB_LAUNCH_PROVE(ProverWideTables, false, true, ctx->d_wide_tables, packed, nullptr, nullptr);
     else if (pair) PB_LAUNCH_PROVE(ProverPairTables, false, true, ctx->d_pair_tables, packed, nullptr, nullptr);
@@ -1186,13 +1199,13 @@ static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t
 }
 static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
                          const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st,
-                         const uint8_t* packed = nullptr) {
+                         const uint8_t* packed = nullptr, int wire3 = 0) {
   const uint32_t* pk = reinterpret_cast<const uint32_t*>(packed);
   if (ctx->key_canonical && !ctx->force_exact && !(status && !done_list))
-    if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n, pk);
-    else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk);
+    if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3);
+    else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3);
   else
-    verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n, pk);
+    verify_kernel<<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, proofs, chal, u, status, verdict, gt, n, pk, wire3);
   LAUNCH_CHECK("verify_kernel");
   return PB_OK;
 }
@@ -1240,7 +1253,7 @@ int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const u
 // chal == u == nullptr: Fiat-Shamir mode; packed != nullptr: packed input records instead of witness / rnd / chal / u
 static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                             uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event,
-                            const uint8_t* packed = nullptr) {
+                            const uint8_t* packed = nullptr, int wire3 = 0) {
   ARG(verdict);
   ARG(ctx && ctx->vk_valid);
   { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
@@ -1255,9 +1268,9 @@ static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uin
   int rc = scratch_for(ctx, st, n, &scratch);
   if (rc) return rc;
   CU(cudaMemsetAsync(scratch, 0, 4 * sizeof(uint32_t), st));
-  rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict, nullptr, packed);
+  rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict, nullptr, packed, wire3);
   if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
-  if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st, packed);
+  if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st, packed, wire3);
   return rc;
 }
 int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
@@ -1301,12 +1314,13 @@ int pb_fs_challenges_dev(const pb_ctx* ctx, const uint8_t* proofs, uint8_t* chal
 
 // dense list of the completed proofs of a chunk (stream-ordered): offs[0 .. groups) and the count in offs[cap / 128 + 3]
 static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uint8_t* verdict, size_t m, uint32_t* offs, uint32_t* count,
-                         uint8_t* dense, uint8_t* sv, bool pack, cudaStream_t st, uint32_t* count_host = nullptr) {
+                         uint8_t* dense, uint8_t* sv, int pack /*0 structs, 1 packed v2, 2 packed v3*/, cudaStream_t st, uint32_t* count_host = nullptr) {
   done_counts_kernel<<<blocks_for((m + GBLOCK - 1) / GBLOCK, 256), 256, 0, st>>>(status, m, offs);
   done_offsets_kernel<<<1, 1024, 0, st>>>(m, offs, count, count_host);
   LAUNCH_CHECK("done_offsets_kernel");
-  if (pack) gather_done_kernel<true><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
-  else gather_done_kernel<false><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
+  if (pack == 2) gather_done_kernel<2><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
+  else if (pack == 1) gather_done_kernel<1><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
+  else gather_done_kernel<0><<<blocks_for(m, GBLOCK), GBLOCK, 0, st>>>(proofs, status, verdict, m, offs, dense, sv);
   LAUNCH_CHECK("gather_done_kernel");
   return PB_OK;
 }
@@ -1323,7 +1337,8 @@ static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uin
 // Modes (PipeMode): PROVE / STRUCT move the reference's structs both ways (27 B in, 34 + 2 B out per item).
 // COMPACT: struct inputs; only the proofs that exist come back -- the completed ones, dense, in item order (the zero
 // records of items on which the reference exits do not travel).  PACKED: packed wire v2 both ways (wire.cuh: 16 B in,
-// 22 B per completed proof + 1 B per item out).  In the last two the size of a chunk's D2H copy is known only when its
+// 22 B per completed proof + 1 B per item out); PACKED3: packed wire v3 (14 B in, 12 B per completed proof + 1 B per item
+// out; SRS on the curve only).  In the dense modes the size of a chunk's D2H copy is known only when its
 // kernels have run: the host waits for chunk c - PIPE_LOOKAHEAD's kernels (the GPU has the chunks in between queued),
 // reads the count from pinned memory and issues that chunk's copy.
 static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
@@ -1342,29 +1357,32 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     CU(cudaMalloc(&ctx->d_u, cap)); CU(cudaMalloc(&ctx->d_status, cap)); CU(cudaMalloc(&ctx->d_verdict, cap)); CU(cudaMalloc(&ctx->d_sv, cap));
     ctx->small_cap = cap;
   }
-  const bool packed = mode == PIPE_PACKED, dense = mode == PIPE_COMPACT || mode == PIPE_PACKED;
-  const size_t rec = packed ? PACKED_PROOF_BYTES : 34;
-  // Chunk schedule: fill (first H2D + first kernels) and drain (last D2H) are exposed time, so the first and last chunks
-  // are small and the sizes double towards the middle, where chunks have the full size pipe_chunk().
+  const bool wire3 = mode == PIPE_PACKED3, packed = mode == PIPE_PACKED || wire3, dense = mode == PIPE_COMPACT || packed;
+  const size_t rec = wire3 ? PACKED3_PROOF_BYTES : packed ? PACKED_PROOF_BYTES : 34;
+  const size_t rec_in = wire3 ? PACKED3_IN_BYTES : PACKED_IN_BYTES;
+  // Chunk schedule.  The H2D engine is the stage that is busy from the first byte to the last, so what is exposed is the
+  // time AFTER the last input byte has landed: the last chunk's kernels and its D2H copy.  Full-size chunks first (large
+  // copies run at the link's rate, profiles/r1/pcie_probe.txt), then a tail that halves down to PIPE_TAIL_MIN items.
+  // PB_PIPE_RAMP_UP=1 also ramps the head up from PIPE_TAIL_MIN (round 1's symmetric schedule).
   std::vector<size_t> sched;
   {
-    const size_t small = 1u << 15;
+    static const size_t small_env = getenv("PB_PIPE_SMALL") ? strtoull(getenv("PB_PIPE_SMALL"), nullptr, 10) & ~(size_t)127 : 0;
+    static const bool ramp_up = getenv("PB_PIPE_RAMP_UP") && getenv("PB_PIPE_RAMP_UP")[0] == '1';
+    const size_t small = small_env >= 128 ? small_env : PIPE_TAIL_MIN;
     const size_t ragged = n % 128;          // every chunk but the very last starts at a multiple of 128 items (16-byte aligned slices)
-    size_t head = small, left = n - ragged;
-    std::vector<size_t> tail;
-    while (left > 0) {
-      if (left <= 2 * head || head >= chunk) break;
-      sched.push_back(head);
-      tail.push_back(head);
-      left -= 2 * head;
-      head *= 2;
-    }
+    size_t left = n - ragged;
+    std::vector<size_t> tail;               // ascending
+    for (size_t t = small; t < chunk && left > 2 * t; t *= 2) { tail.push_back(t); left -= t; }
+    if (ramp_up)
+      for (size_t t = small; t < chunk && left > 2 * t; t *= 2) { sched.push_back(t); left -= t; }
     while (left > 0) { size_t m = left < chunk ? left : chunk; sched.push_back(m); left -= m; }
     for (size_t k = tail.size(); k-- > 0;) sched.push_back(tail[k]);
     if (ragged) sched.push_back(ragged);
   }
   // PB_PIPE_TRACE=1: print, per chunk, when its inputs landed / its kernels finished / its proofs were copied out
-  static const bool trace = getenv("PB_PIPE_TRACE") && getenv("PB_PIPE_TRACE")[0] == '1';
+  // PB_PIPE_TRACE=2: only the host-side line (no events between the stages, which cost API calls of their own)
+  static const int trace_level = getenv("PB_PIPE_TRACE") ? atoi(getenv("PB_PIPE_TRACE")) : 0;
+  const bool trace = trace_level == 1;
   std::vector<cudaEvent_t> tev;
   cudaEvent_t t0 = nullptr;
   if (trace) {
@@ -1387,6 +1405,9 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     return PB_OK;
   };
   size_t done = 0, c = 0;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+  double host_enq = 0;
   for (size_t m : sched) {
     if (dense && c >= (size_t)PIPE_LOOKAHEAD && (rc = finish(c - PIPE_LOOKAHEAD))) return rc;
     PipeSlot& s = ctx->slots[c % PIPE_SLOTS];
@@ -1394,7 +1415,7 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     uint8_t *d_wit = s.in, *d_rnd = s.in + ctx->slot_cap * 12, *d_chal = s.in + ctx->slot_cap * 21;
     if (reuse) CU(cudaStreamWaitEvent(ctx->s_in, s.ev_k, 0));
     if (packed) {
-      CU(cudaMemcpyAsync(s.in, witness + done * PACKED_IN_BYTES, m * PACKED_IN_BYTES, cudaMemcpyHostToDevice, ctx->s_in));
+      CU(cudaMemcpyAsync(s.in, witness + done * rec_in, m * rec_in, cudaMemcpyHostToDevice, ctx->s_in));
     } else {
       CU(cudaMemcpyAsync(d_wit, witness + done * 12, m * 12, cudaMemcpyHostToDevice, ctx->s_in));
       CU(cudaMemcpyAsync(d_rnd, rnd + done * 9, m * 9, cudaMemcpyHostToDevice, ctx->s_in));
@@ -1403,26 +1424,29 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     }
     CU(cudaEventRecord(s.ev_in, ctx->s_in));
     if (trace) CU(cudaEventRecord(tev[3 * c], ctx->s_in));
-    CU(cudaStreamWaitEvent(ctx->s_k, s.ev_in, 0));
-    if (reuse) CU(cudaStreamWaitEvent(ctx->s_k, s.ev_out, 0));
+    // Two compute streams, chunks alternating: the latency-bound tail of one chunk (the last wave of its kernels, the small
+    // count / offset / gather launches and the gaps between dependent launches) overlaps the next chunk's prover.
+    cudaStream_t sk = PB_PIPE_TWO_STREAMS && (c & 1) ? ctx->s_k2 : ctx->s_k;
+    CU(cudaStreamWaitEvent(sk, s.ev_in, 0));
+    if (reuse) CU(cudaStreamWaitEvent(sk, s.ev_out, 0));
     if (packed)
-      rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, ctx->s_k, nullptr, s.in);
+      rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, sk, nullptr, s.in, wire3);
     else if (mode != PIPE_PROVE)
       rc = prove_verify_dev(ctx, d_wit, d_rnd, chal ? d_chal : nullptr, u ? ctx->d_u + done : nullptr, s.proofs, ctx->d_status + done,
-                            ctx->d_verdict + done, m, ctx->s_k, nullptr);
+                            ctx->d_verdict + done, m, sk, nullptr);
     else if (chal)
-      rc = pb_plonk_prove_dev(ctx, d_wit, d_rnd, d_chal, s.proofs, ctx->d_status + done, m, ctx->s_k);
+      rc = pb_plonk_prove_dev(ctx, d_wit, d_rnd, d_chal, s.proofs, ctx->d_status + done, m, sk);
     else
-      rc = pb_plonk_prove_fs_dev(ctx, d_wit, d_rnd, s.proofs, ctx->d_status + done, nullptr, m, ctx->s_k);
+      rc = pb_plonk_prove_fs_dev(ctx, d_wit, d_rnd, s.proofs, ctx->d_status + done, nullptr, m, sk);
     if (rc) return rc;
     if (dense) {
       uint32_t* cnt = s.offs + ctx->slot_cap / 128 + 3;
       // the count also lands in mapped pinned memory (a store by the kernel, not a copy queued behind the D2H engine's proofs)
-      if ((rc = launch_gather(s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.offs, cnt, s.dense, ctx->d_sv + done, packed, ctx->s_k,
+      if ((rc = launch_gather(s.proofs, ctx->d_status + done, ctx->d_verdict + done, m, s.offs, cnt, s.dense, ctx->d_sv + done, wire3 ? 2 : packed ? 1 : 0, sk,
                               ctx->h_count_dev + c % PIPE_SLOTS))) return rc;
     }
-    CU(cudaEventRecord(s.ev_k, ctx->s_k));
-    if (trace) CU(cudaEventRecord(tev[3 * c + 1], ctx->s_k));
+    CU(cudaEventRecord(s.ev_k, sk));
+    if (trace) CU(cudaEventRecord(tev[3 * c + 1], sk));
     if (!dense) {
       CU(cudaStreamWaitEvent(ctx->s_out, s.ev_k, 0));
       CU(cudaMemcpyAsync(proofs + done * 34, s.proofs, m * 34, cudaMemcpyDeviceToHost, ctx->s_out));
@@ -1432,11 +1456,13 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
     done += m;
     c++;
   }
+  host_enq = host_ms();
   if (dense)
     for (size_t k = c > (size_t)PIPE_LOOKAHEAD ? c - PIPE_LOOKAHEAD : 0; k < c; k++)
       if ((rc = finish(k))) return rc;
-  // s_out is ordered after the last kernels (ev_k of the last chunk), which are ordered after all earlier ones on s_k
+  // s_out is ordered after the last kernels: ev_k of the last chunk of each compute stream
   if (!dense && c) CU(cudaStreamWaitEvent(ctx->s_out, ctx->slots[(c - 1) % PIPE_SLOTS].ev_k, 0));
+  if (!dense && c > 1) CU(cudaStreamWaitEvent(ctx->s_out, ctx->slots[(c - 2) % PIPE_SLOTS].ev_k, 0));
   if (packed) {
     CU(cudaMemcpyAsync(status /* = sv */, ctx->d_sv, n, cudaMemcpyDeviceToHost, ctx->s_out));
   } else {
@@ -1446,7 +1472,9 @@ static int pipeline(const pb_ctx* cctx, const uint8_t* witness, const uint8_t* r
   CU(cudaStreamSynchronize(ctx->s_out));
   CU(cudaStreamSynchronize(ctx->s_in));
   CU(cudaStreamSynchronize(ctx->s_k));
+  CU(cudaStreamSynchronize(ctx->s_k2));
   if (n_done) *n_done = total_done;
+  if (trace_level) fprintf(stderr, "pipe host: %zu chunks enqueued at %.3f ms, call done at %.3f ms\n", sched.size(), host_enq, host_ms());
   if (trace) {
     for (size_t k = 0; k < sched.size(); k++) {
       float a = 0, b = 0, d = 0;
@@ -1486,30 +1514,47 @@ int pb_plonk_prove_verify_packed(const pb_ctx* ctx, const uint8_t* packed_in, ui
   ARG(ctx->vk_valid);
   return pipeline(ctx, packed_in, nullptr, nullptr, nullptr, packed_proofs, sv, nullptr, n, PIPE_PACKED, n_done);
 }
+int pb_plonk_prove_verify_packed3(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, size_t* n_done, uint8_t* sv, size_t n) {
+  if (n_done) *n_done = 0;
+  if (n == 0) return PB_OK;
+  ARG(ctx && packed_in && packed_proofs && n_done && sv);
+  ARG(ctx->vk_valid);
+  if (!ctx->srs_canonical) return fail(PB_ERR_ARG, "plonk_b200: packed wire v3 needs an SRS whose points are canonical points of the curve (use v2)");
+  return pipeline(ctx, packed_in, nullptr, nullptr, nullptr, packed_proofs, sv, nullptr, n, PIPE_PACKED3, n_done);
+}
 size_t pb_packed_workspace_bytes(size_t n) {
   const size_t cap = (n + 127) & ~(size_t)127;
   return cap * 34 + cap + cap + (cap / 128 + 4) * sizeof(uint32_t) + 64;   // proofs | status | verdict | offs
 }
-int pb_plonk_prove_verify_packed_dev(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, uint32_t* n_done_dev, uint8_t* sv,
-                                     void* workspace, size_t n, void* stream) {
+static int packed_dev(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, uint32_t* n_done_dev, uint8_t* sv,
+                      void* workspace, size_t n, void* stream, int wire3) {
   if (n == 0) return PB_OK;
   ARG(ctx && packed_in && packed_proofs && n_done_dev && sv && workspace);
   ARG(aligned16(packed_in) && aligned16(packed_proofs) && aligned16(workspace));
+  if (wire3 && !ctx->srs_canonical) return fail(PB_ERR_ARG, "plonk_b200: packed wire v3 needs an SRS whose points are canonical points of the curve (use v2)");
   const size_t cap = (n + 127) & ~(size_t)127;
   uint8_t* proofs = static_cast<uint8_t*>(workspace);
   uint8_t* status = proofs + cap * 34;
   uint8_t* verdict = status + cap;
   uint32_t* offs = reinterpret_cast<uint32_t*>(verdict + cap);
-  int rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed_in);
+  int rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed_in, wire3);
   if (rc) return rc;
-  return launch_gather(proofs, status, verdict, n, offs, n_done_dev, packed_proofs, sv, true, S(stream));
+  return launch_gather(proofs, status, verdict, n, offs, n_done_dev, packed_proofs, sv, wire3 ? 2 : 1, S(stream));
+}
+int pb_plonk_prove_verify_packed_dev(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, uint32_t* n_done_dev, uint8_t* sv,
+                                     void* workspace, size_t n, void* stream) {
+  return packed_dev(ctx, packed_in, packed_proofs, n_done_dev, sv, workspace, n, stream, 0);
+}
+int pb_plonk_prove_verify_packed3_dev(const pb_ctx* ctx, const uint8_t* packed_in, uint8_t* packed_proofs, uint32_t* n_done_dev, uint8_t* sv,
+                                      void* workspace, size_t n, void* stream) {
+  return packed_dev(ctx, packed_in, packed_proofs, n_done_dev, sv, workspace, n, stream, 1);
 }
 int pb_gather_completed_dev(const uint8_t* proofs, const uint8_t* status, uint8_t* proofs_dense, uint32_t* n_done_dev, uint32_t* offs_scratch,
                             size_t n, void* stream) {
   if (n == 0) return PB_OK;
   ARG(proofs && status && proofs_dense && n_done_dev && offs_scratch);
   ARG(aligned16(proofs) && aligned16(proofs_dense));
-  return launch_gather(proofs, status, nullptr, n, offs_scratch, n_done_dev, proofs_dense, nullptr, false, S(stream));
+  return launch_gather(proofs, status, nullptr, n, offs_scratch, n_done_dev, proofs_dense, nullptr, 0, S(stream));
 }
 
 // format conversion on the host (no arithmetic of the path): the reference's structs <-> packed wire v2
@@ -1562,6 +1607,71 @@ int pb_wire_unpack_proofs(const uint8_t* packed, uint8_t* proofs, size_t n) {
     uint16_t r[11];
     for (int k = 0; k < 11; k++) r[k] = (uint16_t)(packed[i * 22 + 2 * k] | packed[i * 22 + 2 * k + 1] << 8);
     if (!unpack_proof22(r, proofs + i * 34)) return fail(PB_ERR_ARG, "plonk_b200: packed proof record is not a canonical encoding");
+  }
+  return PB_OK;
+}
+// the same for packed wire v3 (14-byte input records, 12-byte proof records of points ON THE CURVE)
+static const CurveIndexImage k_curve_index = CurveIndexImage();
+int pb_wire3_pack_inputs(const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u, uint8_t* packed, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(witness && rnd && chal && u && packed);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t v[PACKED_VALUES];
+    uint16_t h[7];
+    for (int k = 0; k < 12; k++) v[k] = witness[i * 12 + k];
+    for (int k = 0; k < 9; k++) v[12 + k] = rnd[i * 9 + k];
+    for (int k = 0; k < 5; k++) v[21 + k] = chal[i * 5 + k];
+    v[26] = u[i];
+    bool ok = true;
+    for (int k = 0; k < PACKED_VALUES; k++) ok = ok && v[k] < 17u;
+    if (ok) pack_input14(v, h);
+    else for (int k = 0; k < 7; k++) h[k] = 0xFFFFu;   // not an encoding: the prover reports PB_PROVE_BAD_INPUT
+    for (int k = 0; k < 7; k++) { packed[i * 14 + 2 * k] = (uint8_t)(h[k] & 0xFF); packed[i * 14 + 2 * k + 1] = (uint8_t)(h[k] >> 8); }
+  }
+  return PB_OK;
+}
+int pb_wire3_unpack_inputs(const uint8_t* packed, uint8_t* witness, uint8_t* rnd, uint8_t* chal, uint8_t* u, uint8_t* valid, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(packed && witness && rnd && chal && u);
+  for (size_t i = 0; i < n; i++) {
+    uint16_t h[7];
+    uint32_t w[4], v[PACKED_VALUES];
+    for (int k = 0; k < 7; k++) h[k] = (uint16_t)(packed[i * 14 + 2 * k] | packed[i * 14 + 2 * k + 1] << 8);
+    input14_words(h, w);
+    const bool ok = unpack_input16(w[0], w[1], w[2], w[3], v);
+    for (int k = 0; k < 12; k++) witness[i * 12 + k] = ok ? (uint8_t)v[k] : 0xFF;
+    for (int k = 0; k < 9; k++) rnd[i * 9 + k] = ok ? (uint8_t)v[12 + k] : 0xFF;
+    for (int k = 0; k < 5; k++) chal[i * 5 + k] = ok ? (uint8_t)v[21 + k] : 0xFF;
+    u[i] = ok ? (uint8_t)v[26] : 0xFF;
+    if (valid) valid[i] = ok ? 1 : 0;
+  }
+  return PB_OK;
+}
+int pb_wire3_pack_proofs(const uint8_t* proofs, uint8_t* packed, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(proofs && packed);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t* r = proofs + i * 34;
+    for (int j = 0; j < 9; j++) {        // every point must be one of the 102: otherwise the record has no v3 encoding
+      const uint32_t x = r[3 * j], y = r[3 * j + 1];
+      const bool on = r[3 * j + 2] ? (x == 0 && y == 0) : (x < 101u && y < 101u && y * y % 101u == (x * x % 101u * x + 3u) % 101u);
+      if (!on) return fail(PB_ERR_ARG, "plonk_b200: a proof point is not a canonical point of the curve: no packed v3 encoding");
+    }
+    for (int j = 0; j < 7; j++) if (r[27 + j] >= 17u) return fail(PB_ERR_ARG, "plonk_b200: an opening is not a canonical F17 element");
+    uint32_t w[3];
+    pack_proof12(r, k_curve_index.base, w);
+    for (int k = 0; k < 3; k++) for (int b = 0; b < 4; b++) packed[i * 12 + 4 * k + b] = (uint8_t)(w[k] >> (8 * b));
+  }
+  return PB_OK;
+}
+int pb_wire3_unpack_proofs(const uint8_t* packed, uint8_t* proofs, size_t n) {
+  if (n == 0) return PB_OK;
+  ARG(packed && proofs);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[3];
+    for (int k = 0; k < 3; k++) { w[k] = 0; for (int b = 0; b < 4; b++) w[k] |= (uint32_t)packed[i * 12 + 4 * k + b] << (8 * b); }
+    if (!unpack_proof12(w, k_curve_index.px, k_curve_index.py, proofs + i * 34))
+      return fail(PB_ERR_ARG, "plonk_b200: packed v3 proof record is not a canonical encoding");
   }
   return PB_OK;
 }

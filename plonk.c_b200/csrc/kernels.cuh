@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
                                                       const uint8_t* __restrict__ chal, uint8_t* __restrict__ proofs,
                                                       uint8_t* __restrict__ status, size_t n, uint32_t* __restrict__ done_list,
                                                       uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
-                                                      uint8_t* __restrict__ chal_out = nullptr) {
+                                                      uint8_t* __restrict__ chal_out = nullptr, int wire3 = 0) {
   __shared__ ProveSmem<Tables> sm;
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * PBLOCK;
@@ -818,12 +818,24 @@ __global__ void __launch_bounds__(PBLOCK, PB_PROVE_MINBLOCKS) prove_kernel(const
 #if PB_PROVE_PREFETCH
     {
       const size_t pf = first + (size_t)PB_PROVE_PREFETCH * PBLOCK;   // 16 lines of 128 bytes per block
-      if (pf + PBLOCK <= n && tid < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(wit + pf * 16 + tid * 128));
+      if (pf + PBLOCK <= n && tid < (wire3 ? 14 : 16)) asm volatile("prefetch.global.L2 [%0];" ::"l"(wit + pf * (wire3 ? 14 : 16) + tid * 128));
     }
 #endif
     uint32_t v[PACKED_VALUES];
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (live) q = reinterpret_cast<const uint4*>(wit)[first + tid];
+    if (wire3) {        // v3: 14-byte records, seven 16-bit loads (a warp's records are 448 contiguous bytes)
+      uint16_t h[7] = {0, 0, 0, 0, 0, 0, 0};
+      const uint16_t* rec = reinterpret_cast<const uint16_t*>(wit) + (first + tid) * 7;
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) h[k] = __ldg(rec + k);
+      }
+      uint32_t w[4];
+      input14_words(h, w);
+      q = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (live) {
+      q = reinterpret_cast<const uint4*>(wit)[first + tid];
+    }
     bad = !unpack_input16(q.x, q.y, q.z, q.w, v);
 #pragma unroll
     for (int k = 0; k < 4; k++) { wa[k] = v[k]; wb[k] = v[4 + k]; wc[k] = v[8 + k]; }
@@ -974,12 +986,18 @@ struct __align__(16) VerifySmem {
 };
 
 // status (optional): items whose status byte is non-zero are skipped and get verdict 0xFF
-// packed (optional): the 16-byte packed input records (wire.cuh); the challenges and u are then word 3 of the item's record
+// the word of a packed input record that holds alpha beta gamma z v u: word 3 of a 16-byte v2 record, G of a 14-byte v3 record
+PB_D uint32_t packed_tail_word(const uint32_t* __restrict__ packed, size_t item, int wire3) {
+  if (!wire3) return __ldg(packed + item * 4 + 3);
+  const uint16_t* h = reinterpret_cast<const uint16_t*>(packed) + item * 7;
+  return input14_tail_word(__ldg(h + 1), __ldg(h + 3), __ldg(h + 5), __ldg(h + 6));
+}
+// packed (optional): the packed input records (wire.cuh); the challenges and u are then read from the item's record
 // and `chal` / `u` are not read.
 __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ VerifyKey key, const uint8_t* __restrict__ proofs,
                                                        const uint8_t* __restrict__ chal, const uint8_t* __restrict__ u,
                                                        const uint8_t* __restrict__ status, uint8_t* __restrict__ verdict,
-                                                       uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr) {
+                                                       uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr, int wire3 = 0) {
   __shared__ VerifySmem sm;
   const int tid = threadIdx.x;
   build_field_tables(sm.ft);
@@ -1005,7 +1023,7 @@ __global__ void __launch_bounds__(BLOCK) verify_kernel(const __grid_constant__ V
     fs_derive(key.fs_seed, pbytes, op, ch, uu);
   } else if (packed) {
     uint32_t d[7];
-    unpack7(packed[i * 4 + 3], d);      // a non-canonical word never gets here: the prover reports the item as bad input
+    unpack7(packed_tail_word(packed, i, wire3), d);      // a non-canonical word never gets here: the prover reports the item as bad input
 #pragma unroll
     for (int k = 0; k < 5; k++) ch[k] = d[k];
     uu = d[5];
@@ -1038,7 +1056,7 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
                                                             const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                             const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
                                                             const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
-                                                            uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr) {
+                                                            uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr, int wire3 = 0) {
   __shared__ VerifyFastSmem sm;
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * BLOCK;
@@ -1109,7 +1127,7 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
     fs_derive(key.fs_seed, pbytes, op, ch, uu);
   } else if (packed) {
     uint32_t d[7];
-    unpack7(packed[item * 4 + 3], d);   // a non-canonical word never gets here: the prover reports the item as bad input
+    unpack7(packed_tail_word(packed, item, wire3), d);   // a non-canonical word never gets here: the prover reports the item as bad input
 #pragma unroll
     for (int k = 0; k < 5; k++) ch[k] = d[k];
     uu = d[5];
@@ -1194,16 +1212,19 @@ __global__ void __launch_bounds__(1024) done_offsets_kernel(size_t m, uint32_t* 
   for (uint32_t g = lo; g < hi; g++) { const uint32_t c = offs[g]; offs[g] = run; run += c; }
 }
 
-// Step 2: block g moves its completed PROOF records to dense[offs[g]...], as 34-byte structs (PACK = false) or as 22-byte
-// packed records (PACK = true; then sv[i] = status/verdict nibbles is written for every item as well).  The records of a
+// Step 2: block g moves its completed PROOF records to dense[offs[g]...], as 34-byte structs (PACK = 0), as 22-byte
+// packed v2 records (PACK = 1) or as 12-byte v3 records (PACK = 2; the points must be on the curve, wire.cuh); with PACK != 0
+// sv[i] = status/verdict nibbles is written for every item as well.  The records of a
 // block form one contiguous run of the output; it is assembled in shared memory at the same 16-byte phase as its
 // destination, so that the body goes out in 128-bit stores.  dense must be 16-byte aligned.
-template <bool PACK>
+template <int PACK>
 __global__ void __launch_bounds__(GBLOCK) gather_done_kernel(const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ status,
                                                              const uint8_t* __restrict__ verdict, size_t m, const uint32_t* __restrict__ offs,
                                                              uint8_t* __restrict__ dense, uint8_t* __restrict__ sv) {
-  constexpr int REC = PACK ? PACKED_PROOF_BYTES : 34;
+  constexpr int REC = PACK == 2 ? PACKED3_PROOF_BYTES : PACK == 1 ? PACKED_PROOF_BYTES : 34;
   __shared__ __align__(16) uint8_t src[GBLOCK * 34];
+  __shared__ __align__(16) uint8_t cbase[104];
+  if (PACK == 2 && threadIdx.x < 26) reinterpret_cast<uint32_t*>(cbase)[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_curve_index.base)[threadIdx.x];
   __shared__ __align__(16) uint8_t dst[GBLOCK * REC + 16];
   __shared__ uint32_t wcnt[GBLOCK / 32];
   const int tid = threadIdx.x;
@@ -1223,7 +1244,12 @@ __global__ void __launch_bounds__(GBLOCK) gather_done_kernel(const uint8_t* __re
   const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(dense) + g0) & 15u);   // even: REC is even
   if (done) {
     uint16_t* o = reinterpret_cast<uint16_t*>(dst + skew + rank * REC);
-    if (PACK) {
+    if (PACK == 2) {
+      uint32_t rec[3];
+      pack_proof12(src + tid * 34, cbase, rec);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { o[2 * k] = (uint16_t)(rec[k] & 0xFFFFu); o[2 * k + 1] = (uint16_t)(rec[k] >> 16); }
+    } else if (PACK == 1) {
       uint16_t rec[11];
       pack_proof22(src + tid * 34, rec);
 #pragma unroll

@@ -593,21 +593,38 @@ class Plonk:
         k = self.prove_verify_packed_into(packed_in, pp, sv)
         return pp[:k], sv
 
-    def prove_verify_packed_dev(self, packed_in):
-        """Device path (torch CUDA tensors): -> (packed_proofs [n][22] capacity, n_done (device int32[1]), sv[n])."""
+    def prove_verify_packed_dev(self, packed_in, v3=False):
+        """Device path (torch CUDA tensors): -> (packed_proofs [n][22] (v3: [n][12]) capacity, n_done (device int32[1]), sv[n])."""
         import torch
         n = _n(packed_in)
         dev = packed_in.device
         lib().pb_packed_workspace_bytes.restype = C.c_size_t
         ws = torch.empty(lib().pb_packed_workspace_bytes(C.c_size_t(n)), dtype=torch.uint8, device=dev)
-        pp = torch.empty((n, 22), dtype=torch.uint8, device=dev)
+        pp = torch.empty((n, 12 if v3 else 22), dtype=torch.uint8, device=dev)
         sv = torch.empty(n, dtype=torch.uint8, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        fn = lib().pb_plonk_prove_verify_packed3_dev if v3 else lib().pb_plonk_prove_verify_packed_dev
         with torch.cuda.device(dev):
-            _check(lib().pb_plonk_prove_verify_packed_dev(self._h, C.c_void_p(packed_in.data_ptr()), C.c_void_p(pp.data_ptr()),
-                                                          C.c_void_p(cnt.data_ptr()), C.c_void_p(sv.data_ptr()), C.c_void_p(ws.data_ptr()),
-                                                          C.c_size_t(n), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            _check(fn(self._h, C.c_void_p(packed_in.data_ptr()), C.c_void_p(pp.data_ptr()),
+                      C.c_void_p(cnt.data_ptr()), C.c_void_p(sv.data_ptr()), C.c_void_p(ws.data_ptr()),
+                      C.c_size_t(n), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return pp, cnt, sv
+
+    def prove_verify_packed3_into(self, packed_in, packed_proofs, sv):
+        """Host path (numpy), packed wire v3: packed_in [n][14] -> packed_proofs[:n_done] ([n][12] capacity), sv[n].
+        Only for an SRS whose points are canonical points of the curve (PlonkError otherwise)."""
+        c = _Call("pb_plonk_prove_verify_packed3", packed_in)
+        assert not c.dev
+        n = _n(packed_in)
+        n_done = C.c_size_t(0)
+        c.run(self._h, c.inp(packed_in), c.outbuf(packed_proofs, (n, 12)), C.byref(n_done), c.outbuf(sv, (n,)), C.c_size_t(n))
+        return int(n_done.value)
+
+    def prove_verify_packed3(self, packed_in):
+        n = _n(packed_in)
+        pp, sv = np.empty((n, 12), np.uint8), np.empty(n, np.uint8)
+        k = self.prove_verify_packed3_into(packed_in, pp, sv)
+        return pp[:k], sv
 
     def prove_verify_seeded(self, seed, start, count, variant="U17"):
         """Inputs generated on the device from (seed, start, count); only the 18 counters come back."""
@@ -691,6 +708,37 @@ def wire_unpack_proofs(packed):
     packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, 22)
     out = np.empty((packed.shape[0], 34), np.uint8)
     _check(lib().pb_wire_unpack_proofs(packed.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(packed.shape[0])))
+    return out
+
+
+def wire3_pack_inputs(witness, rnd, chal, u):
+    n = _n(witness)
+    out = np.empty((n, 14), np.uint8)
+    a = [np.ascontiguousarray(x, np.uint8) for x in (witness, rnd, chal, u)]
+    _check(lib().pb_wire3_pack_inputs(*(x.ctypes.data_as(C.c_void_p) for x in a), out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+    return out
+
+
+def wire3_unpack_inputs(packed):
+    packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, 14)
+    n = packed.shape[0]
+    wit, rnd, chal, u, valid = np.empty((n, 12), np.uint8), np.empty((n, 9), np.uint8), np.empty((n, 5), np.uint8), np.empty(n, np.uint8), np.empty(n, np.uint8)
+    _check(lib().pb_wire3_unpack_inputs(packed.ctypes.data_as(C.c_void_p), *(x.ctypes.data_as(C.c_void_p) for x in (wit, rnd, chal, u, valid)),
+                                        C.c_size_t(n)))
+    return wit, rnd, chal, u, valid.astype(bool)
+
+
+def wire3_pack_proofs(proofs):
+    proofs = np.ascontiguousarray(proofs, np.uint8).reshape(-1, 34)
+    out = np.empty((proofs.shape[0], 12), np.uint8)
+    _check(lib().pb_wire3_pack_proofs(proofs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(proofs.shape[0])))
+    return out
+
+
+def wire3_unpack_proofs(packed):
+    packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, 12)
+    out = np.empty((packed.shape[0], 34), np.uint8)
+    _check(lib().pb_wire3_unpack_proofs(packed.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(packed.shape[0])))
     return out
 
 

@@ -29,7 +29,9 @@ Version 2 -- the packed wire format (csrc/wire.cuh; what pb_plonk_prove_verify_p
      proofs n_done x 22: nine u16 points x | y << 7 | infinite << 14, one u32 with the seven openings as base-17 digits;
      only completed proofs (status 0), in item order]                                   if flags & 4
 
-The numpy functions below are the format's reference implementation; the C helpers pb_wire_* and the device functions
+Packed wire v3 (14 B in, 12 B per completed proof; only for SRSs on the curve) is a wire-only format: see csrc/wire.cuh.
+
+The numpy functions below are the formats' reference implementation; the C helpers pb_wire_* and the device functions
 of csrc/wire.cuh are checked against them (tests/test_wire.py).
 """
 import struct
@@ -94,6 +96,114 @@ def unpack_proofs(packed):
     pts = np.stack([w16 & 0x7F, (w16 >> 7) & 0x7F, w16 >> 14], axis=2)
     out[:, :27] = pts.reshape(m, 27)
     out[:, 27:] = ((sc[:, None] // _POW17[None, :]) % np.uint64(17)).astype(np.uint8)
+    return out
+
+
+# ---------------------------------------------------------------- packed wire v3 (numpy reference implementation)
+# 14 B in, 12 B per completed proof out; layout in csrc/wire.cuh and include/plonk_b200.h.
+PACKED3_IN_BYTES, PACKED3_PROOF_BYTES = 14, 12
+
+
+def curve_points():
+    """The 102 points of E(F_101): y^2 = x^3 + 3 in wire order: index 0 = infinity (stored as x = y = 0), then the affine
+    points by (x, y).  -> (px[102], py[102], base[102]) with base[x] = index of the first point with abscissa x."""
+    px, py, base = [0], [0], []
+    for x in range(101):
+        base.append(len(px))
+        rhs = (x * x * x + 3) % 101
+        for y in range(101):
+            if y * y % 101 == rhs:
+                px.append(x)
+                py.append(y)
+    base.append(len(px))
+    assert len(px) == 102
+    return np.array(px, np.uint8), np.array(py, np.uint8), np.array(base, np.uint8)
+
+
+_PX, _PY, _BASE = curve_points()
+
+
+def pack_inputs3(witness, rand, chal, u):
+    """[n][12], [n][9], [n][5], [n] -> [n][14] v3 records (all-ones record for an item with a byte > 16)."""
+    n = int(witness.shape[0])
+    v = np.zeros((n, 27), np.uint64)
+    v[:, 0:12] = witness
+    v[:, 12:21] = rand
+    v[:, 21:26] = chal
+    v[:, 26] = u
+    words = (v[:, :21].reshape(n, 3, 7) * _POW17[None, None, :]).sum(axis=2)
+    G = (v[:, 21:27] * _POW17[None, :6]).sum(axis=1)
+    for k in range(3):
+        words[:, k] |= ((G >> np.uint64(16 + 3 * k)) & np.uint64(7)) << np.uint64(29)
+    out = np.empty((n, 14), np.uint8)
+    out[:, :12] = np.ascontiguousarray(words.astype("<u4")).view(np.uint8).reshape(n, 12)
+    out[:, 12:] = np.ascontiguousarray((G & np.uint64(0xFFFF)).astype("<u2")).view(np.uint8).reshape(n, 2)
+    out[(v > 16).any(axis=1)] = 0xFF
+    return out
+
+
+def unpack_inputs3(packed):
+    """[n][14] -> (witness, rand, chal, u, valid).  Invalid records decode to 0xFF."""
+    q = np.ascontiguousarray(packed, np.uint8).reshape(-1, 14)
+    n = q.shape[0]
+    words = np.ascontiguousarray(q[:, :12]).view("<u4").reshape(n, 3).astype(np.uint64)
+    G = np.ascontiguousarray(q[:, 12:]).view("<u2").reshape(n).astype(np.uint64)
+    for k in range(3):
+        G |= (words[:, k] >> np.uint64(29)) << np.uint64(16 + 3 * k)
+    low = words & np.uint64(0x1FFFFFFF)
+    valid = (low < np.uint64(17 ** 7)).all(axis=1) & (G < np.uint64(17 ** 6))
+    v = np.empty((n, 27), np.uint8)
+    v[:, :21] = ((low[:, :, None] // _POW17[None, None, :]) % np.uint64(17)).reshape(n, 21)
+    v[:, 21:] = (G[:, None] // _POW17[None, :6]) % np.uint64(17)
+    v[~valid] = 0xFF
+    return (np.ascontiguousarray(v[:, 0:12]), np.ascontiguousarray(v[:, 12:21]), np.ascontiguousarray(v[:, 21:26]),
+            np.ascontiguousarray(v[:, 26]), valid)
+
+
+def pack_proofs3(proofs):
+    """[m][34] PROOF structs whose points are on the curve -> [m][12] v3 records."""
+    p = np.ascontiguousarray(proofs, np.uint8).reshape(-1, 34)
+    m = p.shape[0]
+    pts = p[:, :27].reshape(m, 9, 3).astype(np.int64)
+    x, y, inf = pts[:, :, 0], pts[:, :, 1], pts[:, :, 2] != 0
+    on = np.where(inf, (x == 0) & (y == 0), (x < 101) & (y < 101) & ((y * y - x * x * x - 3) % 101 == 0))
+    if not on.all() or (p[:, 27:] > 16).any():
+        raise ValueError("proof record has no packed v3 encoding (a point off the curve or an opening > 16)")
+    idx = np.where(inf, 0, _BASE[np.minimum(x, 100)].astype(np.int64) + (2 * y > 101)).astype(np.uint64)
+    sc = p[:, 27:].astype(np.uint64)
+    words = np.zeros((m, 3), np.uint64)
+    for k in range(3):
+        words[:, k] = (idx[:, 3 * k] | idx[:, 3 * k + 1] << np.uint64(7) | idx[:, 3 * k + 2] << np.uint64(14)
+                       | (sc[:, 2 * k] + np.uint64(17) * sc[:, 2 * k + 1]) << np.uint64(21)
+                       | ((sc[:, 6] >> np.uint64(2 * k)) & np.uint64(3)) << np.uint64(30))
+    return np.ascontiguousarray(words.astype("<u4")).view(np.uint8).reshape(m, 12)
+
+
+def unpack_proofs3(packed):
+    """[m][12] -> [m][34]"""
+    q = np.ascontiguousarray(packed, np.uint8).reshape(-1, 12)
+    m = q.shape[0]
+    w = q.view("<u4").reshape(m, 3).astype(np.uint64)
+    out = np.empty((m, 34), np.uint8)
+    last = np.zeros(m, np.uint64)
+    for k in range(3):
+        for j in range(3):
+            i = (w[:, k] >> np.uint64(7 * j)) & np.uint64(0x7F)
+            if (i >= 102).any():
+                raise ValueError("packed v3 proof record is not a canonical encoding")
+            i = i.astype(np.int64)
+            out[:, 3 * (3 * k + j)] = _PX[i]
+            out[:, 3 * (3 * k + j) + 1] = _PY[i]
+            out[:, 3 * (3 * k + j) + 2] = i == 0
+        pair = (w[:, k] >> np.uint64(21)) & np.uint64(0x1FF)
+        if (pair >= 289).any():
+            raise ValueError("packed v3 proof record is not a canonical encoding")
+        out[:, 27 + 2 * k] = pair % np.uint64(17)
+        out[:, 28 + 2 * k] = pair // np.uint64(17)
+        last |= (w[:, k] >> np.uint64(30)) << np.uint64(2 * k)
+    if (last >= 17).any():
+        raise ValueError("packed v3 proof record is not a canonical encoding")
+    out[:, 33] = last
     return out
 
 

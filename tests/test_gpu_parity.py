@@ -464,6 +464,51 @@ def test_compact_and_packed_many_chunks(host, W):
     ps.eq("compact, second call", (dense3, s3, v3), (dense, s2, v2))
 
 
+def test_packed_v3(host, oracle, W):
+    """Packed wire v3 (14 B in, 12 B per completed proof: points as curve indices) against the oracle, host and device
+    paths, in every table mode; bad records flagged; an SRS off the curve is refused."""
+    import os
+    import torch
+    import util
+    from plonk_c_b200 import wire
+    n = 70001
+    for mode, env in (("generator9", {}), ("identity6", {}), ("generator9", {"PB_WIDE_TABLES": "0"}), ("generator9", {"PB_FORCE_EXACT": "1"})):
+        os.environ.update(env)
+        try:
+            g1s, g2 = util.SRS_MODES[mode](W)
+            pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+            wit, rnd, chal, u = W.make_batch(61, 3, n, "U17")
+            packed = wire.pack_inputs3(wit, rnd, chal, u)
+            packed[11] = 0xFF                                                   # 29-bit fields >= 17^7
+            packed[12, 12:] = 0xFF; packed[12, 3] |= 0xE0; packed[12, 7] |= 0xE0; packed[12, 11] |= 0xE0     # G >= 17^6
+            rp, rs, rv = _oracle_pv(oracle, W, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u)
+            for i in (11, 12):
+                rp[i] = 0; rs[i] = 254; rv[i] = 0xFF
+            want = (wire.pack_proofs3(rp[rs == 0]), wire.make_sv(rs, rv))
+            pp, sv = pk.prove_verify_packed3(packed)
+            ps.eq(f"packed v3 host {mode} {env}", (pp, sv), want)
+            ps.eq(f"packed v3 {mode}: unpack", wire.scatter_proofs(wire.unpack_proofs3(pp), wire.split_sv(sv)[0]), rp)
+            ppd, cnt, svd = pk.prove_verify_packed_dev(torch.from_numpy(packed).cuda(), v3=True)
+            k = int(cnt.item())
+            ps.eq(f"packed v3 dev {mode} {env}", (ppd[:k].cpu().numpy(), svd.cpu().numpy()), want)
+        finally:
+            for key in env:
+                del os.environ[key]
+    # many chunks (wraps the ring of buffer sets) against the v2 path on the GPU itself, and n = 0
+    pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
+    n = (1 << 21) + 77
+    batch = W.make_batch(62, 0, n, "U17")
+    pp2, sv2 = pk.prove_verify_packed(wire.pack_inputs(*batch))
+    pp3, sv3 = pk.prove_verify_packed3(wire.pack_inputs3(*batch))
+    ps.eq("packed v3, many chunks", (wire.unpack_proofs3(pp3), sv3), (wire.unpack_proofs(pp2), sv2))
+    e = pk.prove_verify_packed3(np.empty((0, 14), np.uint8))
+    assert e[0].shape == (0, 12) and e[1].shape == (0,)
+    # an SRS with points off the curve has no v3 encoding for its commitments
+    bad = host.Plonk(W.PLONK_TEST_CIRCUIT, *util.garbage_srs())
+    with pytest.raises(host.PlonkB200Error):
+        bad.prove_verify_packed3(wire.pack_inputs3(*W.make_batch(1, 0, 256, "U17")))
+
+
 def test_srs_eval_raw_and_satisfy_rows(host, oracle, W):
     """The context-free entry points behind the drop-in srs_eval_at_s / constraints_satisfy: one launch each, exactly the
     reference's loops -- including an untrimmed polynomial over a garbage SRS, where a trailing zero term changes the result."""

@@ -122,6 +122,94 @@ def test_packed_proofs_round_trip(host, oracle, W):
         assert np.array_equal(s2, st) and np.array_equal(v2, vd)
 
 
+# ---------------------------------------------------------------- packed wire v3 (14 B in, 12 B per proof; points as curve indices)
+def test_v3_curve_point_list():
+    px, py, base = wire.curve_points()
+    assert len(px) == 102 and px[0] == 0 and py[0] == 0
+    x, y = px[1:].astype(np.int64), py[1:].astype(np.int64)
+    assert ((y * y - x * x * x - 3) % 101 == 0).all()                                    # all on the curve
+    keys = x * 101 + y
+    assert (np.diff(keys) > 0).all()                                                     # strictly ordered by (x, y): no duplicates
+    assert all(base[v] == 1 + (x < v).sum() for v in range(101)) and base[101] == 102
+    # the encoder's rule "second point of an abscissa = the one with 2y > 101" matches the list
+    idx = base[x] + (2 * y > 101)
+    assert np.array_equal(idx, np.arange(1, 102))
+
+
+def test_v3_inputs_three_way_and_rejections(host):
+    rng = np.random.default_rng(12)
+    n = 40000
+    wit, rnd, chal, u = (rng.integers(0, 17, s, dtype=np.uint8) for s in ((n, 12), (n, 9), (n, 5), (n,)))
+    wit[0], rnd[0], chal[0], u[0] = 16, 16, 16, 16
+    wit[1], rnd[1], chal[1], u[1] = 0, 0, 0, 0
+    p = wire.pack_inputs3(wit, rnd, chal, u)
+    assert p.shape == (n, 14) and np.array_equal(p, host.wire3_pack_inputs(wit, rnd, chal, u))
+    w0 = p[0, :12].view("<u4")
+    assert ((w0 & 0x1FFFFFFF) == 17 ** 7 - 1).all()
+    G = int(p[0, 12:].view("<u2")[0]) | sum(int(w0[k] >> 29) << (16 + 3 * k) for k in range(3))
+    assert G == 17 ** 6 - 1
+    for unpack in (wire.unpack_inputs3, host.wire3_unpack_inputs):
+        w2, r2, c2, u2, valid = unpack(p)
+        assert valid.all() and np.array_equal(w2, wit) and np.array_equal(r2, rnd) and np.array_equal(c2, chal) and np.array_equal(u2, u)
+    # non-encodings: a 29-bit field >= 17^7, G >= 17^6, random bytes
+    bad = p[:64].copy()
+    words = bad[:, :12].view("<u4")
+    words[:16, 1] = (words[:16, 1] & 0xE0000000) | 17 ** 7
+    bad[16:32, 12:] = 0xFF; words[16:32] |= 0xE0000000                                    # G = 2^25 - 1 > 17^6
+    bad[32:64] = rng.integers(0, 256, (32, 14), dtype=np.uint8)
+    bad[32:64, 3] |= 0x1F; bad[32:64, 2] = 0xFF                                             # word 0's field = 2^29 - 1: never an encoding
+    a, b = wire.unpack_inputs3(bad), host.wire3_unpack_inputs(bad)
+    assert not a[4].any() and all(np.array_equal(x, y) for x, y in zip(a, b)) and (a[0] == 0xFF).all()
+    # an input byte > 16 has no encoding
+    wit[5, 3] = 17; u[6] = 99
+    for pack in (wire.pack_inputs3, host.wire3_pack_inputs):
+        q = pack(wit, rnd, chal, u)
+        assert (q[5] == 0xFF).all() and (q[6] == 0xFF).all() and np.array_equal(q[7], p[7])
+    assert not wire.unpack_inputs3(q)[4][5:7].any()
+
+
+def test_v3_proofs_three_way(host, oracle, W):
+    n = 20000
+    for g1s, g2 in (W.generator_srs(9), W.identity_srs(9)):
+        wit, rnd, chal, u = W.make_batch(32, 0, n)
+        proofs, status = oracle.plonk_prove_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal)
+        done = proofs[status == 0]
+        pp = wire.pack_proofs3(done)
+        assert pp.shape == (done.shape[0], 12) and np.array_equal(pp, host.wire3_pack_proofs(done))
+        assert np.array_equal(wire.unpack_proofs3(pp), done) and np.array_equal(host.wire3_unpack_proofs(pp), done)
+    # every point of the curve in every slot, every opening value
+    px, py, _ = wire.curve_points()
+    rng = np.random.default_rng(9)
+    m = 102 * 9
+    rec = np.zeros((m, 34), np.uint8)
+    idx = rng.integers(0, 102, (m, 9))
+    for j in range(9):
+        idx[j * 102:(j + 1) * 102, j] = np.arange(102)
+    rec[:, 0:27:3], rec[:, 1:27:3], rec[:, 2:27:3] = px[idx], py[idx], idx == 0
+    rec[:, 27:] = rng.integers(0, 17, (m, 7)); rec[:17, 33] = np.arange(17); rec[17:34, 27:] = 16
+    pp = wire.pack_proofs3(rec)
+    assert np.array_equal(pp, host.wire3_pack_proofs(rec)) and np.array_equal(wire.unpack_proofs3(pp), rec)
+    assert np.array_equal(host.wire3_unpack_proofs(pp), rec)
+    # records without an encoding are refused by both packers, non-encodings by both unpackers
+    off = rec[:1].copy(); off[0, 1] = (off[0, 1] + 1) % 101
+    if off[0, 2]: off[0, 0] = 5
+    with pytest.raises(ValueError):
+        wire.pack_proofs3(off)
+    with pytest.raises(host.PlonkB200Error):
+        host.wire3_pack_proofs(off)
+    for word, value in ((0, 102), (1, 127 << 7), (2, 289 << 21), (2, (3 << 30) | (3 << 21))):      # index 102; index 127; pair 289; 7th opening >= 17
+        q = pp[40:41].copy()
+        w = q.view("<u4")
+        if value == 102: w[0, word] = (w[0, word] & ~np.uint32(0x7F)) | np.uint32(102)
+        elif value == 127 << 7: w[0, word] |= np.uint32(127 << 7)
+        elif value == 289 << 21: w[0, word] = (w[0, word] & ~np.uint32(0x1FF << 21)) | np.uint32(289 << 21)
+        else: w[0, 0] |= np.uint32(3 << 30); w[0, 1] |= np.uint32(3 << 30); w[0, 2] |= np.uint32(1 << 30)   # 31
+        with pytest.raises(ValueError):
+            wire.unpack_proofs3(q)
+        with pytest.raises(host.PlonkB200Error):
+            host.wire3_unpack_proofs(q)
+
+
 def test_device_generator_equals_workload(W):
     """synth_item (wire.cuh), the generator of the seeded mode, is workload.make_batch bit for bit -- both variants,
     far-apart start offsets, and its packed records are the packing of its struct arrays."""
