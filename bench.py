@@ -394,23 +394,30 @@ def run_b200(args):
         barrier()
         return shard.reduce_max(a.elapsed_time(b), dev)
 
-    # ---- the same step on the shared-memory SRS path (pair tables, PB_WIDE_TABLES=0): BASELINE's "SRS held in shared memory"
-    os.environ["PB_WIDE_TABLES"] = "0"
-    try:
-        pk_pair = host.Plonk(W.PLONK_TEST_CIRCUIT, srs[0], srs[1], device=local_rank)
-    finally:
-        del os.environ["PB_WIDE_TABLES"]
+    # ---- the same step without the context-sized look-up tables: (1) PB_VERIFY_TABLES=0: the verifier that does the group
+    # arithmetic (Straus + Miller loops; the headline's verifier before the table path existed); (2) also PB_WIDE_TABLES=0:
+    # the prover on the shared-memory pair tables -- BASELINE's "SRS held in shared memory"
+    def alt_value(env):
+        os.environ.update(env)
+        try:
+            pk_alt = host.Plonk(W.PLONK_TEST_CIRCUIT, srs[0], srs[1], device=local_rank)
+        finally:
+            for key in env:
+                del os.environ[key]
 
-    def step_pair(k):
-        (wit, rnd, chal, u), (proofs, status, verdict) = sets[k % NBUF]
-        host._check(lib.pb_plonk_prove_verify_ex_dev(pk_pair._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict),
-                                                     C.c_size_t(n), sp, None))
-        host._check(lib.pb_tally_dev(P(proofs), P(status), P(verdict), C.c_size_t(n), P(counts), sp))
-    for k in range(3):
-        step_pair(k)
-    pair_steps = min(args.steps, 20)
-    pair_ms = timed_steps(step_pair, pair_steps)
-    pk_pair.close()
+        def step_alt(k):
+            (wit, rnd, chal, u), (proofs, status, verdict) = sets[k % NBUF]
+            host._check(lib.pb_plonk_prove_verify_ex_dev(pk_alt._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict),
+                                                         C.c_size_t(n), sp, None))
+            host._check(lib.pb_tally_dev(P(proofs), P(status), P(verdict), C.c_size_t(n), P(counts), sp))
+        for k in range(3):
+            step_alt(k)
+        steps = min(args.steps, 20)
+        ms = timed_steps(step_alt, steps)
+        pk_alt.close()
+        return ms, steps
+    arith_ms, arith_steps = alt_value({"PB_VERIFY_TABLES": "0"})
+    pair_ms, pair_steps = alt_value({"PB_VERIFY_TABLES": "0", "PB_WIDE_TABLES": "0"})
 
     # ---- seeded mode: inputs generated on the device, only the counters come back (not an e2e number)
     ws = pk.seeded_workspace(n, dev)
@@ -569,9 +576,13 @@ def run_b200(args):
                    "api": "pb_plonk_prove_verify_seeded_dev (seed, start, count) -> 18 counters",
                    "note": "inputs generated on the device (splitmix64 stream of workload.py), proved, verified, tallied; no batch data "
                            "crosses PCIe, so this is NOT an end-to-end number"},
+        "value_arith_verifier": {"value": total * arith_steps / (arith_ms * 1e-3), "unit": UNIT, "ms_per_step": arith_ms / arith_steps, "steps": arith_steps,
+                                 "note": "same step with PB_VERIFY_TABLES=0: the verifier computes the group operations and the two Miller loops "
+                                         "(Straus kernel, 150 us per 2^21 items) instead of looking discrete logarithms and pairings up (DESIGN.md 3.2)"},
         "value_pair_tables": {"value": total * pair_steps / (pair_ms * 1e-3), "unit": UNIT, "ms_per_step": pair_ms / pair_steps, "steps": pair_steps,
-                              "note": "same step with PB_WIDE_TABLES=0: the SRS fixed-base pair tables (5.8 KB) live in shared memory "
-                                      "(BASELINE north star (3)); the headline keeps a 48 MB one-look-up table in L2 instead"},
+                              "note": "same step with PB_WIDE_TABLES=0 and PB_VERIFY_TABLES=0: the SRS fixed-base pair tables (5.8 KB) live in shared "
+                                      "memory (BASELINE north star (3)) and the verifier does the arithmetic; the headline keeps a 48 MB one-look-up "
+                                      "table in L2 and the verifier's 2 KB of logarithm / pairing tables instead"},
         "completed_proofs_per_step": done_all,
         "gpu_launches": 3 * args.steps,
         "roofline": roof,

@@ -111,6 +111,7 @@ struct pb_ctx {
   ProverWideTables* d_wide_tables = nullptr;   // device: widest fast path (48 MB look-up table), only when srs_canonical and not PB_WIDE_TABLES=0
   uint16_t* d_wide_store = nullptr;            // 3 * 17^3 + 17^6 packed points behind d_wide_tables
   VerifyTables* d_verify_tables = nullptr;     // device: fast path, only when key_canonical
+  VerifyLogTables* d_verify_log = nullptr;     // device: table path (discrete logarithms + pairing tables), only when key_canonical and not PB_VERIFY_TABLES=0
   bool srs_canonical = false;         // every SRS point is a canonically encoded point of E(F_101)
   bool key_canonical = false;         // same for the nine verifier-key points
   bool force_exact = false;           // PB_FORCE_EXACT=1: always take the sequential path (tests)
@@ -1093,6 +1094,16 @@ int pb_ctx_create(pb_ctx** out, int device, const uint8_t circuit[PB_CIRCUIT_BYT
       verify_tables_kernel<<<1, 256>>>(d_kt.as<uint32_t>(), c->d_verify_tables);
       LAUNCHB("verify_tables_kernel");
       CUB(cudaDeviceSynchronize());
+      const char* evt = getenv("PB_VERIFY_TABLES");
+      if (!(evt && evt[0] == '0')) {
+        DEVB(d_ok, 16);
+        CUB(cudaMalloc(&c->d_verify_log, sizeof(VerifyLogTables)));
+        verify_log_tables_kernel<<<1, 256>>>(c->vk, c->d_verify_tables, c->d_verify_log, d_ok.as<uint32_t>());
+        LAUNCHB("verify_log_tables_kernel");
+        uint32_t ok = 0;
+        CUB(cudaMemcpy(&ok, d_ok.p, 4, cudaMemcpyDeviceToHost));
+        if (!ok) { cudaFree(c->d_verify_log); c->d_verify_log = nullptr; }
+      }
     }
   }
 #undef CUB
@@ -1111,6 +1122,7 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (c->d_wide_store) cudaFree(c->d_wide_store);
   for (auto& kv : c->scratch) if (kv.second.first) cudaFree(kv.second.first);
   if (c->d_verify_tables) cudaFree(c->d_verify_tables);
+  if (c->d_verify_log) cudaFree(c->d_verify_log);
   if (c->d_srs_table) cudaFree(c->d_srs_table);
   for (auto& s : c->slots) {
     for (cudaEvent_t e : {s.ev_in, s.ev_k, s.ev_out}) if (e) cudaEventDestroy(e);
@@ -1201,7 +1213,11 @@ static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t
                          const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st,
                          const uint8_t* packed = nullptr, int wire3 = 0) {
   const uint32_t* pk = reinterpret_cast<const uint32_t*>(packed);
-  if (ctx->key_canonical && !ctx->force_exact && !(status && !done_list))
+  const bool fast = ctx->key_canonical && !ctx->force_exact && !(status && !done_list);
+  if (fast && ctx->d_verify_log)
+    if (gt) verify_log_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3);
+    else verify_log_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3);
+  else if (fast)
     if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3);
     else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3);
   else

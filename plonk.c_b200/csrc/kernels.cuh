@@ -1051,8 +1051,11 @@ struct __align__(16) VerifyFastSmem {
 #endif
 };
 
+#ifndef PB_VERIFY_MINBLOCKS
+#define PB_VERIFY_MINBLOCKS 7   // 72 registers; measured 6: 150.4 us, 7: 149.2, default (64 registers): 150.6, 9: 152.0, 10: 154.0 (profiles/r2/NOTES.md)
+#endif
 template <bool WANT_GT>
-__global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constant__ VerifyKey key, const VerifyTables* __restrict__ gvt,
+__global__ void __launch_bounds__(BLOCK, PB_VERIFY_MINBLOCKS) verify_fast_kernel(const __grid_constant__ VerifyKey key, const VerifyTables* __restrict__ gvt,
                                                             const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                             const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
                                                             const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
@@ -1142,6 +1145,117 @@ __global__ void __launch_bounds__(BLOCK) verify_fast_kernel(const __grid_constan
 #endif
   verdict[item] = (uint8_t)o.verdict;
   if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+}
+
+// Table-path verifier (verifier.cuh: verify_one_log): same addressing modes and the same record / challenge handling as
+// verify_fast_kernel; the only shared memory is the 2.2 KB of tables (one bulk copy) and, in the dense mode, the staged records.
+struct __align__(16) VerifyLogSmem {
+  __align__(16) VerifyLogTables lt;
+  __align__(16) uint8_t proof[BLOCK * 34];
+  __align__(16) uint8_t chal[BLOCK * 5];
+};
+template <bool WANT_GT>
+__global__ void __launch_bounds__(BLOCK) verify_log_kernel(const __grid_constant__ VerifyKey key, const VerifyLogTables* __restrict__ glt,
+                                                           const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
+                                                           const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
+                                                           const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
+                                                           uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr, int wire3 = 0) {
+  __shared__ VerifyLogSmem sm;
+  const int tid = threadIdx.x;
+  const size_t first = (size_t)blockIdx.x * BLOCK;
+  const size_t limit = done_list ? (size_t)*done_count : n;
+  if (first >= limit) return;                                             // whole block beyond the dense list
+  static_assert(sizeof(VerifyLogTables) % 16 == 0, "bulk copies move multiples of 16 bytes");
+#if PB_BULK
+  __shared__ __align__(8) uint64_t mbar;
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&mbar, (uint32_t)sizeof(VerifyLogTables));
+    bulk_load(&sm.lt, glt, (uint32_t)sizeof(VerifyLogTables), &mbar);
+  }
+#else
+  for (int k = tid; k < (int)(sizeof(VerifyLogTables) / 4); k += BLOCK)
+    reinterpret_cast<uint32_t*>(&sm.lt)[k] = reinterpret_cast<const uint32_t*>(glt)[k];
+#endif
+  size_t item = first + tid;
+  const bool live = item < limit;
+  const bool fs = chal == nullptr && packed == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
+  uint32_t pbytes[27], op[7], ch[5];
+  if (done_list) {
+#if !PB_BULK
+    __syncthreads();
+#endif
+    if (!live) return;
+    item = done_list[item];
+    const uint16_t* pr = reinterpret_cast<const uint16_t*>(proofs + item * 34);
+    uint32_t b[34];
+#pragma unroll
+    for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+#pragma unroll
+    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
+    if (chal) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
+    }
+#if PB_BULK
+    mbar_wait(&mbar, 0);
+#endif
+  } else {
+    stage_in<34, BLOCK>(sm.proof, proofs, first, n);
+    if (chal) stage_in<5, BLOCK>(sm.chal, chal, first, n);
+    __syncthreads();
+#if PB_BULK
+    mbar_wait(&mbar, 0);
+#endif
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
+    if (chal) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+    }
+  }
+  uint32_t uu;
+  if (fs) {
+    fs_derive(key.fs_seed, pbytes, op, ch, uu);
+  } else if (packed) {
+    uint32_t d[7];
+    unpack7(packed_tail_word(packed, item, wire3), d);   // a non-canonical word never gets here: the prover reports the item as bad input
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = d[k];
+    uu = d[5];
+  } else {
+    uu = u[item];
+  }
+  VerifyOut o;
+  verify_one_log<WANT_GT>(sm.lt, pbytes, op, ch, uu, o);
+  verdict[item] = (uint8_t)o.verdict;
+  if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+}
+
+// VerifyLogTables at context creation: the sequential part by one thread, then one entry per thread.  ok[0] = 0 if the
+// construction failed (the context then keeps the Straus kernel).
+__global__ void __launch_bounds__(256) verify_log_tables_kernel(const __grid_constant__ VerifyKey key, const VerifyTables* __restrict__ vt,
+                                                                VerifyLogTables* __restrict__ out, uint32_t* __restrict__ ok) {
+  __shared__ FieldTables ft;
+  __shared__ VerifyLogTables lt;
+  __shared__ uint8_t alog[104];
+  __shared__ uint32_t good;
+  build_field_tables(ft);
+  __syncthreads();
+  if (threadIdx.x == 0) good = vlt_group(ft, lt, alog) ? 1u : 0u;
+  __syncthreads();
+  if (good)
+    for (uint32_t t = threadIdx.x; t < VLT_ENTRIES; t += blockDim.x) vlt_entry(ft, key, *vt, alog, lt, t);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < sizeof(VerifyLogTables) / 4; k += blockDim.x)
+    reinterpret_cast<uint32_t*>(out)[k] = reinterpret_cast<const uint32_t*>(&lt)[k];
+  if (threadIdx.x == 0) *ok = good;
 }
 
 // status bytes -> dense list of the completed items (for pb_plonk_verify_completed_dev, where the list does not come

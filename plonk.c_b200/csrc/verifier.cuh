@@ -235,4 +235,147 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Table path ("log" verifier).  Same preconditions as the fast path.  E(F_101) has 102 points and 102 is squarefree, so
+// the group is cyclic: with a generator Q every point is k Q, the reference's g1_add is addition of the k's mod 102 and
+// g1_mul(P, s) is s * k (the scalar is never reduced, g1.h:91-103; here s < 17).  The right-hand point of step 11 is then
+// ONE sum of 14 products of small integers, reduced mod 102 -- no group operation at all -- and, since the verifier pairs
+// with just two G2 points (both in the key), pairing(k Q, g2_s) and pairing(k Q, g2_one) are two 102-entry tables built
+// at context creation with the reference's own pairing (pairing17: miller17 + final exponentiation).  The check
+// gtp_equal(pairing(lhs, g2_s), pairing(rhs, g2_one)) is two look-ups and a compare.  This is memoisation made possible
+// by the toy parameters, exactly like the prover's 17^6-entry commitment table; PB_VERIFY_TABLES=0 at context creation
+// keeps the Straus + Miller-loop kernel above, and bench.py reports that configuration too.
+// Curve membership (step 1) is a look-up as well: (x, y) is on the curve iff it IS the point at its index in the list.
+struct alignas(16) VerifyLogTables {
+  uint8_t cbase[104];      // x -> index of the first point with abscissa x (wire.cuh: CurveIndexImage); [101] = 102
+  uint8_t px[104], py[104];  // index -> coordinates; [0] = (0, 0) for infinity, [102..103] = 0xFF (no point)
+  uint8_t dlog[104];       // index -> k with point = k Q; dlog[0] = 0
+  uint8_t L2[4][292];      // dlog of VerifyTables.P2[t][i]
+  uint8_t Lneg[24];        // dlog of VerifyTables.one_neg[e]
+  uint8_t inv17[32];       // hf_inverses (FieldTables.inv17): the only field table this path needs
+  uint16_t gt_s[104];      // k -> pairing(k Q, g2_s) as a | b << 8
+  uint16_t gt_1[104];      // k -> pairing(k Q, g2_one)
+};
+constexpr uint32_t GROUP_ORDER = 102u;
+
+// index of a canonical curve point in the list (curve_index of wire.cuh, restated here so that this header stands alone)
+PB_HD uint32_t vlt_index(const VerifyLogTables& lt, G1 p) {
+  const uint32_t i = lt.cbase[p.x < 101u ? p.x : 0u] + (2u * p.y > 101u ? 1u : 0u);
+  return p.inf ? 0u : i;
+}
+// step A of the construction (sequential): the point list, a generator, the discrete logarithms.  Returns false if no
+// point has order 102 (cannot happen on this curve; the caller then keeps the Straus kernel).
+PB_HD bool vlt_group(const FieldTables& ft, VerifyLogTables& lt, uint8_t (&alog)[104]) {
+  uint32_t n = 1;
+  lt.px[0] = 0; lt.py[0] = 0;
+  for (uint32_t x = 0; x < 101u; x++) {
+    lt.cbase[x] = (uint8_t)n;
+    const uint32_t rhs = red101(red101(x * x) * x + 3u);
+    for (uint32_t y = 0; y < 101u; y++)
+      if (red101(y * y) == rhs && n < 104u) { lt.px[n] = (uint8_t)x; lt.py[n] = (uint8_t)y; n++; }
+  }
+  if (n != GROUP_ORDER) return false;
+  for (uint32_t k = 101; k < 104; k++) lt.cbase[k] = (uint8_t)n;
+  for (uint32_t k = n; k < 104; k++) { lt.px[k] = 0xFF; lt.py[k] = 0xFF; }
+  for (uint32_t k = 0; k < 32; k++) lt.inv17[k] = ft.inv17[k];
+  for (uint32_t cand = 1; cand < GROUP_ORDER; cand++) {
+    const G1 q{lt.px[cand], lt.py[cand], 0u};
+    G1 p = q;
+    uint32_t ord = 1;
+    while (!p.inf && ord <= GROUP_ORDER) { p = g1_add(ft, p, q); ord++; }     // the reference's addition, g1.h:42-83
+    if (ord != GROUP_ORDER) continue;
+    for (uint32_t k = 0; k < 104; k++) { lt.dlog[k] = 0; alog[k] = 0; }
+    p = q;
+    for (uint32_t k = 1; k < GROUP_ORDER; k++) {
+      const uint32_t i = vlt_index(lt, p);
+      lt.dlog[i] = (uint8_t)k;
+      alog[k] = (uint8_t)i;
+      p = g1_add(ft, p, q);
+    }
+    return true;
+  }
+  return false;
+}
+// step B (independent entries t < VLT_ENTRIES): the two pairing tables, then the logarithms of the key tables
+constexpr uint32_t VLT_ENTRIES = GROUP_ORDER + 4u * 289u + 17u;
+PB_HD void vlt_entry(const FieldTables& ft, const VerifyKey& key, const VerifyTables& vt, const uint8_t (&alog)[104], VerifyLogTables& lt, uint32_t t) {
+  if (t < GROUP_ORDER) {
+    const uint32_t i = alog[t];
+    const G1 p{lt.px[i], lt.py[i], i == 0u ? 1u : 0u};
+    const GT a = pairing17(ft, p, key.g2_s), b = pairing17(ft, p, key.g2_one);
+    lt.gt_s[t] = (uint16_t)(a.a | a.b << 8);
+    lt.gt_1[t] = (uint16_t)(b.a | b.b << 8);
+    if (t < 2u) { lt.gt_s[GROUP_ORDER + t] = 0; lt.gt_1[GROUP_ORDER + t] = 0; }
+  } else if (t < GROUP_ORDER + 4u * 289u) {
+    const uint32_t j = (t - GROUP_ORDER) / 289u, i = (t - GROUP_ORDER) % 289u;
+    lt.L2[j][i] = lt.dlog[vlt_index(lt, unpack_g1(vt.P2[j][i]))];
+  } else {
+    const uint32_t e = t - GROUP_ORDER - 4u * 289u;
+    lt.Lneg[e] = lt.dlog[vlt_index(lt, unpack_g1(vt.one_neg[e]))];
+  }
+}
+
+template <bool WANT_GT = true>
+PB_HD void verify_one_log(const VerifyLogTables& lt, const uint32_t (&pb)[27], const uint32_t (&op)[7], const uint32_t (&ch)[5],
+                         uint32_t u, VerifyOut& out) {
+  out.lhs = GT{0u, 0u};
+  out.rhs = GT{0u, 0u};
+  // step 1: encodings and curve membership; lg[j] = discrete logarithm of commitment j
+  bool bad_pt = false;
+  uint32_t lg[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const uint32_t x = pb[3 * j], y = pb[3 * j + 1], f = pb[3 * j + 2];
+    bad_pt |= x > 100u || y > 100u || f > 1u || (f == 1u && (x | y) != 0u);
+    uint32_t i = lt.cbase[x > 100u ? 0u : x] + (2u * y > 101u ? 1u : 0u);
+    i = f != 0u ? 0u : i;
+    bad_pt |= f == 0u && (lt.px[i] != x || lt.py[i] != y);          // on the curve <=> it is the listed point
+    lg[j] = lt.dlog[i];
+  }
+  bool bad_sc = u > 16u;
+#pragma unroll
+  for (int j = 0; j < 7; j++) bad_sc |= op[j] > 16u;
+#pragma unroll
+  for (int j = 0; j < 5; j++) bad_sc |= ch[j] > 16u;
+  if (bad_pt) { out.verdict = 2u; return; }
+  if (bad_sc) { out.verdict = 3u; return; }
+
+  // steps 4-10: the scalars, exactly as in verify_one
+  const uint32_t a_z = op[0], b_z = op[1], c_z = op[2], s1_z = op[3], s2_z = op[4], r_z = op[5], zw_z = op[6];
+  const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
+  constexpr uint32_t K1 = 2u, K2 = 3u, OMEGA = 4u;
+  const uint32_t z2 = red17(z * z), z3 = red17(z2 * z), z4 = red17(z2 * z2);
+  const uint32_t zh_z = sub17(z4, 1u);
+  const uint32_t l1_z = red17(13u * (1u + z + z2 + z3));
+  const uint32_t alpha2 = red17(alpha * alpha);
+  const uint32_t pa = red17(a_z + beta * s1_z + gamma), pbb = red17(b_z + beta * s2_z + gamma);
+  const uint32_t pab = red17(pa * pbb);
+  const uint32_t perm = red17(red17(red17(pab * red17(c_z + gamma)) * zw_z) * alpha);
+  const uint32_t t_num = red17(r_z + 2u * P17 - perm - red17(l1_z * alpha2));
+  const uint32_t t_z = red17(t_num * lt.inv17[zh_z]);
+  const uint32_t bz = red17(beta * z);
+  const uint32_t ga = red17(a_z + bz + gamma), gb = red17(b_z + K1 * bz + gamma), gc = red17(c_z + K2 * bz + gamma);
+  const uint32_t d_z = red17(red17(red17(red17(red17(ga * gb) * gc) * alpha) * v) + red17(red17(l1_z * alpha2) * v) + u);
+  const uint32_t d_s3 = red17(red17(red17(red17(pab * alpha) * v) * beta) * zw_z);
+  const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
+  const uint32_t z6 = red17(z4 * z2), z12 = red17(z6 * z6);
+  const uint32_t e = red17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);
+  const uint32_t uzw = red17(red17(u * z) * OMEGA);
+
+  // step 11 in the exponent: [D] + [F] - [E] + z [W_z] + u z omega [W_zw] on the right, [W_z] + u [W_zw] on the left.
+  // k_r <= 5 * 101 + 101 + 8 * 16 * 101 < 2^14; floor(k / 102) = (k * 41121) >> 22 is exact below 110 376
+  uint32_t k_r = (uint32_t)lt.L2[0][red17(red17(a_z * b_z) * v) * 17u + red17(a_z * v)] + lt.L2[1][red17(b_z * v) * 17u + red17(c_z * v)] +
+                 lt.L2[2][v * 17u + d_s3] + lt.L2[3][v5 * 17u + v6] + lt.Lneg[e] + lg[4] +
+                 z * lg[7] + uzw * lg[8] + z6 * lg[5] + z12 * lg[6] + v2 * lg[0] + v3 * lg[1] + v4 * lg[2] + d_z * lg[3];
+  k_r -= GROUP_ORDER * ((k_r * 41121u) >> 22);
+  uint32_t k_l = lg[7] + u * lg[8];
+  k_l -= GROUP_ORDER * ((k_l * 41121u) >> 22);
+  const uint32_t gl = lt.gt_s[k_l], gr = lt.gt_1[k_r];
+  if constexpr (WANT_GT) {
+    out.lhs = GT{gl & 0xFFu, gl >> 8};
+    out.rhs = GT{gr & 0xFFu, gr >> 8};
+  }
+  out.verdict = gl == gr ? 1u : 0u;                                  // gtp_equal, pairing.h:9-11
+}
+
 }  // namespace pb

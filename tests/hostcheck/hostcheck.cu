@@ -236,6 +236,86 @@ void hc_verify_fast(const uint8_t* key, const uint32_t seed4[4], const uint8_t* 
     if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
   }
 }
+// table-path verifier (verifier.cuh: verify_one_log): the tables are built by the same two functions the context-creation
+// kernel calls (vlt_group, vlt_entry), from a VerifyTables built as above.  Returns 0, or 1 if no generator was found.
+static void build_vt(const FieldTables& ft, G1* const* dst, VerifyTables& vt) {
+  static uint32_t KT[9][17];
+  for (int j = 0; j < 9; j++)
+    for (uint32_t c = 0; c < 17; c++) { G1 r = g1_mul(ft, *dst[j], c); KT[j][c] = pack_g1(r.x, r.y, r.inf); }
+  const int ia[4] = {0, 2, 4, 5}, ib[4] = {1, 3, 7, 6};
+  for (uint32_t t = 0; t < 4; t++)
+    for (uint32_t a = 0; a < 17; a++)
+      for (uint32_t b = 0; b < 17; b++) {
+        G1 p = unpack_g1(KT[ia[t]][a]), q = unpack_g1(KT[ib[t]][b]);
+        if (t == 2) q = g1_neg(q);
+        G1 r = g1_add(ft, p, q);
+        vt.P2[t][a * 17 + b] = pack_g1(r.x, r.y, r.inf);
+      }
+  for (uint32_t c = 0; c < 17; c++) { G1 r = g1_neg(unpack_g1(KT[8][c])); vt.one_neg[c] = pack_g1(r.x, r.y, r.inf); }
+}
+int hc_verify_log(const uint8_t* key, const uint32_t seed4[4], const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, uint8_t* verdict, uint8_t* gt, size_t n) {
+  FieldTables ft = make_ft();
+  FsState fs_seed;
+  memcpy(fs_seed.v, seed4, 16);
+  VerifyKey k;
+  G1* dst[9] = {&k.qm, &k.ql, &k.qr, &k.qo, &k.qc, &k.s1, &k.s2, &k.s3, &k.g1_one};
+  for (int j = 0; j < 9; j++) *dst[j] = ld(key + 3 * j);
+  k.g2_one = G2{key[27], key[28]};
+  k.g2_s = G2{key[29], key[30]};
+  static VerifyTables vt;
+  build_vt(ft, dst, vt);
+  static VerifyLogTables lt;
+  uint8_t alog[104];
+  memset(&lt, 0, sizeof lt);
+  if (!vlt_group(ft, lt, alog)) return 1;
+  for (uint32_t t = 0; t < VLT_ENTRIES; t++) vlt_entry(ft, k, vt, alog, lt, t);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t pbv[27], op[7], ch[5];
+    for (int j = 0; j < 27; j++) pbv[j] = proofs[34 * i + j];
+    for (int j = 0; j < 7; j++) op[j] = proofs[34 * i + 27 + j];
+    uint32_t uu;
+    if (chal) { for (int j = 0; j < 5; j++) ch[j] = chal[5 * i + j]; uu = u[i]; }
+    else fs_derive(fs_seed, pbv, op, ch, uu);
+    VerifyOut o;
+    if (gt) verify_one_log<true>(lt, pbv, op, ch, uu, o);
+    else verify_one_log<false>(lt, pbv, op, ch, uu, o);
+    verdict[i] = (uint8_t)o.verdict;
+    if (gt) { gt[4 * i] = (uint8_t)o.lhs.a; gt[4 * i + 1] = (uint8_t)o.lhs.b; gt[4 * i + 2] = (uint8_t)o.rhs.a; gt[4 * i + 3] = (uint8_t)o.rhs.b; }
+  }
+  return 0;
+}
+// The premise of the table path, exhaustively: for ALL 102 x 102 pairs of curve points the reference's g1_add (and its
+// canonical-point variant g1_add_c) is addition of discrete logarithms mod 102; g1_double, g1_neg and g1_mul by every
+// scalar < 17 agree with it; the membership look-up equals g1_is_on_curve on all 101 x 101 x 2 encodings.  Returns the
+// number of disagreements (0), or ~0 if no generator exists.
+uint64_t hc_check_discrete_logs() {
+  FieldTables ft = make_ft();
+  static VerifyLogTables lt;
+  uint8_t alog[104];
+  memset(&lt, 0, sizeof lt);
+  if (!vlt_group(ft, lt, alog)) return ~0ull;
+  uint64_t bad = 0;
+  auto pt = [&](uint32_t i) { return G1{lt.px[i], lt.py[i], i == 0u ? 1u : 0u}; };
+  auto same = [&](G1 r, uint32_t k) { const uint32_t i = alog[k % GROUP_ORDER]; const G1 w = pt(i); return r.x == w.x && r.y == w.y && r.inf == w.inf; };
+  for (uint32_t i = 0; i < GROUP_ORDER; i++) {
+    bad += alog[lt.dlog[i]] != i;
+    const G1 p = pt(i);
+    const uint32_t ki = lt.dlog[i];
+    bad += !same(g1_double(ft, p), 2u * ki) + !same(g1_double_c(ft, p), 2u * ki) + !same(g1_neg(p), GROUP_ORDER - ki);
+    for (uint32_t sc = 0; sc < 17; sc++) bad += !same(g1_mul(ft, p, sc), sc * ki);
+    for (uint32_t j = 0; j < GROUP_ORDER; j++) {
+      const G1 q = pt(j);
+      bad += !same(g1_add(ft, p, q), ki + lt.dlog[j]) + !same(g1_add_c(ft, p, q), ki + lt.dlog[j]);
+    }
+  }
+  for (uint32_t x = 0; x < 101; x++)
+    for (uint32_t y = 0; y < 101; y++) {
+      const bool on = g1_is_on_curve(G1{x, y, 0u});
+      const uint32_t i = lt.cbase[x] + (2u * y > 101u ? 1u : 0u);
+      bad += on != (lt.px[i] == x && lt.py[i] == y);
+    }
+  return bad;
+}
 // the shared-final-exponentiation identity behind pairings_equal17_c, checked on GT values directly:
 // (f1^600 == f2^600)  ==  (either zero ? both zero : (f1 conj(f2))^600 == 1), f2 over ALL of GT, f1 over every `step`-th value
 uint64_t hc_check_shared_final_exp(uint32_t step) {

@@ -255,7 +255,7 @@ class HostcheckImpl:
 
     def _prove_fn(self):
         # fast: False = sequential tables (any SRS); True = pair tables; "wide" = one-look-up T6 tables (prover only)
-        return {False: self.lib.hc_prove, True: self.lib.hc_prove_pairs, "wide": self.lib.hc_prove_wide}[self.fast]
+        return {False: self.lib.hc_prove, True: self.lib.hc_prove_pairs, "wide": self.lib.hc_prove_wide, "log": self.lib.hc_prove_pairs}[self.fast]
 
     def wide_tables(self, g1s):
         """(T6 [17^6][3], T3 [17^3][3]) as the wide-table builder produces them for this SRS"""
@@ -308,12 +308,16 @@ class HostcheckImpl:
                           _p(proofs), _p(status), _p(chal), C.c_size_t(n))
         return proofs, status, chal
 
+    def _verify_fn(self):
+        # fast=True: Straus + Miller-loop verifier; fast="log": the table path (discrete logarithms, pairing tables); else exact
+        return self.lib.hc_verify_log if self.fast == "log" else self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify
+
     def plonk_verify_batch(self, circuit, g1s, g2, proofs, chal, u, nthreads=1, want_gt=True):
         key = np.concatenate([self.o.verifier_key(circuit, g1s, g2).ravel(), np.asarray(g2, np.uint8)]).astype(np.uint8)
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
+        self._verify_fn()(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt
 
     def plonk_verdict_only(self, circuit, g1s, g2, proofs, chal, u):
@@ -321,7 +325,7 @@ class HostcheckImpl:
         proofs, chal, u = (np.ascontiguousarray(x, np.uint8) for x in (proofs, chal, u))
         n = proofs.shape[0]
         verdict = np.zeros(n, np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), None, C.c_size_t(n))
+        self._verify_fn()(_p(key), self._seed_words(0).ctypes.data_as(C.c_void_p), _p(proofs), _p(chal), _p(u), _p(verdict), None, C.c_size_t(n))
         return verdict
 
     def plonk_verify_fs_batch(self, circuit, g1s, g2, proofs, want_gt=True):
@@ -329,6 +333,6 @@ class HostcheckImpl:
         proofs = np.ascontiguousarray(proofs, np.uint8)
         n = proofs.shape[0]
         verdict, gt = np.zeros(n, np.uint8), np.zeros((n, 4), np.uint8)
-        (self.lib.hc_verify_fast if self.fast is True else self.lib.hc_verify)(_p(key), self._seed_words(self.fs_seed(circuit, g1s, g2)).ctypes.data_as(C.c_void_p), _p(proofs), None, None,
+        self._verify_fn()(_p(key), self._seed_words(self.fs_seed(circuit, g1s, g2)).ctypes.data_as(C.c_void_p), _p(proofs), None, None,
                                                                       _p(verdict), _p(gt), C.c_size_t(n))
         return verdict, gt

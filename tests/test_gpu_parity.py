@@ -205,6 +205,22 @@ def test_protocol_pair_tables_path(host, oracle, W):
         del os.environ["PB_WIDE_TABLES"]
 
 
+def test_protocol_straus_verifier_path(host, oracle, W):
+    """PB_VERIFY_TABLES=0 keeps a context on the Straus + Miller-loop verifier kernel (no discrete-logarithm / pairing
+    tables): the arithmetic path must stay identical to the oracle too, verdicts and pairing values."""
+    import os
+    os.environ["PB_VERIFY_TABLES"] = "0"
+    try:
+        impl = GpuImpl(host, "device")
+        modes = [("generator9", lambda W: W.generator_srs(9)), ("generator6", lambda W: W.generator_srs(6)), ("identity6", lambda W: W.identity_srs(6))]
+        ps.check_protocol(impl, oracle, W, n=30000, modes=modes)
+        ps.check_fiat_shamir(impl, oracle, W, n=10000, modes=modes[:1])
+        ps.check_whole_curve_srs(impl, oracle, W, n=3000, trials=3)
+        ps.check_golden_transcript(impl, W)
+    finally:
+        del os.environ["PB_VERIFY_TABLES"]
+
+
 def test_host_pipeline_pinned_matches_pageable(host, W):
     """Host-pointer prove+verify with pinned buffers against the same call with pageable buffers, explicit and
     Fiat-Shamir mode, a ragged size spanning many pipeline chunks."""

@@ -187,3 +187,19 @@ def test_hostcheck_random_circuits(oracle, W):
 def test_hostcheck_whole_curve_srs(oracle, W):
     ps.check_whole_curve_srs(HostcheckImpl(oracle, fast=True), oracle, W, n=3000, trials=6)
     ps.check_whole_curve_srs(HostcheckImpl(oracle), oracle, W, n=2000, trials=2)
+
+
+def test_hostcheck_log_verifier(oracle, W):
+    """The table-path verifier (discrete logarithms mod 102 + two pairing tables): its premise exhaustively, then the same
+    protocol / Fiat-Shamir / whole-curve-SRS / random-circuit suites as the Straus verifier, verdicts and pairing values."""
+    import ctypes as C
+    import util
+    hcl = HostcheckImpl(oracle, fast="log")
+    hcl.lib.hc_check_discrete_logs.restype = C.c_uint64
+    assert hcl.lib.hc_check_discrete_logs() == 0
+    modes = [(m, f) for m, f in util.SRS_MODES.items()]
+    ps.check_protocol(hcl, oracle, W, n=8000, modes=modes)
+    ps.check_golden_transcript(hcl, W)
+    ps.check_fiat_shamir(hcl, oracle, W, n=4000, modes=modes)
+    ps.check_whole_curve_srs(hcl, oracle, W, n=3000, trials=6)
+    ps.check_random_circuits(hcl, oracle, W, n=1500, circuits=4)
