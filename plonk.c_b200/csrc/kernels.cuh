@@ -1154,8 +1154,11 @@ struct __align__(16) VerifyLogSmem {
   __align__(16) uint8_t proof[BLOCK * 34];
   __align__(16) uint8_t chal[BLOCK * 5];
 };
+#ifndef PB_VERIFY_LOG_MINBLOCKS
+#define PB_VERIFY_LOG_MINBLOCKS 8   // 60 registers; measured (us per 2^21 attempted items): no cap (91 registers) 55.2, 8: 46.9, 10: 47.2, 12: 51.3, 16: 62.2
+#endif
 template <bool WANT_GT>
-__global__ void __launch_bounds__(BLOCK) verify_log_kernel(const __grid_constant__ VerifyKey key, const VerifyLogTables* __restrict__ glt,
+__global__ void __launch_bounds__(BLOCK, PB_VERIFY_LOG_MINBLOCKS) verify_log_kernel(const __grid_constant__ VerifyKey key, const VerifyLogTables* __restrict__ glt,
                                                            const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                            const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
                                                            const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,

@@ -246,17 +246,21 @@ PB_HD void verify_one_fast(const VerifyKey& k, const VerifyTables& vt, const Fie
 // by the toy parameters, exactly like the prover's 17^6-entry commitment table; PB_VERIFY_TABLES=0 at context creation
 // keeps the Straus + Miller-loop kernel above, and bench.py reports that configuration too.
 // Curve membership (step 1) is a look-up as well: (x, y) is on the curve iff it IS the point at its index in the list.
+constexpr uint32_t VLT_MOD17_RANGE = 512u;
 struct alignas(16) VerifyLogTables {
+  uint32_t pw[104];        // index -> the point as x | y << 8 | infinite << 16 ([0] = 0x10000); [102..103] = 0xFFFFFFFF (no point)
   uint8_t cbase[104];      // x -> index of the first point with abscissa x (wire.cuh: CurveIndexImage); [101] = 102
-  uint8_t px[104], py[104];  // index -> coordinates; [0] = (0, 0) for infinity, [102..103] = 0xFF (no point)
   uint8_t dlog[104];       // index -> k with point = k Q; dlog[0] = 0
   uint8_t L2[4][292];      // dlog of VerifyTables.P2[t][i]
   uint8_t Lneg[24];        // dlog of VerifyTables.one_neg[e]
   uint8_t inv17[32];       // hf_inverses (FieldTables.inv17): the only field table this path needs
   uint16_t gt_s[104];      // k -> pairing(k Q, g2_s) as a | b << 8
   uint16_t gt_1[104];      // k -> pairing(k Q, g2_one)
+  uint8_t mod17[VLT_MOD17_RANGE];   // x mod 17 for x < 512: every reduction of the scalar part but one is of a product of two residues
 };
 constexpr uint32_t GROUP_ORDER = 102u;
+PB_HD uint32_t vlt_px(const VerifyLogTables& lt, uint32_t i) { return lt.pw[i] & 0xFFu; }
+PB_HD uint32_t vlt_py(const VerifyLogTables& lt, uint32_t i) { return (lt.pw[i] >> 8) & 0xFFu; }
 
 // index of a canonical curve point in the list (curve_index of wire.cuh, restated here so that this header stands alone)
 PB_HD uint32_t vlt_index(const VerifyLogTables& lt, G1 p) {
@@ -267,19 +271,20 @@ PB_HD uint32_t vlt_index(const VerifyLogTables& lt, G1 p) {
 // point has order 102 (cannot happen on this curve; the caller then keeps the Straus kernel).
 PB_HD bool vlt_group(const FieldTables& ft, VerifyLogTables& lt, uint8_t (&alog)[104]) {
   uint32_t n = 1;
-  lt.px[0] = 0; lt.py[0] = 0;
+  lt.pw[0] = 1u << 16;
   for (uint32_t x = 0; x < 101u; x++) {
     lt.cbase[x] = (uint8_t)n;
     const uint32_t rhs = red101(red101(x * x) * x + 3u);
     for (uint32_t y = 0; y < 101u; y++)
-      if (red101(y * y) == rhs && n < 104u) { lt.px[n] = (uint8_t)x; lt.py[n] = (uint8_t)y; n++; }
+      if (red101(y * y) == rhs && n < 104u) { lt.pw[n] = x | y << 8; n++; }
   }
   if (n != GROUP_ORDER) return false;
   for (uint32_t k = 101; k < 104; k++) lt.cbase[k] = (uint8_t)n;
-  for (uint32_t k = n; k < 104; k++) { lt.px[k] = 0xFF; lt.py[k] = 0xFF; }
+  for (uint32_t k = n; k < 104; k++) lt.pw[k] = 0xFFFFFFFFu;
   for (uint32_t k = 0; k < 32; k++) lt.inv17[k] = ft.inv17[k];
+  for (uint32_t k = 0; k < VLT_MOD17_RANGE; k++) lt.mod17[k] = (uint8_t)(k % 17u);
   for (uint32_t cand = 1; cand < GROUP_ORDER; cand++) {
-    const G1 q{lt.px[cand], lt.py[cand], 0u};
+    const G1 q{vlt_px(lt, cand), vlt_py(lt, cand), 0u};
     G1 p = q;
     uint32_t ord = 1;
     while (!p.inf && ord <= GROUP_ORDER) { p = g1_add(ft, p, q); ord++; }     // the reference's addition, g1.h:42-83
@@ -301,7 +306,7 @@ constexpr uint32_t VLT_ENTRIES = GROUP_ORDER + 4u * 289u + 17u;
 PB_HD void vlt_entry(const FieldTables& ft, const VerifyKey& key, const VerifyTables& vt, const uint8_t (&alog)[104], VerifyLogTables& lt, uint32_t t) {
   if (t < GROUP_ORDER) {
     const uint32_t i = alog[t];
-    const G1 p{lt.px[i], lt.py[i], i == 0u ? 1u : 0u};
+    const G1 p{vlt_px(lt, i), vlt_py(lt, i), i == 0u ? 1u : 0u};
     const GT a = pairing17(ft, p, key.g2_s), b = pairing17(ft, p, key.g2_one);
     lt.gt_s[t] = (uint16_t)(a.a | a.b << 8);
     lt.gt_1[t] = (uint16_t)(b.a | b.b << 8);
@@ -320,51 +325,55 @@ PB_HD void verify_one_log(const VerifyLogTables& lt, const uint32_t (&pb)[27], c
                          uint32_t u, VerifyOut& out) {
   out.lhs = GT{0u, 0u};
   out.rhs = GT{0u, 0u};
-  // step 1: encodings and curve membership; lg[j] = discrete logarithm of commitment j
+  // step 1: encodings and curve membership; lg[j] = discrete logarithm of commitment j.  With w = x | y << 8 | f << 16 the
+  // four tests of verify_one (x, y <= 100; f <= 1; f == 1 => x = y = 0; on the curve) are ONE compare: w must BE the
+  // listed point at its own index (0 for f != 0, else first index of abscissa min(x, 100), + 1 for the larger root).
   bool bad_pt = false;
   uint32_t lg[9];
 #pragma unroll
   for (int j = 0; j < 9; j++) {
     const uint32_t x = pb[3 * j], y = pb[3 * j + 1], f = pb[3 * j + 2];
-    bad_pt |= x > 100u || y > 100u || f > 1u || (f == 1u && (x | y) != 0u);
-    uint32_t i = lt.cbase[x > 100u ? 0u : x] + (2u * y > 101u ? 1u : 0u);
+    uint32_t i = lt.cbase[x > 100u ? 100u : x] + (2u * y > 101u ? 1u : 0u);
     i = f != 0u ? 0u : i;
-    bad_pt |= f == 0u && (lt.px[i] != x || lt.py[i] != y);          // on the curve <=> it is the listed point
+    bad_pt |= lt.pw[i] != (x | y << 8 | f << 16);
     lg[j] = lt.dlog[i];
   }
-  bool bad_sc = u > 16u;
+  // openings, challenges, u are field elements: all <= 16  <=>  their maximum is
+  uint32_t top = u;
 #pragma unroll
-  for (int j = 0; j < 7; j++) bad_sc |= op[j] > 16u;
+  for (int j = 0; j < 7; j++) top = umax(top, op[j]);
 #pragma unroll
-  for (int j = 0; j < 5; j++) bad_sc |= ch[j] > 16u;
+  for (int j = 0; j < 5; j++) top = umax(top, ch[j]);
   if (bad_pt) { out.verdict = 2u; return; }
-  if (bad_sc) { out.verdict = 3u; return; }
+  if (top > 16u) { out.verdict = 3u; return; }
 
-  // steps 4-10: the scalars, exactly as in verify_one
+  // steps 4-10: the scalars, exactly as in verify_one; m() = mod 17 by look-up (arguments < 512, bounds at the sites)
+  auto m = [&](uint32_t x) -> uint32_t { PB_BOUND(x, VLT_MOD17_RANGE, "verifier mod17 index"); return lt.mod17[x]; };
   const uint32_t a_z = op[0], b_z = op[1], c_z = op[2], s1_z = op[3], s2_z = op[4], r_z = op[5], zw_z = op[6];
   const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
   constexpr uint32_t K1 = 2u, K2 = 3u, OMEGA = 4u;
-  const uint32_t z2 = red17(z * z), z3 = red17(z2 * z), z4 = red17(z2 * z2);
+  const uint32_t z2 = m(z * z), z3 = m(z2 * z), z4 = m(z2 * z2);                       // products of residues: <= 256
   const uint32_t zh_z = sub17(z4, 1u);
-  const uint32_t l1_z = red17(13u * (1u + z + z2 + z3));
-  const uint32_t alpha2 = red17(alpha * alpha);
-  const uint32_t pa = red17(a_z + beta * s1_z + gamma), pbb = red17(b_z + beta * s2_z + gamma);
-  const uint32_t pab = red17(pa * pbb);
-  const uint32_t perm = red17(red17(red17(pab * red17(c_z + gamma)) * zw_z) * alpha);
-  const uint32_t t_num = red17(r_z + 2u * P17 - perm - red17(l1_z * alpha2));
-  const uint32_t t_z = red17(t_num * lt.inv17[zh_z]);
-  const uint32_t bz = red17(beta * z);
-  const uint32_t ga = red17(a_z + bz + gamma), gb = red17(b_z + K1 * bz + gamma), gc = red17(c_z + K2 * bz + gamma);
-  const uint32_t d_z = red17(red17(red17(red17(red17(ga * gb) * gc) * alpha) * v) + red17(red17(l1_z * alpha2) * v) + u);
-  const uint32_t d_s3 = red17(red17(red17(red17(pab * alpha) * v) * beta) * zw_z);
-  const uint32_t v2 = red17(v * v), v3 = red17(v2 * v), v4 = red17(v3 * v), v5 = red17(v4 * v), v6 = red17(v5 * v);
-  const uint32_t z6 = red17(z4 * z2), z12 = red17(z6 * z6);
-  const uint32_t e = red17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);
-  const uint32_t uzw = red17(red17(u * z) * OMEGA);
+  const uint32_t l1_z = m(13u * m(1u + z + z2 + z3));                                  // <= 49, then <= 208
+  const uint32_t alpha2 = m(alpha * alpha);
+  const uint32_t pa = m(a_z + beta * s1_z + gamma), pbb = m(b_z + beta * s2_z + gamma); // <= 288
+  const uint32_t pab = m(pa * pbb);
+  const uint32_t perm = m(m(m(pab * m(c_z + gamma)) * zw_z) * alpha);
+  const uint32_t l1a2 = m(l1_z * alpha2);
+  const uint32_t t_num = m(r_z + 2u * P17 - perm - l1a2);                               // <= 50
+  const uint32_t t_z = m(t_num * lt.inv17[zh_z]);
+  const uint32_t bz = m(beta * z);
+  const uint32_t ga = m(a_z + bz + gamma), gb = m(b_z + K1 * bz + gamma), gc = m(c_z + K2 * bz + gamma);   // <= 80
+  const uint32_t d_z = m(m(m(m(m(ga * gb) * gc) * alpha) * v) + m(l1a2 * v) + u);      // <= 48
+  const uint32_t d_s3 = m(m(m(m(pab * alpha) * v) * beta) * zw_z);
+  const uint32_t v2 = m(v * v), v3 = m(v2 * v), v4 = m(v3 * v), v5 = m(v4 * v), v6 = m(v5 * v);
+  const uint32_t z6 = m(z4 * z2), z12 = m(z6 * z6);
+  const uint32_t e = red17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);   // <= 1808: Barrett
+  const uint32_t uzw = m(m(u * z) * OMEGA);
 
   // step 11 in the exponent: [D] + [F] - [E] + z [W_z] + u z omega [W_zw] on the right, [W_z] + u [W_zw] on the left.
   // k_r <= 5 * 101 + 101 + 8 * 16 * 101 < 2^14; floor(k / 102) = (k * 41121) >> 22 is exact below 110 376
-  uint32_t k_r = (uint32_t)lt.L2[0][red17(red17(a_z * b_z) * v) * 17u + red17(a_z * v)] + lt.L2[1][red17(b_z * v) * 17u + red17(c_z * v)] +
+  uint32_t k_r = (uint32_t)lt.L2[0][m(m(a_z * b_z) * v) * 17u + m(a_z * v)] + lt.L2[1][m(b_z * v) * 17u + m(c_z * v)] +
                  lt.L2[2][v * 17u + d_s3] + lt.L2[3][v5 * 17u + v6] + lt.Lneg[e] + lg[4] +
                  z * lg[7] + uzw * lg[8] + z6 * lg[5] + z12 * lg[6] + v2 * lg[0] + v3 * lg[1] + v4 * lg[2] + d_z * lg[3];
   k_r -= GROUP_ORDER * ((k_r * 41121u) >> 22);

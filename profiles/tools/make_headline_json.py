@@ -6,7 +6,8 @@ import sys
 
 cold, warm = json.load(open(sys.argv[1])), json.load(open(sys.argv[2]))
 out = {"_source": sys.argv[3]}
-for key, frag in (("prove_kernel", "prove_kernel"), ("verify_kernel", "verify_fast_kernel")):
+for key, frags in (("prove_kernel", ("prove_kernel",)), ("verify_kernel", ("verify_log_kernel", "verify_fast_kernel"))):
+    frag = next(f for f in frags if any(f in r["kernel"] for r in cold))     # the table-path verifier when the capture has it
     c = next(r for r in cold if frag in r["kernel"])
     w = next(r for r in warm if frag in r["kernel"])
     out[key] = {

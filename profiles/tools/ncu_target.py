@@ -25,18 +25,19 @@ if what in ("headline", "headline_pair", "headline_packed"):
     import os
     if what == "headline_pair":
         os.environ["PB_WIDE_TABLES"] = "0"
+        os.environ["PB_VERIFY_TABLES"] = "0"       # the configuration without context-sized tables: pair-table prover, Straus verifier
     n = 1 << 21
     pk = host.Plonk(W.PLONK_TEST_CIRCUIT, *W.generator_srs(9))
     sets = []
     for b in range(3):      # three different batches, as the bench rotates its buffer sets
         batch = W.make_batch(2025 + b, 0, n, "U17")
-        sets.append([T(x) for x in batch] + [T(wire.pack_inputs(*batch))])
+        sets.append([T(x) for x in batch] + [T(wire.pack_inputs3(*batch))])
     proofs = torch.empty((n, 34), dtype=torch.uint8, device=dev)
     status = torch.empty(n, dtype=torch.uint8, device=dev)
     verdict = torch.empty(n, dtype=torch.uint8, device=dev)
     for wit, rnd, chal, u, packed in sets:
         if what == "headline_packed":
-            pk.prove_verify_packed_dev(packed)
+            pk.prove_verify_packed_dev(packed, v3=True)
         else:
             host._check(lib.pb_plonk_prove_verify_ex_dev(pk._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict), C.c_size_t(n), sp, None))
     torch.cuda.synchronize()

@@ -295,7 +295,7 @@ uint64_t hc_check_discrete_logs() {
   memset(&lt, 0, sizeof lt);
   if (!vlt_group(ft, lt, alog)) return ~0ull;
   uint64_t bad = 0;
-  auto pt = [&](uint32_t i) { return G1{lt.px[i], lt.py[i], i == 0u ? 1u : 0u}; };
+  auto pt = [&](uint32_t i) { return G1{vlt_px(lt, i), vlt_py(lt, i), i == 0u ? 1u : 0u}; };
   auto same = [&](G1 r, uint32_t k) { const uint32_t i = alog[k % GROUP_ORDER]; const G1 w = pt(i); return r.x == w.x && r.y == w.y && r.inf == w.inf; };
   for (uint32_t i = 0; i < GROUP_ORDER; i++) {
     bad += alog[lt.dlog[i]] != i;
@@ -312,7 +312,7 @@ uint64_t hc_check_discrete_logs() {
     for (uint32_t y = 0; y < 101; y++) {
       const bool on = g1_is_on_curve(G1{x, y, 0u});
       const uint32_t i = lt.cbase[x] + (2u * y > 101u ? 1u : 0u);
-      bad += on != (lt.px[i] == x && lt.py[i] == y);
+      bad += on != (lt.pw[i] == (x | y << 8));
     }
   return bad;
 }
