@@ -897,7 +897,7 @@ def run_config(args):
         line = {"metric": "plonk_prove_verify_fs_proofs_per_s", "unit": "proofs/s", "value": n / (ms * 1e-3), "config": {
             "workload": "BASELINE config 5 in Fiat-Shamir mode (challenges drawn from the transcript in the kernels): 2^21 items, "
                         "generator SRS n=9, U17 blinding"},
-            "kernel_ms": {"prove_kernel<FS>": k_prove, "verify_fast_kernel(fs)": k_verify, "both": ms},
+            "kernel_ms": {"prove_kernel<FS>": k_prove, "verify_kernel(fs)": k_verify, "both": ms},
             "matches_oracle_on_sample": ok,
             "roofline": {"bound": "int32", "kernel": "prove_kernel<FS>", "unit": "TIOP/s", "achieved": None, "traffic": None,
                          "note": "same arithmetic as the explicit-challenge prover plus ~17 hash mixes; see the default workload for the roofline"},
