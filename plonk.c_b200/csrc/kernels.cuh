@@ -1178,11 +1178,20 @@ __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLO
   __shared__ __align__(8) uint64_t mbar;
   if (tid == 0) mbar_init(&mbar, 1);
   __syncthreads();
+  // status mode, full block: the block's 128 records (and challenge rows) are ONE contiguous 4352-byte (640-byte) slice -- it
+  // arrives by bulk copy with the tables, and the compacted lanes read their records from shared memory: 34 wavefronts of
+  // the load path per block where 17 strided two-byte loads per lane cost ~160 per warp
+  const bool bulk_rec = status != nullptr && done_list == nullptr && first + VLBLOCK <= n;
   if (tid == 0) {
-    mbar_arrive_expect_tx(&mbar, (uint32_t)sizeof(VerifyLogTables));
+    mbar_arrive_expect_tx(&mbar, (uint32_t)sizeof(VerifyLogTables) + (bulk_rec ? (uint32_t)VLBLOCK * (34u + (chal ? 5u : 0u)) : 0u));
     bulk_load(&sm.lt, glt, (uint32_t)sizeof(VerifyLogTables), &mbar);
+    if (bulk_rec) {
+      bulk_load(sm.proof, proofs + first * 34, VLBLOCK * 34, &mbar);
+      if (chal) bulk_load(sm.chal, chal + first * 5, VLBLOCK * 5, &mbar);
+    }
   }
 #else
+  constexpr bool bulk_rec = false;
   for (int k = tid; k < (int)(sizeof(VerifyLogTables) / 4); k += VLBLOCK)
     reinterpret_cast<uint32_t*>(&sm.lt)[k] = reinterpret_cast<const uint32_t*>(glt)[k];
 #endif
@@ -1211,6 +1220,25 @@ __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLO
     compacted = (uint32_t)tid < cnt;
     if (compacted) item = first + lane_of[tid];
   }
+  if (bulk_rec) {
+    if (!compacted) return;
+#if PB_BULK
+    mbar_wait(&mbar, 0);                                                  // tables and the block's records landed
+#endif
+    const uint32_t src = (uint32_t)(item - first);
+    const uint16_t* pr = reinterpret_cast<const uint16_t*>(sm.proof + src * 34u);
+    uint32_t b[34];
+#pragma unroll
+    for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+#pragma unroll
+    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
+    if (chal) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = sm.chal[src * 5u + k];
+    }
+  } else
   if (done_list || by_status) {
 #if !PB_BULK
     __syncthreads();
