@@ -1351,8 +1351,9 @@ static int launch_gather(const uint8_t* proofs, const uint8_t* status, const uin
   return PB_OK;
 }
 
-// host-pointer versions: a three-stage pipeline over chunks, one stream per hardware engine -- s_in (H2D copy engine),
-// s_k (SMs), s_out (D2H copy engine) -- tied together by events, over a ring of PIPE_SLOTS buffer sets:
+// host-pointer versions: a three-stage pipeline over chunks, one stream per copy engine and two for the SMs -- s_in (H2D copy
+// engine), s_k / s_k2 (SMs, chunks alternating), s_out (D2H copy engine) -- tied together by events, over a ring of PIPE_SLOTS
+// buffer sets:
 //   H2D(c) waits for kernels(c - SLOTS) (input buffers free);  kernels(c) wait for H2D(c) and D2H(c - SLOTS) (output buffers free);
 //   D2H(c) waits for kernels(c).
 // The input stage therefore never waits for the (slower) output stage, so once the inputs are up the D2H engine has the
