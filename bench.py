@@ -317,13 +317,13 @@ def run_b200(args):
         (wit, rnd, chal, u), (proofs, status, verdict) = sets[k % NBUF]
         if evs is not None:
             evs[0].record(stream)
-        # ONE public call: prover launch, (event), verifier launch over the dense list of completed proofs
+        # ONE public call: prover launch, (event), verifier launch; the batch's counters come out of the verifier's epilogue
+        # (table path) or of a third launch (pb_tally_dev) where the context has no table-path verifier
         mid = C.c_void_p(evs[1].cuda_event) if evs is not None else None
-        host._check(lib.pb_plonk_prove_verify_ex_dev(pk._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict),
-                                                     C.c_size_t(n), sp, mid))
+        host._check(lib.pb_plonk_prove_verify_tally_dev(pk._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict), P(counts),
+                                                        C.c_size_t(n), sp, mid))
         if evs is not None:
             evs[2].record(stream)
-        host._check(lib.pb_tally_dev(P(proofs), P(status), P(verdict), C.c_size_t(n), P(counts), sp))
 
     def barrier():
         if dist is not None:
@@ -407,9 +407,8 @@ def run_b200(args):
 
         def step_alt(k):
             (wit, rnd, chal, u), (proofs, status, verdict) = sets[k % NBUF]
-            host._check(lib.pb_plonk_prove_verify_ex_dev(pk_alt._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict),
-                                                         C.c_size_t(n), sp, None))
-            host._check(lib.pb_tally_dev(P(proofs), P(status), P(verdict), C.c_size_t(n), P(counts), sp))
+            host._check(lib.pb_plonk_prove_verify_tally_dev(pk_alt._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict), P(counts),
+                                                            C.c_size_t(n), sp, None))
         for k in range(3):
             step_alt(k)
         steps = min(args.steps, 20)
@@ -584,7 +583,7 @@ def run_b200(args):
                                       "memory (BASELINE north star (3)) and the verifier does the arithmetic; the headline keeps a 48 MB one-look-up "
                                       "table in L2 and the verifier's 2 KB of logarithm / pairing tables instead"},
         "completed_proofs_per_step": done_all,
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 2 * args.steps,      # prove + verify (which also produces the counters); 3 with PB_VERIFY_TABLES=0
         "roofline": roof,
         "clocks": sampler.summary(t0, t1) if sampler else None,
         "outcome": {"status_histogram": {str(i): int(c) for i, c in enumerate(gcounts[:16]) if c},

@@ -374,6 +374,12 @@ int pb_witness_from_values(const size_t *a_idx, const size_t *b_idx, const size_
 /* on-device tally: counts[0..15] += number of items per status byte (0..14, 15 = anything else),
  * counts[16] += verdict==1, counts[17] += a 64-bit sum of all proof bytes (checksum). counts: int64[18] device ptr */
 int pb_tally_dev(const uint8_t *proofs, const uint8_t *status, const uint8_t *verdict, size_t n, int64_t *counts, void *stream);
+/* prove, verify and count in one call: counts[18] += what pb_tally_dev would add for this batch's proofs / status / verdict.
+ * With the table-path verifier the counters come out of the verifier's epilogue (no third pass over the batch); otherwise
+ * this is pb_plonk_prove_verify_ex_dev followed by pb_tally_dev.  mid_event as in pb_plonk_prove_verify_ex_dev. */
+int pb_plonk_prove_verify_tally_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
+                                    const uint8_t *u, uint8_t *proofs, uint8_t *status, uint8_t *verdict, int64_t *counts,
+                                    size_t n, void *stream, void *mid_event);
 
 
 /* ---- roofline denominators measured on the device the caller is on (MEASURED_PEAKS.json

@@ -1212,13 +1212,14 @@ static int launch_prove(const pb_ctx* ctx, const uint8_t* witness, const uint8_t
 static bool table_verifier(const pb_ctx* ctx) { return ctx->key_canonical && !ctx->force_exact && ctx->d_verify_log != nullptr; }
 static int launch_verify(const pb_ctx* ctx, const uint8_t* proofs, const uint8_t* chal, const uint8_t* u, const uint8_t* status,
                          const uint32_t* done_list, const uint32_t* done_count, uint8_t* verdict, uint8_t* gt, size_t n, cudaStream_t st,
-                         const uint8_t* packed = nullptr, int wire3 = 0) {
+                         const uint8_t* packed = nullptr, int wire3 = 0, int64_t* counts = nullptr) {
   const uint32_t* pk = reinterpret_cast<const uint32_t*>(packed);
   const bool fast = ctx->key_canonical && !ctx->force_exact && !(status && !done_list);
   if (table_verifier(ctx)) {     // the dense list, every item, or (status without a list) each block compacting its own items
     const uint8_t* by_status = done_list ? nullptr : status;
-    if (gt) verify_log_kernel<true><<<blocks_for(n, VLBLOCK), VLBLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3, by_status);
-    else verify_log_kernel<false><<<blocks_for(n, VLBLOCK), VLBLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3, by_status);
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(by_status ? counts : nullptr);   // fused tally: status mode only
+    if (gt) verify_log_kernel<true><<<blocks_for(n, VLBLOCK), VLBLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3, by_status, cnt);
+    else verify_log_kernel<false><<<blocks_for(n, VLBLOCK), VLBLOCK, 0, st>>>(ctx->vk, ctx->d_verify_log, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3, by_status, cnt);
   } else if (fast)
     if (gt) verify_fast_kernel<true><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, gt, n, pk, wire3);
     else verify_fast_kernel<false><<<blocks_for(n, BLOCK), BLOCK, 0, st>>>(ctx->vk, ctx->d_verify_tables, proofs, chal, u, done_list, done_count, verdict, nullptr, n, pk, wire3);
@@ -1271,7 +1272,7 @@ int pb_plonk_prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const u
 // chal == u == nullptr: Fiat-Shamir mode; packed != nullptr: packed input records instead of witness / rnd / chal / u
 static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                             uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event,
-                            const uint8_t* packed = nullptr, int wire3 = 0) {
+                            const uint8_t* packed = nullptr, int wire3 = 0, int64_t* counts = nullptr) {
   ARG(verdict);
   ARG(ctx && ctx->vk_valid);
   { int rc_dev = on_ctx_device(ctx); if (rc_dev) return rc_dev; }
@@ -1287,7 +1288,7 @@ static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uin
     // no atomics in the prover (178.6 us against 184-186), no memset launch.
     int rcs = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, nullptr, nullptr, nullptr, nullptr, packed, wire3);
     if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
-    if (!rcs) rcs = launch_verify(ctx, proofs, chal, u, status, nullptr, nullptr, verdict, nullptr, n, st, packed, wire3);
+    if (!rcs) rcs = launch_verify(ctx, proofs, chal, u, status, nullptr, nullptr, verdict, nullptr, n, st, packed, wire3, counts);   // counters in the verifier's epilogue
     return rcs;
   }
   uint32_t* scratch = nullptr;
@@ -1297,7 +1298,14 @@ static int prove_verify_dev(const pb_ctx* ctx, const uint8_t* witness, const uin
   rc = launch_prove(ctx, witness, rnd, chal, proofs, status, n, st, scratch + 4, scratch, verdict, nullptr, packed, wire3);
   if (mid_event) cudaEventRecord(reinterpret_cast<cudaEvent_t>(mid_event), st);
   if (!rc) rc = launch_verify(ctx, proofs, chal, u, status, scratch + 4, scratch, verdict, nullptr, n, st, packed, wire3);
+  if (!rc && counts) rc = pb_tally_dev(proofs, status, verdict, n, counts, stream);      // no table path: the separate pass
   return rc;
+}
+int pb_plonk_prove_verify_tally_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
+                                    uint8_t* proofs, uint8_t* status, uint8_t* verdict, int64_t* counts, size_t n, void* stream, void* mid_event) {
+  if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
+  ARG(counts && chal && u);
+  return prove_verify_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, mid_event, nullptr, 0, counts);
 }
 int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
                                  uint8_t* proofs, uint8_t* status, uint8_t* verdict, size_t n, void* stream, void* mid_event) {
@@ -1773,8 +1781,7 @@ int pb_plonk_prove_verify_seeded_dev(const pb_ctx* ctx, uint64_t seed, uint64_t 
   uint8_t* status = proofs + cap * 34;
   uint8_t* verdict = status + cap;
   int rc = pb_synth_batch_dev(ctx, seed, start, n, variant, nullptr, nullptr, nullptr, nullptr, packed, stream);
-  if (!rc) rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed);
-  if (!rc) rc = pb_tally_dev(proofs, status, verdict, n, counts_dev, stream);
+  if (!rc) rc = prove_verify_dev(ctx, nullptr, nullptr, nullptr, nullptr, proofs, status, verdict, n, stream, nullptr, packed, 0, counts_dev);
   return rc;
 }
 int pb_plonk_prove_verify_seeded(const pb_ctx* cctx, uint64_t seed, uint64_t start, size_t count, int variant, int64_t counts[18]) {

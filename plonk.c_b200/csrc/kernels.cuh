@@ -1161,19 +1161,29 @@ struct __align__(16) VerifyLogSmem {
 #ifndef PB_VERIFY_LOG_MINBLOCKS
 #define PB_VERIFY_LOG_MINBLOCKS 8   // 60 registers; measured (us per 2^21 attempted items): no cap (91 registers) 55.2, 8: 46.9, 10: 47.2, 12: 51.3, 16: 62.2
 #endif
+// counts (optional, status mode only): the per-batch counters of pb_tally_dev -- status histogram, accepted proofs, byte sum
+// of the proofs -- fall out of what this kernel already holds ("an epilogue block-reduce that produces the
+// per-rank counters"): shared-memory atomics per lane, eighteen global atomics per block.
 template <bool WANT_GT>
 __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLOCK) verify_log_kernel(const __grid_constant__ VerifyKey key, const VerifyLogTables* __restrict__ glt,
                                                            const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ chal,
                                                            const uint8_t* __restrict__ u, const uint32_t* __restrict__ done_list,
                                                            const uint32_t* __restrict__ done_count, uint8_t* __restrict__ verdict,
                                                            uint8_t* __restrict__ gt, size_t n, const uint32_t* __restrict__ packed = nullptr, int wire3 = 0,
-                                                           const uint8_t* __restrict__ status = nullptr) {
+                                                           const uint8_t* __restrict__ status = nullptr, unsigned long long* __restrict__ counts = nullptr) {
   __shared__ VerifyLogSmem sm;
+  __shared__ unsigned int tally[18];
   const int tid = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * VLBLOCK;
   const size_t limit = done_list ? (size_t)*done_count : n;
   if (first >= limit) return;                                             // whole block beyond the dense list
   static_assert(sizeof(VerifyLogTables) % 16 == 0, "bulk copies move multiples of 16 bytes");
+  // status mode (status given, no list): the block compacts ITS OWN 128 items -- ranks of the completed ones by ballot and
+  // a four-entry scan, their lane numbers into a 128-byte table -- and lane r takes the r-th of them.  No list in global
+  // memory, no atomics in the prover; the lanes beyond the block's count idle (whole warps of them, mostly).
+  const bool by_status = status != nullptr && done_list == nullptr;
+  const bool tallying = counts != nullptr && by_status;
+  if (tid < 18) tally[tid] = 0u;
 #if PB_BULK
   __shared__ __align__(8) uint64_t mbar;
   if (tid == 0) mbar_init(&mbar, 1);
@@ -1181,7 +1191,7 @@ __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLO
   // status mode, full block: the block's 128 records (and challenge rows) are ONE contiguous 4352-byte (640-byte) slice -- it
   // arrives by bulk copy with the tables, and the compacted lanes read their records from shared memory: 34 wavefronts of
   // the load path per block where 17 strided two-byte loads per lane cost ~160 per warp
-  const bool bulk_rec = status != nullptr && done_list == nullptr && first + VLBLOCK <= n;
+  const bool bulk_rec = by_status && first + VLBLOCK <= n;
   if (tid == 0) {
     mbar_arrive_expect_tx(&mbar, (uint32_t)sizeof(VerifyLogTables) + (bulk_rec ? (uint32_t)VLBLOCK * (34u + (chal ? 5u : 0u)) : 0u));
     bulk_load(&sm.lt, glt, (uint32_t)sizeof(VerifyLogTables), &mbar);
@@ -1194,21 +1204,20 @@ __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLO
   constexpr bool bulk_rec = false;
   for (int k = tid; k < (int)(sizeof(VerifyLogTables) / 4); k += VLBLOCK)
     reinterpret_cast<uint32_t*>(&sm.lt)[k] = reinterpret_cast<const uint32_t*>(glt)[k];
+  __syncthreads();
 #endif
   size_t item = first + tid;
   const bool live = item < limit;
   const bool fs = chal == nullptr && packed == nullptr;   // Fiat-Shamir mode: the challenges and u come from the proof bytes (transcript.cuh)
-  uint32_t pbytes[27], op[7], ch[5];
-  // status mode (status given, no list): the block compacts ITS OWN 128 items -- ranks of the completed ones by ballot and
-  // a four-entry scan, their lane numbers into a 128-byte table -- and lane r takes the r-th of them.  No list in global
-  // memory, no atomics in the prover; the lanes beyond the block's count idle (whole warps of them, mostly).
-  const bool by_status = status != nullptr && done_list == nullptr;
-  bool compacted = false;
+  uint32_t b[34], ch[5];
+  bool active = live;
   if (by_status) {
     __shared__ uint8_t lane_of[VLBLOCK];
     __shared__ uint32_t wcnt[VLBLOCK / 32];
-    const bool done = live && status[item] == 0;
+    const uint32_t st = live ? status[item] : 1u;
+    const bool done = live && st == 0u;
     if (live && !done) verdict[item] = 0xFF;
+    if (tallying && live) atomicAdd(&tally[st < 15u ? st : 15u], 1u);
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, done);
     if ((tid & 31) == 0) wcnt[tid >> 5] = (uint32_t)__popc(bal);
     __syncthreads();
@@ -1217,82 +1226,89 @@ __global__ void __launch_bounds__(VLBLOCK, PB_VERIFY_LOG_MINBLOCKS * 128 / VLBLO
     for (int w = 0; w < VLBLOCK / 32; w++) { if (w < (tid >> 5)) rank += wcnt[w]; cnt += wcnt[w]; }
     if (done) lane_of[rank] = (uint8_t)tid;
     __syncthreads();
-    compacted = (uint32_t)tid < cnt;
-    if (compacted) item = first + lane_of[tid];
+    active = (uint32_t)tid < cnt;
+    if (active) item = first + lane_of[tid];
   }
   if (bulk_rec) {
-    if (!compacted) return;
+    if (active) {
 #if PB_BULK
-    mbar_wait(&mbar, 0);                                                  // tables and the block's records landed
+      mbar_wait(&mbar, 0);                                                // tables and the block's records landed
 #endif
-    const uint32_t src = (uint32_t)(item - first);
-    const uint16_t* pr = reinterpret_cast<const uint16_t*>(sm.proof + src * 34u);
-    uint32_t b[34];
+      const uint32_t src = (uint32_t)(item - first);
+      const uint16_t* pr = reinterpret_cast<const uint16_t*>(sm.proof + src * 34u);
 #pragma unroll
-    for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+      for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+      if (chal) {
 #pragma unroll
-    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
-#pragma unroll
-    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
-    if (chal) {
-#pragma unroll
-      for (int k = 0; k < 5; k++) ch[k] = sm.chal[src * 5u + k];
+        for (int k = 0; k < 5; k++) ch[k] = sm.chal[src * 5u + k];
+      }
     }
-  } else
-  if (done_list || by_status) {
-#if !PB_BULK
-    __syncthreads();
-#endif
-    if (by_status ? !compacted : !live) return;
-    if (done_list) item = done_list[item];
-    const uint16_t* pr = reinterpret_cast<const uint16_t*>(proofs + item * 34);
-    uint32_t b[34];
+  } else if (done_list || by_status) {
+    // dense-list mode (or the ragged last block of the status mode): the items of a block are scattered, so each lane reads
+    // its own 34-byte record straight into registers (17 two-byte loads: records are 2-byte aligned)
+    if (active) {
+      if (done_list) item = done_list[item];
+      const uint16_t* pr = reinterpret_cast<const uint16_t*>(proofs + item * 34);
 #pragma unroll
-    for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+      for (int k = 0; k < 17; k++) { const uint32_t w = pr[k]; b[2 * k] = w & 0xFFu; b[2 * k + 1] = w >> 8; }
+      if (chal) {
 #pragma unroll
-    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
-#pragma unroll
-    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
-    if (chal) {
-#pragma unroll
-      for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
-    }
+        for (int k = 0; k < 5; k++) ch[k] = chal[item * 5 + k];
+      }
 #if PB_BULK
-    mbar_wait(&mbar, 0);
+      mbar_wait(&mbar, 0);                                                // tables landed (the record loads above were in flight meanwhile)
 #endif
+    }
   } else {
     stage_in<34, VLBLOCK>(sm.proof, proofs, first, n);
     if (chal) stage_in<5, VLBLOCK>(sm.chal, chal, first, n);
     __syncthreads();
+    if (active) {
 #if PB_BULK
-    mbar_wait(&mbar, 0);
+      mbar_wait(&mbar, 0);
 #endif
-    if (!live) return;
 #pragma unroll
-    for (int k = 0; k < 27; k++) pbytes[k] = sm.proof[tid * 34 + k];
+      for (int k = 0; k < 34; k++) b[k] = sm.proof[tid * 34 + k];
+      if (chal) {
 #pragma unroll
-    for (int k = 0; k < 7; k++) op[k] = sm.proof[tid * 34 + 27 + k];
-    if (chal) {
-#pragma unroll
-      for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+        for (int k = 0; k < 5; k++) ch[k] = sm.chal[tid * 5 + k];
+      }
     }
   }
-  uint32_t uu;
-  if (fs) {
-    fs_derive(key.fs_seed, pbytes, op, ch, uu);
-  } else if (packed) {
-    uint32_t d[7];
-    unpack7(packed_tail_word(packed, item, wire3), d);   // a non-canonical word never gets here: the prover reports the item as bad input
+  if (active) {
+    uint32_t pbytes[27], op[7];
 #pragma unroll
-    for (int k = 0; k < 5; k++) ch[k] = d[k];
-    uu = d[5];
-  } else {
-    uu = u[item];
+    for (int k = 0; k < 27; k++) pbytes[k] = b[k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) op[k] = b[27 + k];
+    uint32_t uu;
+    if (fs) {
+      fs_derive(key.fs_seed, pbytes, op, ch, uu);
+    } else if (packed) {
+      uint32_t d[7];
+      unpack7(packed_tail_word(packed, item, wire3), d);   // a non-canonical word never gets here: the prover reports the item as bad input
+#pragma unroll
+      for (int k = 0; k < 5; k++) ch[k] = d[k];
+      uu = d[5];
+    } else {
+      uu = u[item];
+    }
+    VerifyOut o;
+    verify_one_log<WANT_GT>(sm.lt, pbytes, op, ch, uu, o);
+    verdict[item] = (uint8_t)o.verdict;
+    if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+    if (tallying) {
+      uint32_t bsum = 0u;
+#pragma unroll
+      for (int k = 0; k < 34; k++) bsum += b[k];
+      atomicAdd(&tally[17], bsum);                                        // <= 128 * 34 * 255 per block
+      if (o.verdict == 1u) atomicAdd(&tally[16], 1u);
+    }
   }
-  VerifyOut o;
-  verify_one_log<WANT_GT>(sm.lt, pbytes, op, ch, uu, o);
-  verdict[item] = (uint8_t)o.verdict;
-  if constexpr (WANT_GT) reinterpret_cast<uint32_t*>(gt)[item] = o.lhs.a | (o.lhs.b << 8) | (o.rhs.a << 16) | (o.rhs.b << 24);
+  if (tallying) {                                                          // uniform: every lane of the block gets here
+    __syncthreads();
+    if (tid < 18 && tally[tid] != 0u) atomicAdd(counts + tid, (unsigned long long)tally[tid]);
+  }
 }
 
 // VerifyLogTables at context creation: the sequential part by one thread, then one entry per thread.  ok[0] = 0 if the

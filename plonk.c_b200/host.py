@@ -504,6 +504,21 @@ class Plonk:
         c.run(self._h, c.inp(witness), c.inp(rnd), c.inp(chal), c.inp(u), pp, ps, pv, C.c_size_t(n))
         return proofs, status, verdict
 
+    def prove_verify_tally_dev(self, witness, rnd, chal, u, counts):
+        """Device path (torch CUDA tensors): prove, verify, and counts (torch int64[18], CUDA) += the batch's counters, in
+        one call -> (proofs, status, verdict)."""
+        import torch
+        n = _n(witness)
+        dev = witness.device
+        proofs = torch.empty((n, 34), dtype=torch.uint8, device=dev)
+        status = torch.empty(n, dtype=torch.uint8, device=dev)
+        verdict = torch.empty(n, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _check(lib().pb_plonk_prove_verify_tally_dev(
+                self._h, *(C.c_void_p(t.data_ptr()) for t in (witness, rnd, chal, u, proofs, status, verdict, counts)),
+                C.c_size_t(n), C.c_void_p(torch.cuda.current_stream().cuda_stream), None))
+        return proofs, status, verdict
+
     # ---- Fiat-Shamir mode (include/plonk_b200.h; specification oracle/fs_spec.inc)
     def fs_seed(self):
         """the transcript state after absorbing circuit and SRS, as one int: v0 | v1 << 32 | v2 << 64 | v3 << 96"""

@@ -480,6 +480,37 @@ def test_compact_and_packed_many_chunks(host, W):
     ps.eq("compact, second call", (dense3, s3, v3), (dense, s2, v2))
 
 
+def test_prove_verify_tally_fused(host, oracle, W):
+    """pb_plonk_prove_verify_tally_dev: outputs as pb_plonk_prove_verify_dev, counters as pb_tally_dev of those outputs --
+    with the table-path verifier (counters from its epilogue), with the arithmetic verifier and on the exact path (separate
+    pass), for a ragged size, twice into the same counters."""
+    import os
+    import torch
+    from plonk_c_b200 import shard
+    n = 70001
+    g1s, g2 = W.generator_srs(9)
+    wit, rnd, chal, u = W.make_batch(71, 5, n, "U17")
+    wit[17, 2] = 200                                     # a bad input byte: status 254 lands in the histogram's last bin
+    u[33] = 99                                           # a bad verifier scalar: verdict 3
+    d = [torch.from_numpy(x).cuda() for x in (wit, rnd, chal, u)]
+    for env in ({}, {"PB_VERIFY_TABLES": "0"}, {"PB_FORCE_EXACT": "1"}):
+        os.environ.update(env)
+        try:
+            pk = host.Plonk(W.PLONK_TEST_CIRCUIT, g1s, g2)
+            counts = torch.zeros(shard.N_COUNTERS, dtype=torch.int64, device="cuda")
+            p, s, v = pk.prove_verify_tally_dev(*d, counts)
+            p2, s2, v2 = pk.prove_verify(*d)
+            ps.eq(f"fused tally outputs {env}", tuple(t.cpu().numpy() for t in (p, s, v)), tuple(t.cpu().numpy() for t in (p2, s2, v2)))
+            want = shard.tally_host(p2.cpu().numpy(), s2.cpu().numpy(), v2.cpu().numpy())
+            ps.eq(f"fused tally counters {env}", counts.cpu().numpy(), want)
+            pk.prove_verify_tally_dev(*d, counts)
+            ps.eq(f"fused tally accumulates {env}", counts.cpu().numpy(), 2 * want)
+            assert int(s.cpu()[17]) == 254 and int(v.cpu()[17]) == 0xFF and (int(s.cpu()[33]) != 0 or int(v.cpu()[33]) == 3)
+        finally:
+            for key in env:
+                del os.environ[key]
+
+
 def test_packed_v3(host, oracle, W):
     """Packed wire v3 (14 B in, 12 B per completed proof: points as curve indices) against the oracle, host and device
     paths, in every table mode; bad records flagged; an SRS off the curve is refused."""
