@@ -35,11 +35,13 @@ if what in ("headline", "headline_pair", "headline_packed"):
     proofs = torch.empty((n, 34), dtype=torch.uint8, device=dev)
     status = torch.empty(n, dtype=torch.uint8, device=dev)
     verdict = torch.empty(n, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(18, dtype=torch.int64, device=dev)
     for wit, rnd, chal, u, packed in sets:
         if what == "headline_packed":
             pk.prove_verify_packed_dev(packed, v3=True)
         else:
-            host._check(lib.pb_plonk_prove_verify_ex_dev(pk._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict), C.c_size_t(n), sp, None))
+            # the bench step's call: prover launch, verifier launch (which also produces the batch's counters)
+            host._check(lib.pb_plonk_prove_verify_tally_dev(pk._h, P(wit), P(rnd), P(chal), P(u), P(proofs), P(status), P(verdict), P(counts), C.c_size_t(n), sp, None))
     torch.cuda.synchronize()
     print(f"{what}: 3 x (prove, verify) launches of {n} items; completed {(status == 0).sum().item()}")
 else:
