@@ -8,7 +8,10 @@ A "step" is one pass of the hot path over one batch of synthetic proofs: per ran
 BASELINE.json config 5's 2^24 proofs sharded over 8 GPUs; weak scaling) random satisfying witnesses of the
 plonk-test circuit with uniform blinding scalars and challenges (variant U17), generator SRS of size n = 9
 (SURVEY.md section 8(d)).  One step = plonk_prove over the batch, plonk_verify of every completed proof, and the
-on-device tally of statuses / verdicts / proof checksum.
+on-device tally of statuses / verdicts / proof checksum -- one call, pb_plonk_prove_verify_tally_dev: two launches (the
+counters come out of the verifier's epilogue), three where a context has no table-path verifier.
+value_arith_verifier / value_pair_tables: the same step on contexts created with PB_VERIFY_TABLES=0 (the verifier computes
+the group operations and Miller loops) and additionally PB_WIDE_TABLES=0 (no context-sized look-up table at all).
 
 value   proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
 e2e     proofs/s through a public host-pointer call, pinned host buffers in and out, H2D and D2H copies inside the
