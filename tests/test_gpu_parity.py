@@ -556,6 +556,22 @@ def test_packed_v3(host, oracle, W):
         bad.prove_verify_packed3(wire.pack_inputs3(*W.make_batch(1, 0, 256, "U17")))
 
 
+def test_pipeline_ring_reuse_with_small_chunks():
+    """The ring of buffer sets wraps only for batches of more than eight chunks (4 M proofs at the default chunk size).  The
+    chunk size is read once per process, so a child process runs the many-chunk comparisons with 2^15-item chunks: 65 chunks
+    over 8 slots, every host-pointer format against the struct path."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PB_PIPE_CHUNK="32768")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "many_chunks or pinned_matches_pageable or packed_v3", "-p", "no:cacheprovider"],
+                       env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_srs_eval_raw_and_satisfy_rows(host, oracle, W):
     """The context-free entry points behind the drop-in srs_eval_at_s / constraints_satisfy: one launch each, exactly the
     reference's loops -- including an untrimmed polynomial over a garbage SRS, where a trailing zero term changes the result."""
