@@ -29,7 +29,9 @@ Version 2 -- the packed wire format (csrc/wire.cuh; what pb_plonk_prove_verify_p
      proofs n_done x 22: nine u16 points x | y << 7 | infinite << 14, one u32 with the seven openings as base-17 digits;
      only completed proofs (status 0), in item order]                                   if flags & 4
 
-Packed wire v3 (14 B in, 12 B per completed proof; only for SRSs on the curve) is a wire-only format: see csrc/wire.cuh.
+Version 3 -- packed wire v3 (csrc/wire.cuh; what pb_plonk_prove_verify_packed3 moves): as version 2 with 14-byte input
+records and 12-byte proof records (commitments as 7-bit indices into the 102 points of the curve: only for SRSs on the
+curve; write_batch raises ValueError for a proof with a point off it).
 
 The numpy functions below are the formats' reference implementation; the C helpers pb_wire_* and the device functions
 of csrc/wire.cuh are checked against them (tests/test_wire.py).
@@ -231,7 +233,7 @@ def write_batch(path, circuit, srs_g1s, srs_g2, witness, rand, chal, u, proofs=N
     n = int(witness.shape[0])
     g1s = np.ascontiguousarray(srs_g1s, np.uint8)
     assert (proofs is None) == (status is None)
-    assert version in (1, 2)
+    assert version in (1, 2, 3)
     if version == 1:
         flags = (1 if proofs is not None else 0) | (2 if verdict is not None else 0)
     else:
@@ -254,13 +256,13 @@ def write_batch(path, circuit, srs_g1s, srs_g2, witness, rand, chal, u, proofs=N
             if verdict is not None:
                 f.write(np.ascontiguousarray(verdict, np.uint8).reshape(n).tobytes())
         else:
-            f.write(pack_inputs(witness, rand, chal, u).tobytes())
+            f.write((pack_inputs3 if version == 3 else pack_inputs)(witness, rand, chal, u).tobytes())
             if proofs is not None:
                 status = np.ascontiguousarray(status, np.uint8).reshape(n)
                 done = np.ascontiguousarray(proofs, np.uint8).reshape(n, 34)[status == 0]
                 f.write(struct.pack("<Q", int(done.shape[0])))
                 f.write(make_sv(status, np.ascontiguousarray(verdict, np.uint8).reshape(n)).tobytes())
-                f.write(pack_proofs(done).tobytes())
+                f.write((pack_proofs3 if version == 3 else pack_proofs)(done).tobytes())     # v3: ValueError for a point off the curve
 
 
 def read_batch(path, raw=False):
@@ -268,8 +270,8 @@ def read_batch(path, raw=False):
     struct arrays, plus "packed_inputs" / "packed_proofs" / "sv" exactly as stored when raw=True)."""
     with open(path, "rb") as f:
         magic, version, n, srs_len, flags = _HDR.unpack(f.read(_HDR.size))
-    if magic != MAGIC or version not in (1, 2):
-        raise ValueError(f"{path}: not a .pbatch v1/v2 file")
+    if magic != MAGIC or version not in (1, 2, 3):
+        raise ValueError(f"{path}: not a .pbatch v1/v2/v3 file")
     mm = np.memmap(path, dtype=np.uint8, mode="r", offset=_HDR.size)
     out, pos = {"n": n, "flags": flags, "version": version}, 0
 
@@ -288,14 +290,15 @@ def read_batch(path, raw=False):
         if flags & 2:
             take("verdict", (n,))
     else:
-        take("packed_inputs", (n, 16))
-        out["witness"], out["rand"], out["chal"], out["u"], out["valid"] = unpack_inputs(np.array(out["packed_inputs"]))
+        v3 = version == 3
+        take("packed_inputs", (n, 14 if v3 else 16))
+        out["witness"], out["rand"], out["chal"], out["u"], out["valid"] = (unpack_inputs3 if v3 else unpack_inputs)(np.array(out["packed_inputs"]))
         if flags & 4:
             take("n_done", (8,))
             out["n_done"] = int(np.array(out["n_done"]).view("<u8")[0])
-            take("sv", (n,)); take("packed_proofs", (out["n_done"], 22))
+            take("sv", (n,)); take("packed_proofs", (out["n_done"], 12 if v3 else 22))
             out["status"], out["verdict"] = split_sv(np.array(out["sv"]))
-            out["proofs"] = scatter_proofs(unpack_proofs(np.array(out["packed_proofs"])), out["status"])
+            out["proofs"] = scatter_proofs((unpack_proofs3 if v3 else unpack_proofs)(np.array(out["packed_proofs"])), out["status"])
         if not raw:
             for k in ("packed_inputs", "packed_proofs", "sv"):
                 out.pop(k, None)

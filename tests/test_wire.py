@@ -248,6 +248,37 @@ def test_pbatch_v2_round_trip(tmp_path, oracle, W):
     assert raw["packed_inputs"].shape == (n, 16) and raw["packed_proofs"].shape == (k, 22)
 
 
+def test_pbatch_v3_round_trip(tmp_path, oracle, W):
+    import util
+    n = 3001
+    g1s, g2 = W.generator_srs(9)
+    wit, rnd, chal, u = W.make_batch(9, 0, n)
+    proofs, status = oracle.plonk_prove_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal)
+    verdict, _ = oracle.plonk_verify_batch(W.PLONK_TEST_CIRCUIT, g1s, g2, proofs, chal, u)
+    verdict = np.where(status == 0, verdict, 0xFF).astype(np.uint8)
+    path = tmp_path / "batch3.pbatch"
+    wire.write_batch(path, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u, proofs, status, verdict, version=3)
+    k = int((status == 0).sum())
+    assert path.stat().st_size == 28 + 44 + 30 + 4 + n * 14 + 8 + n + k * 12
+    b = wire.read_batch(path)
+    assert b["version"] == 3 and b["n_done"] == k and b["valid"].all()
+    for key, v in dict(circuit=W.PLONK_TEST_CIRCUIT, srs_g1s=g1s, srs_g2=g2, witness=wit, rand=rnd, chal=chal, u=u,
+                       proofs=proofs, status=status, verdict=verdict).items():
+        assert np.array_equal(b[key], v), key
+    raw = wire.read_batch(path, raw=True)
+    assert raw["packed_inputs"].shape == (n, 14) and raw["packed_proofs"].shape == (k, 12)
+    # inputs only; and proofs over an SRS off the curve have no v3 encoding
+    wire.write_batch(path, W.PLONK_TEST_CIRCUIT, g1s, g2, wit, rnd, chal, u, version=3)
+    b = wire.read_batch(path)
+    assert b["flags"] == 0 and "proofs" not in b and np.array_equal(b["witness"], wit)
+    gs, g2g = util.garbage_srs()
+    gp, gst = oracle.plonk_prove_batch(W.PLONK_TEST_CIRCUIT, gs, g2g, wit[:500], rnd[:500], chal[:500])
+    if (gst == 0).any():
+        with pytest.raises(ValueError):
+            wire.write_batch(path, W.PLONK_TEST_CIRCUIT, gs, g2g, wit[:500], rnd[:500], chal[:500], u[:500], gp, gst,
+                             np.where(gst == 0, 0, 0xFF).astype(np.uint8), version=3)
+
+
 @pytest.mark.gpu
 def test_file_to_gpu_to_file(tmp_path, host, oracle, W):
     """A batch file is proved and verified on the GPU straight from its memory-mapped arrays; results equal the oracle's."""
