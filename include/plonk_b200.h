@@ -245,7 +245,11 @@ int pb_plonk_prove_dev(const pb_ctx *ctx, const uint8_t *witness, const uint8_t 
 int pb_plonk_prove(const pb_ctx *ctx, const uint8_t *witness, const uint8_t *rnd, const uint8_t *chal,
                    uint8_t *proofs, uint8_t *status, size_t n);
 /* plonk_verify (new; specification: oracle/verify_spec.inc): proofs[n][34], chal[n][5], u[n] ->
- * verdict[n]; gt (optional, may be NULL): [n][4] = lhs.a lhs.b rhs.a rhs.b of the final pairing check */
+ * verdict[n]; gt (optional, may be NULL): [n][4] = lhs.a lhs.b rhs.a rhs.b of the final pairing check.
+ * Three implementations with identical results, chosen per context: the specification's own sequence of group operations
+ * (any key); for a key of canonical curve points, fixed-base tables + one joint double-and-add + two Miller loops; and, by
+ * default for such a key, discrete logarithms mod 102 with two 102-entry pairing tables built at context creation with the
+ * first implementation's pairing (environment PB_VERIFY_TABLES=0 at pb_ctx_create keeps the second). */
 int pb_plonk_verify_dev(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
                         uint8_t *verdict, uint8_t *gt, size_t n, void *stream);
 int pb_plonk_verify(const pb_ctx *ctx, const uint8_t *proofs, const uint8_t *chal, const uint8_t *u,
