@@ -1305,6 +1305,7 @@ int pb_plonk_prove_verify_tally_dev(const pb_ctx* ctx, const uint8_t* witness, c
                                     uint8_t* proofs, uint8_t* status, uint8_t* verdict, int64_t* counts, size_t n, void* stream, void* mid_event) {
   if (n == 0) return PB_OK;   // an empty batch is valid and touches no pointer
   ARG(counts && chal && u);
+  ARG((reinterpret_cast<uintptr_t>(counts) & 7u) == 0);      // 64-bit atomics
   return prove_verify_dev(ctx, witness, rnd, chal, u, proofs, status, verdict, n, stream, mid_event, nullptr, 0, counts);
 }
 int pb_plonk_prove_verify_ex_dev(const pb_ctx* ctx, const uint8_t* witness, const uint8_t* rnd, const uint8_t* chal, const uint8_t* u,
